@@ -1,0 +1,213 @@
+/*
+ * posecodec.h -- C ABI of libposecodec.so, the sm_100a heatmap codec.
+ *
+ * This is the drop-in boundary for the heatmap-codec hot path of
+ * mindspore-lab/mindpose.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference tree).  The reference has no FFI of
+ * its own (it is pure Python); the binding a maintainer would add is the ctypes
+ * stub shown in INTEGRATION.md, and mindpose_b200/_lib.py is that stub.
+ *
+ * Conventions
+ *  - All pointers named d_* are DEVICE pointers (contiguous, dense, row-major);
+ *    pointers named h_* are HOST pointers.  The library never allocates, frees
+ *    or retains caller memory and never synchronises the stream it is given
+ *    (the *_host entry points are the exception: they own a context with
+ *    scratch buffers and return after the results are in the host buffers).
+ *  - Tensors: heatmaps float32 NCHW; images uint8 HWC; keypoints float32
+ *    [N, K, 3] = (x, y, visibility).
+ *  - Sizes follow the reference's config convention where noted ([w, h]).
+ *  - Return value: PC_OK (0) or a negative pc_status; pc_last_error() returns a
+ *    thread-local, human readable message for the last failure on this thread.
+ *    Argument errors map to Python ValueError (the reference raises ValueError
+ *    for bad configuration), CUDA failures to RuntimeError.
+ *  - Re-entrant: no global mutable state; one stream per call.
+ *  - stream is a cudaStream_t passed as void* (0 = legacy default stream).
+ */
+#ifndef POSECODEC_H_
+#define POSECODEC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_VERSION 100 /* 0.1.0 */
+
+typedef enum pc_status {
+  PC_OK = 0,
+  PC_ERR_INVALID_ARGUMENT = -1, /* -> ValueError */
+  PC_ERR_UNSUPPORTED = -2,      /* -> ValueError (shape/config outside the kernels' range) */
+  PC_ERR_CUDA = -3,             /* -> RuntimeError */
+  PC_ERR_NO_DEVICE = -4         /* -> RuntimeError: no sm_100 device / driver */
+} pc_status;
+
+#define PC_MAX_JOINTS 64
+#define PC_MAX_DARK_KERNEL 17 /* kernel_size <= 17 (sigma = 3 recipe) */
+#define PC_MAX_GROUPS 128     /* people per image the grouping kernel can hold */
+
+/* ---- library ----------------------------------------------------------- */
+
+int pc_version(void);
+const char* pc_last_error(void);
+/* Fills sm_count / compute capability of `device`; PC_ERR_NO_DEVICE if absent. */
+int pc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- A1: TopDownBoxToCenterScale._xywh2cs ------------------------------
+ * mindpose/data/transform/topdown_transform.py:131-154 (eval branch).
+ * d_boxes f32 [N,4] (x,y,w,h) -> d_center f32 [N,2], d_scale f32 [N,2]. */
+typedef struct pc_box_params {
+  int32_t image_w, image_h; /* dataset_setting.image_size = [w, h] */
+  float pixel_std;          /* 200 */
+  float scale_padding;      /* 1.25 */
+} pc_box_params;
+int pc_box_to_center_scale(const float* d_boxes, float* d_center, float* d_scale,
+                           const pc_box_params* params, int64_t n, void* stream);
+
+/* ---- A2/A3: get_affine_transform / get_warp_matrix ---------------------
+ * mindpose/data/transform/utils.py:44-98 and :158-190, as called from
+ * TopDownAffine._affine / _udp_affine (topdown_transform.py:203-261).
+ * d_center, d_scale f32 [N,2]; d_rot f32 [N] degrees (NULL = 0).
+ * d_fwd  f64 [N,6]: forward 2x3 matrix (source image -> crop), the matrix the
+ *        reference hands to cv2.warpAffine (UDP: its float32 value, widened).
+ * d_inv  f64 [N,6]: its inverse in cv::warpAffine's op order (crop -> source).
+ * Either output may be NULL. */
+typedef struct pc_affine_params {
+  int32_t image_w, image_h;
+  float pixel_std;
+  int32_t use_udp;
+} pc_affine_params;
+int pc_affine_matrices(const float* d_center, const float* d_scale, const float* d_rot,
+                       double* d_fwd, double* d_inv, const pc_affine_params* params,
+                       int64_t n, void* stream);
+/* Invert caller-supplied forward matrices (e.g. from cv2.getAffineTransform). */
+int pc_invert_affine(const double* d_fwd, double* d_inv, int64_t n, void* stream);
+
+/* ---- A4: cv2.warpAffine(image, M, (w,h), INTER_LINEAR) -----------------
+ * topdown_transform.py:217-222 / :248-253.  OpenCV-exact fixed-point bilinear,
+ * BORDER_CONSTANT 0, uint8, C channels interleaved (C in 1..4).
+ * Crop i reads the dense HWC image at d_src + d_src_offset[i] (bytes) of size
+ * d_src_hw[i] = (rows, cols); several crops may share one source image.
+ * d_inv f64 [N,6] from pc_affine_matrices / pc_invert_affine.
+ * d_dst u8 [N, dst_h, dst_w, C]. */
+typedef struct pc_warp_params {
+  int32_t dst_w, dst_h, channels;
+} pc_warp_params;
+int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offset,
+                      const int32_t* d_src_hw, const double* d_inv, uint8_t* d_dst,
+                      const pc_warp_params* params, int64_t n, void* stream);
+
+/* Keypoint half of TopDownAffine (topdown_transform.py:224-231 / :255-259):
+ * in place on d_keypoints f32 [N,K,3]; standard path moves joints with
+ * visibility > 0 only, UDP moves all joints (matrix taken as float32). */
+int pc_affine_joints(float* d_keypoints, const double* d_fwd, int32_t num_joints,
+                     int32_t use_udp, int64_t n, void* stream);
+
+/* ---- A5/A6: TopDownGenerateTarget._encoding / _udp_encoding ------------
+ * topdown_transform.py:324-375 / :377-430.
+ * d_keypoints f32 [N,K,3] (crop coordinates) ->
+ * d_target f32 [N,K,H,W], d_target_weight f32 [N,K]. */
+typedef struct pc_encode_params {
+  int32_t num_joints;
+  int32_t image_w, image_h;     /* image_size  = [w, h] */
+  int32_t heatmap_w, heatmap_h; /* heatmap_size = [w, h] */
+  float sigma;                  /* 3*sigma must be an integer <= 15 */
+  int32_t use_udp;
+  int32_t use_joint_weights;    /* use_different_joint_weights */
+  float joint_weights[PC_MAX_JOINTS];
+} pc_encode_params;
+int pc_topdown_encode(const float* d_keypoints, float* d_target, float* d_target_weight,
+                      const pc_encode_params* params, int64_t n, void* stream);
+
+/* ---- A8-A13: TopDownHeatMapDecoder.construct (+ flip-test averaging) ----
+ * mindpose/models/decoders/top_down_decoder.py:72-215 and the post-network
+ * half of _MultiRunNet.construct (engine/inferencer/topdown_inferencer.py:165-187).
+ * d_heatmap f32 [N,K,H,W]; d_flipped f32 [N,K,H,W] or NULL (required iff
+ * flip_test); d_center, d_scale f32 [N,2]; d_score f32 [N].
+ * -> d_all_preds f32 [N,K,3] (x, y, maxval), d_all_boxes f32 [N,6].
+ * One pass: each heatmap element is read from HBM exactly once. */
+typedef struct pc_topdown_decode_params {
+  int32_t num_joints, height, width;
+  float pixel_std;
+  int32_t to_original;
+  int32_t shift_coordinate;
+  int32_t use_udp;
+  int32_t dark_udp_refine;
+  int32_t kernel_size;
+  int32_t flip_test;     /* average with d_flipped (channel permute + reversed x) */
+  int32_t shift_heatmap; /* eval_setting.shift_heatmap */
+  int32_t flip_index[PC_MAX_JOINTS];
+  /* Optional explicit blur kernel (decoder.gaussian_kernel, row-major
+   * kernel_size^2 floats).  dark_kernel_set = 0: built as
+   * _create_gaussian_kernel does (top_down_decoder.py:207-215). */
+  int32_t dark_kernel_set;
+  float dark_kernel[PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL];
+} pc_topdown_decode_params;
+int pc_topdown_decode(const float* d_heatmap, const float* d_flipped, const float* d_center,
+                      const float* d_scale, const float* d_score, float* d_all_preds,
+                      float* d_all_boxes, const pc_topdown_decode_params* params, int64_t n,
+                      void* stream);
+
+/* ---- A14-A17: BottomUpHeatMapAEDecoder.construct ------------------------
+ * mindpose/models/decoders/bottom_up_decoder.py:67-203.
+ * num_stages = 2, with_ae_loss = [True, False], tag_per_joint = True (the
+ * HigherHRNet recipe): d_out0 f32 [N, 2K, H0, W0] (heat | tag),
+ * d_out1 f32 [N, K, H1, W1] with H1 = 2*H0, W1 = 2*W0;
+ * num_stages = 1: d_out0 f32 [N, 2K, H1, W1], d_out1 = NULL.
+ * d_mask u8 [N, Hm, Wm] (non-zero = valid).
+ * -> d_val_k f32 [N,K,M], d_tag_k f32 [N,K,M,1], d_ind_k f32 [N,K,M,2] (x, y).
+ * Optional (may be NULL): d_heatmap_raw f32 [N,K,H1,W1] (aggregated, masked,
+ * pre-NMS), d_tagging f32 [N,K,H1,W1,1]. */
+typedef struct pc_bottomup_decode_params {
+  int32_t num_joints;
+  int32_t num_stages;
+  int32_t h0, w0; /* stage-0 map size (ignored when num_stages == 1) */
+  int32_t h1, w1; /* output / highest-resolution map size */
+  int32_t mask_h, mask_w;
+  int32_t use_nms, nms_kernel;
+  int32_t max_num;          /* M <= 32 */
+  int32_t shift_coordinate; /* only 0 is supported (reference quirk A17) */
+} pc_bottomup_decode_params;
+int pc_bottomup_decode(const float* d_out0, const float* d_out1, const uint8_t* d_mask,
+                       float* d_val_k, float* d_tag_k, float* d_ind_k, float* d_heatmap_raw,
+                       float* d_tagging, const pc_bottomup_decode_params* params, int64_t n,
+                       void* stream);
+
+/* ---- A18/A19: match_by_tag + instance score + transform_keypoints -------
+ * mindpose/utils/match.py:14-116, engine/inferencer/bottomup_inferencer.py:
+ * 153-156 and data/transform/utils.py:235-274.
+ * d_val_k [N,K,M], d_tag_k [N,K,M,1], d_ind_k [N,K,M,2] ->
+ * d_ans f32 [N, PC_MAX_GROUPS, K, 4] (x, y, val, tag; insertion order),
+ * d_num_groups i32 [N], d_scores f32 [N, PC_MAX_GROUPS].
+ * d_num_groups[i] = -1 flags an image whose group count exceeded PC_MAX_GROUPS. */
+typedef struct pc_group_params {
+  int32_t num_joints, max_num;
+  float vis_thr, tag_thr;
+  int32_t ignore_too_much, use_rounded_norm;
+  int32_t joint_order[PC_MAX_JOINTS];
+} pc_group_params;
+int pc_group_by_tag(const float* d_val_k, const float* d_tag_k, const float* d_ind_k,
+                    float* d_ans, int32_t* d_num_groups, float* d_scores,
+                    const pc_group_params* params, int64_t n, void* stream);
+/* Back-projection of grouped people, in place on d_ans (utils.py:235-274).
+ * d_center, d_scale f64 [N,2]; d_heatmap_wh f64 [N,2] (= image_shape / downsample_scale). */
+int pc_transform_keypoints(float* d_ans, const int32_t* d_num_groups, const double* d_center,
+                           const double* d_scale, const double* d_heatmap_wh, float pixel_std,
+                           int32_t num_joints, int64_t n, void* stream);
+
+/* ---- host-buffer front end (what the e2e number is measured through) ----
+ * Same decode as pc_topdown_decode but every pointer is a HOST pointer.  The
+ * context owns device scratch and two streams; crops are streamed through in
+ * chunks so the host->device copy of chunk i+1 overlaps the kernel of chunk i. */
+typedef struct pc_ctx pc_ctx;
+int pc_ctx_create(int device, int64_t scratch_bytes, pc_ctx** out);
+int pc_ctx_destroy(pc_ctx* ctx);
+int pc_topdown_decode_host(pc_ctx* ctx, const float* h_heatmap, const float* h_flipped,
+                           const float* h_center, const float* h_scale, const float* h_score,
+                           float* h_all_preds, float* h_all_boxes,
+                           const pc_topdown_decode_params* params, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSECODEC_H_ */

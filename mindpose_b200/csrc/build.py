@@ -1,0 +1,93 @@
+"""Build libposecodec.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m mindpose_b200.csrc.build [--force] [--verbose]
+
+The shared library lands next to the sources (mindpose_b200/csrc/libposecodec.so)
+so that it travels with the repo snapshot; it is git-ignored.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libposecodec.so")
+STAMP = os.path.join(HERE, "build", "stamp.txt")
+SOURCES = [
+    "lib.cu",
+    "topdown_decode.cu",
+    "topdown_encode.cu",
+    "warp_affine.cu",
+    "bottomup_decode.cu",
+    "grouping.cu",
+]
+HEADERS = ["common.cuh", os.path.join("..", "..", "include", "posecodec.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    # bit-exact parity with the reference's op order: no fused multiply-add
+    # contraction anywhere (the kernels are HBM-bound, not FMA-bound)
+    "--fmad=false",
+    "-Xcompiler", "-fPIC,-O2",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; libposecodec needs the CUDA 12.9 toolkit")
+    return exe
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    for rel in SOURCES + HEADERS + ["build.py"]:
+        with open(os.path.join(HERE, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    fp = _fingerprint()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+        with open(STAMP) as f:
+            if f.read().strip() == fp:
+                return LIB
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src} ==\n{out}")
+        failed |= p.returncode != 0
+    with open(os.path.join(HERE, "build", "nvcc.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose or failed:
+        print("\n".join(log))
+    if failed:
+        raise RuntimeError("nvcc failed; see mindpose_b200/csrc/build/nvcc.log")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
+            "-Xlinker", "--exclude-libs,ALL"]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout)
+        raise RuntimeError("link of libposecodec.so failed")
+    with open(STAMP, "w") as f:
+        f.write(fp)
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

@@ -1,0 +1,193 @@
+// lib.cu -- library plumbing of libposecodec: errors, device query, and the
+// host-buffer front end (pc_ctx / pc_topdown_decode_host).
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace pc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  cudaGetLastError();  // clear the sticky-less error state
+  return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? PC_ERR_NO_DEVICE
+                                                                    : PC_ERR_CUDA;
+}
+
+int sm_count_cached() {
+  // per-device cache; devices do not change while the process lives
+  static int counts[64];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (int& c : counts) c = 0;
+  });
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (counts[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    counts[dev] = v;
+  }
+  return counts[dev];
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+extern "C" int pc_version(void) { return PC_VERSION; }
+
+extern "C" const char* pc_last_error(void) { return g_err; }
+
+extern "C" int pc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  PC_REQUIRE(device >= 0 && device < count, PC_ERR_NO_DEVICE,
+             "pc_device_info: device %d not present (%d visible)", device, count);
+  int sms = 0, maj = 0, mnr = 0;
+  PC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  PC_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, device));
+  PC_CUDA(cudaDeviceGetAttribute(&mnr, cudaDevAttrComputeCapabilityMinor, device));
+  if (sm_count) *sm_count = sms;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = mnr;
+  return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Host-buffer front end.  Crops are cut into chunks; chunk c uses slot c % 2
+// (its own stream and device buffers), so the host->device copy of chunk c+1
+// runs while the kernel of chunk c is decoding.  Results are copied back on the
+// slot's stream; one synchronisation per stream at the end.
+// ---------------------------------------------------------------------------
+struct pc_ctx {
+  int device;
+  int64_t scratch_bytes;  // per slot, for heatmap (+ flipped) planes
+  cudaStream_t stream[2];
+  unsigned char* d_maps[2];
+  float* d_small[2];  // center | scale | score | preds | boxes per chunk
+  int64_t small_floats;
+};
+
+static const int64_t kMaxChunkCrops = 1 << 16;
+
+extern "C" int pc_ctx_create(int device, int64_t scratch_bytes, pc_ctx** out) {
+  PC_REQUIRE(out != nullptr, PC_ERR_INVALID_ARGUMENT, "pc_ctx_create: out is NULL");
+  *out = nullptr;
+  PC_REQUIRE(scratch_bytes >= (1 << 20), PC_ERR_INVALID_ARGUMENT,
+             "pc_ctx_create: scratch_bytes must be >= 1 MiB");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  PC_REQUIRE(device >= 0 && device < count, PC_ERR_NO_DEVICE,
+             "pc_ctx_create: device %d not present (%d visible)", device, count);
+  PC_CUDA(cudaSetDevice(device));
+  pc_ctx* c = new pc_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->scratch_bytes = scratch_bytes / 2;
+  // per crop: center 2 + scale 2 + score 1 + boxes 6, plus preds K*3 (K <= 64)
+  c->small_floats = kMaxChunkCrops * (11 + 3 * PC_MAX_JOINTS);
+  for (int s = 0; s < 2; ++s) {
+    cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking);
+    cudaError_t e2 = cudaMalloc((void**)&c->d_maps[s], (size_t)c->scratch_bytes);
+    cudaError_t e3 = cudaMalloc((void**)&c->d_small[s], sizeof(float) * c->small_floats);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+      cudaError_t bad = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+      pc_ctx_destroy(c);
+      return cuda_fail(bad, "pc_ctx_create allocation");
+    }
+  }
+  *out = c;
+  return PC_OK;
+}
+
+extern "C" int pc_ctx_destroy(pc_ctx* c) {
+  if (!c) return PC_OK;
+  cudaSetDevice(c->device);
+  for (int s = 0; s < 2; ++s) {
+    if (c->stream[s]) {
+      cudaStreamSynchronize(c->stream[s]);
+      cudaStreamDestroy(c->stream[s]);
+    }
+    if (c->d_maps[s]) cudaFree(c->d_maps[s]);
+    if (c->d_small[s]) cudaFree(c->d_small[s]);
+  }
+  delete c;
+  return PC_OK;
+}
+
+extern "C" int pc_topdown_decode_host(pc_ctx* c, const float* h_heatmap, const float* h_flipped,
+                                      const float* h_center, const float* h_scale,
+                                      const float* h_score, float* h_all_preds,
+                                      float* h_all_boxes, const pc_topdown_decode_params* p,
+                                      int64_t n) {
+  PC_REQUIRE(c != nullptr && p != nullptr, PC_ERR_INVALID_ARGUMENT,
+             "pc_topdown_decode_host: ctx / params is NULL");
+  PC_REQUIRE(n >= 0, PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode_host: n < 0");
+  PC_REQUIRE(p->num_joints >= 1 && p->num_joints <= PC_MAX_JOINTS && p->height >= 1 &&
+                 p->width >= 1,
+             PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode_host: bad num_joints / map size");
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(h_heatmap && h_center && h_scale && h_score && h_all_preds && h_all_boxes &&
+                 (!p->flip_test || h_flipped),
+             PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode_host: NULL host pointer");
+  PC_CUDA(cudaSetDevice(c->device));
+  const int K = p->num_joints;
+  const int64_t plane = (int64_t)K * p->height * p->width;  // floats per crop
+  const int64_t crop_bytes = plane * 4 * (p->flip_test ? 2 : 1);
+  int64_t chunk = c->scratch_bytes / crop_bytes;
+  if (chunk > kMaxChunkCrops) chunk = kMaxChunkCrops;
+  // at least ~4 chunks so copies and kernels overlap
+  if (chunk > (n + 3) / 4) chunk = (n + 3) / 4;
+  PC_REQUIRE(chunk >= 1, PC_ERR_UNSUPPORTED,
+             "pc_topdown_decode_host: one crop (%lld bytes) exceeds the context scratch",
+             (long long)crop_bytes);
+  int rc = PC_OK;
+  int slot = 0;
+  for (int64_t i0 = 0; i0 < n && rc == PC_OK; i0 += chunk, slot ^= 1) {
+    const int64_t m = (n - i0 < chunk) ? n - i0 : chunk;
+    cudaStream_t st = c->stream[slot];
+    float* d_hm = reinterpret_cast<float*>(c->d_maps[slot]);
+    float* d_fl = p->flip_test ? d_hm + m * plane : nullptr;
+    float* d_center = c->d_small[slot];
+    float* d_scale = d_center + 2 * m;
+    float* d_score = d_scale + 2 * m;
+    float* d_boxes = d_score + m;
+    float* d_preds = d_boxes + 6 * m;
+    PC_CUDA(cudaMemcpyAsync(d_hm, h_heatmap + i0 * plane, sizeof(float) * m * plane,
+                            cudaMemcpyHostToDevice, st));
+    if (p->flip_test)
+      PC_CUDA(cudaMemcpyAsync(d_fl, h_flipped + i0 * plane, sizeof(float) * m * plane,
+                              cudaMemcpyHostToDevice, st));
+    PC_CUDA(cudaMemcpyAsync(d_center, h_center + 2 * i0, sizeof(float) * 2 * m,
+                            cudaMemcpyHostToDevice, st));
+    PC_CUDA(cudaMemcpyAsync(d_scale, h_scale + 2 * i0, sizeof(float) * 2 * m,
+                            cudaMemcpyHostToDevice, st));
+    PC_CUDA(cudaMemcpyAsync(d_score, h_score + i0, sizeof(float) * m, cudaMemcpyHostToDevice,
+                            st));
+    rc = pc_topdown_decode(d_hm, d_fl, d_center, d_scale, d_score, d_preds, d_boxes, p, m, st);
+    if (rc != PC_OK) break;
+    PC_CUDA(cudaMemcpyAsync(h_all_preds + i0 * K * 3, d_preds, sizeof(float) * m * K * 3,
+                            cudaMemcpyDeviceToHost, st));
+    PC_CUDA(cudaMemcpyAsync(h_all_boxes + i0 * 6, d_boxes, sizeof(float) * m * 6,
+                            cudaMemcpyDeviceToHost, st));
+  }
+  cudaError_t e0 = cudaStreamSynchronize(c->stream[0]);
+  cudaError_t e1 = cudaStreamSynchronize(c->stream[1]);
+  if (rc != PC_OK) return rc;
+  if (e0 != cudaSuccess) return cuda_fail(e0, "cudaStreamSynchronize");
+  if (e1 != cudaSuccess) return cuda_fail(e1, "cudaStreamSynchronize");
+  return PC_OK;
+}

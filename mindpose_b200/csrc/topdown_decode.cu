@@ -1,0 +1,455 @@
+// topdown_decode.cu -- fused top-down heatmap decode for sm_100a.
+//
+// Replaces TopDownHeatMapDecoder.construct
+// (mindpose/models/decoders/top_down_decoder.py:72-215) and the post-network
+// half of the flip test (_MultiRunNet.construct,
+// mindpose/engine/inferencer/topdown_inferencer.py:165-187).
+//
+// One persistent CTA per SM.  A work item is one joint map (n, k): its H*W
+// float32 plane (and, for the flip test, the plane flipped[n, flip_index[k]])
+// is contiguous in HBM, so a single elected producer thread moves it into a
+// shared-memory stage with one or two 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier complete_tx).  Seven consumer warps each own one stage at a time:
+// flip-average on the fly, warp-shuffle argmax (value desc, flat index asc),
+// sub-pixel refinement (quarter offset or DARK/UDP Taylor step) out of the
+// staged planes, back-projection, 12-byte result.  Every heatmap byte crosses
+// HBM once; nothing but the results is written.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pc {
+
+constexpr int kDecodeThreads = 256;
+constexpr int kConsumerWarps = kDecodeThreads / 32 - 1;
+constexpr int kMaxStages = 12;
+constexpr int kDarkSamples = 7;
+
+struct DecodeArgs {
+  const float* heatmap;
+  const float* flipped;
+  const float* center;
+  const float* scale;
+  const float* score;
+  float* all_preds;
+  float* all_boxes;
+  int64_t num_items;  // n * K
+  int32_t K, H, W, HW;
+  FastDiv divW, divK;
+  float pixel_std;
+  int32_t to_original, use_udp;
+  int32_t mode;  // 0 none, 1 quarter offset, 2 DARK/UDP
+  int32_t ks;    // DARK kernel size
+  int32_t shift_heatmap;
+  int32_t stages;
+  uint32_t stage_floats;  // floats per stage (HW or 2*HW)
+  int32_t vec_ok;         // W % 4 == 0
+};
+
+struct DecodeTables {
+  int32_t flip_index[PC_MAX_JOINTS];
+  float dark_kernel[PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL];
+};
+
+// Value of the (flip-averaged) map at (y, x); planes are in shared memory.
+template <bool FLIP>
+__device__ __forceinline__ float map_at(const float* hm, const float* fm, int W, int y, int x,
+                                        int shift) {
+  float v = hm[y * W + x];
+  if (FLIP) {
+    int xs = shift ? (x == 0 ? W - 1 : W - x) : (W - 1 - x);
+    v = __fmul_rn(__fadd_rn(v, fm[y * W + xs]), 0.5f);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void take_max(float v, int i, float& bv, int& bi) {
+  if (v > bv) {
+    bv = v;
+    bi = i;
+  }
+}
+
+template <bool FLIP>
+__global__ void __launch_bounds__(kDecodeThreads, 1)
+    topdown_decode_kernel(const DecodeArgs a, const __grid_constant__ DecodeTables tab) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  const size_t stage_bytes_total = (size_t)a.stages * a.stage_floats * sizeof(float);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + stage_bytes_total);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  float* s_kernel = reinterpret_cast<float*>(empty_bar + kMaxStages);
+  float* s_rows = s_kernel + PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL;  // [warps][7][17]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = a.stages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (a.mode == 2) {
+    for (int i = threadIdx.x; i < a.ks * a.ks; i += blockDim.x) s_kernel[i] = tab.dark_kernel[i];
+  }
+  __syncthreads();
+
+  // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int64_t first = blockIdx.x;
+  const int64_t count =
+      first < a.num_items ? (a.num_items - first + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t plane_bytes = (uint32_t)a.HW * sizeof(float);
+
+  if (warp == 0) {
+    // ---------------- producer: one thread issues all bulk copies -----------
+    if (lane == 0) {
+      const uint64_t pol = l2_evict_first_policy();
+      for (int64_t j = 0; j < count; ++j) {
+        const int s = (int)(j % S);
+        const uint32_t round = (uint32_t)(j / S);
+        if (j >= S) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        const int64_t item = first + j * gridDim.x;
+        const int64_t n = item / a.K;
+        const int k = (int)(item - n * a.K);
+        float* dst = stage_base + (size_t)s * a.stage_floats;
+        mbar_arrive_expect_tx(&full_bar[s], FLIP ? 2 * plane_bytes : plane_bytes);
+        bulk_g2s(dst, a.heatmap + item * a.HW, plane_bytes, &full_bar[s], pol);
+        if (FLIP) {
+          const int kf = tab.flip_index[k];
+          bulk_g2s(dst + a.HW, a.flipped + (n * a.K + kf) * a.HW, plane_bytes, &full_bar[s],
+                   pol);
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------- consumers ---------------------------------------
+  const int cw = warp - 1;
+  const int W = a.W, H = a.H, HW = a.HW;
+  const int shift = a.shift_heatmap;
+  float* my_rows = s_rows + cw * (kDarkSamples * PC_MAX_DARK_KERNEL);
+
+  for (int64_t j = cw; j < count; j += kConsumerWarps) {
+    const int s = (int)(j % S);
+    const uint32_t round = (uint32_t)(j / S);
+    const int64_t item = first + j * gridDim.x;
+    const int64_t n = item / a.K;
+    const int k = (int)(item - n * a.K);
+
+    // crop geometry, fetched before the wait so its latency hides behind the TMA
+    float cx = 0.f, cy = 0.f, sw = 0.f, sh = 0.f, sc = 0.f;
+    if (lane == 0) {
+      cx = __ldg(a.center + 2 * n);
+      cy = __ldg(a.center + 2 * n + 1);
+      sw = __ldg(a.scale + 2 * n);
+      sh = __ldg(a.scale + 2 * n + 1);
+      if (k == 0) sc = __ldg(a.score + n);
+    }
+
+    mbar_wait(&full_bar[s], round & 1);
+    const float* hm = stage_base + (size_t)s * a.stage_floats;
+    const float* fm = hm + HW;
+
+    // ---- pass 1: (flip-averaged) argmax, lowest flat index among equals ----
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    if (a.vec_ok) {
+      const int nvec = HW >> 2;
+#pragma unroll 4
+      for (int q = lane; q < nvec; q += 32) {
+        const int idx = q << 2;
+        float4 v = reinterpret_cast<const float4*>(hm)[q];
+        if (FLIP) {
+          const int y = (int)fdiv((uint32_t)idx, a.divW);
+          const int x0 = idx - y * W;
+          const float* frow = fm + y * W;
+          const float4 f = *reinterpret_cast<const float4*>(frow + (W - 4 - x0));
+          float f0, f1, f2, f3;
+          if (shift) {
+            f0 = x0 == 0 ? f.w : frow[W - x0];
+            f1 = f.w;
+            f2 = f.z;
+            f3 = f.y;
+          } else {
+            f0 = f.w;
+            f1 = f.z;
+            f2 = f.y;
+            f3 = f.x;
+          }
+          v.x = __fmul_rn(__fadd_rn(v.x, f0), 0.5f);
+          v.y = __fmul_rn(__fadd_rn(v.y, f1), 0.5f);
+          v.z = __fmul_rn(__fadd_rn(v.z, f2), 0.5f);
+          v.w = __fmul_rn(__fadd_rn(v.w, f3), 0.5f);
+        }
+        take_max(v.x, idx, bv, bi);
+        take_max(v.y, idx + 1, bv, bi);
+        take_max(v.z, idx + 2, bv, bi);
+        take_max(v.w, idx + 3, bv, bi);
+      }
+    } else {
+      for (int idx = lane; idx < HW; idx += 32) {
+        const int y = (int)fdiv((uint32_t)idx, a.divW);
+        const int x = idx - y * W;
+        take_max(map_at<FLIP>(hm, fm, W, y, x, shift), idx, bv, bi);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (bi == 0x7fffffff) {  // no element compared greater than -inf: index 0, as numpy.argmax
+      bi = 0;
+      bv = map_at<FLIP>(hm, fm, W, 0, 0, shift);
+    }
+    const int py = (int)fdiv((uint32_t)bi, a.divW);
+    const int px = bi - py * W;
+
+    float rx = (float)px, ry = (float)py;
+
+    if (a.mode == 1) {
+      // ---- quarter offset (top_down_decoder.py:118-141): interior only ------
+      if (lane == 0) {
+        if (px >= 1 && px <= W - 2) {
+          const float d = __fsub_rn(map_at<FLIP>(hm, fm, W, py, px + 1, shift),
+                                    map_at<FLIP>(hm, fm, W, py, px - 1, shift));
+          rx = __fadd_rn(rx, d > 0.f ? 0.25f : (d < 0.f ? -0.25f : 0.f));
+        }
+        if (py >= 1 && py <= H - 2) {
+          const float d = __fsub_rn(map_at<FLIP>(hm, fm, W, py + 1, px, shift),
+                                    map_at<FLIP>(hm, fm, W, py - 1, px, shift));
+          ry = __fadd_rn(ry, d > 0.f ? 0.25f : (d < 0.f ? -0.25f : 0.f));
+        }
+      }
+    } else if (a.mode == 2) {
+      // ---- DARK / UDP Taylor step (top_down_decoder.py:171-205) -------------
+      // samples: 0:i  1:ix1  2:iy1  3:ix1y1  4:ix1_y1_  5:ix1_  6:iy1_
+      const int ks = a.ks, r = (ks - 1) >> 1;
+      const int ntask = kDarkSamples * ks;
+      for (int t = lane; t < ntask; t += 32) {
+        const int smp = t / ks, ky = t - smp * ks;
+        const int dxs = (smp == 1 || smp == 3) ? 1 : ((smp == 4 || smp == 5) ? -1 : 0);
+        const int dys = (smp == 2 || smp == 3) ? 1 : ((smp == 4 || smp == 6) ? -1 : 0);
+        const int sy = py + dys, sx = px + dxs;
+        float acc = 0.f;
+        const int yy = sy + ky - r;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W && yy >= 0 && yy < H) {
+          const float* wrow = s_kernel + ky * ks;
+          for (int kx = 0; kx < ks; ++kx) {
+            const int xx = sx + kx - r;
+            const float v = (xx >= 0 && xx < W) ? map_at<FLIP>(hm, fm, W, yy, xx, shift) : 0.f;
+            const float p = __fmul_rn(wrow[kx], v);
+            acc = kx == 0 ? p : __fadd_rn(acc, p);
+          }
+        }
+        my_rows[smp * PC_MAX_DARK_KERNEL + ky] = acc;
+      }
+      __syncwarp();
+      float lg = 0.f;
+      if (lane < kDarkSamples) {
+        const int smp = lane;
+        const int dxs = (smp == 1 || smp == 3) ? 1 : ((smp == 4 || smp == 5) ? -1 : 0);
+        const int dys = (smp == 2 || smp == 3) ? 1 : ((smp == 4 || smp == 6) ? -1 : 0);
+        const int sy = py + dys, sx = px + dxs;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+          float tot = my_rows[smp * PC_MAX_DARK_KERNEL];
+          for (int ky = 1; ky < ks; ++ky)
+            tot = __fadd_rn(tot, my_rows[smp * PC_MAX_DARK_KERNEL + ky]);
+          tot = fminf(fmaxf(tot, 0.001f), 50.f);
+          lg = (float)log((double)tot);  // correctly rounded float32 log
+        }  // else: the reference zero-pads the LOG map -> 0.0
+      }
+      __syncwarp();
+      const float i_ = __shfl_sync(0xffffffffu, lg, 0);
+      const float ix1 = __shfl_sync(0xffffffffu, lg, 1);
+      const float iy1 = __shfl_sync(0xffffffffu, lg, 2);
+      const float ix1y1 = __shfl_sync(0xffffffffu, lg, 3);
+      const float ix1_y1_ = __shfl_sync(0xffffffffu, lg, 4);
+      const float ix1_ = __shfl_sync(0xffffffffu, lg, 5);
+      const float iy1_ = __shfl_sync(0xffffffffu, lg, 6);
+      if (lane == 0) {
+        const float dx = __fmul_rn(0.5f, __fsub_rn(ix1, ix1_));
+        const float dy = __fmul_rn(0.5f, __fsub_rn(iy1, iy1_));
+        const float two_i = __fmul_rn(2.f, i_);
+        const float dxx = __fadd_rn(__fsub_rn(ix1, two_i), ix1_);
+        const float dyy = __fadd_rn(__fsub_rn(iy1, two_i), iy1_);
+        float t = __fsub_rn(ix1y1, ix1);
+        t = __fsub_rn(t, iy1);
+        t = __fadd_rn(t, i_);
+        t = __fadd_rn(t, i_);
+        t = __fsub_rn(t, ix1_);
+        t = __fsub_rn(t, iy1_);
+        t = __fadd_rn(t, ix1_y1_);
+        const float dxy = __fmul_rn(0.5f, t);
+        const float ha = __fadd_rn(dxx, 1e-7f), hd = __fadd_rn(dyy, 1e-7f), hb = dxy;
+        const float det = __fsub_rn(__fmul_rn(ha, hd), __fmul_rn(hb, hb));
+        const float i00 = __fdiv_rn(hd, det);
+        const float i01 = __fdiv_rn(-hb, det);
+        const float i11 = __fdiv_rn(ha, det);
+        const float ox = __fadd_rn(__fmul_rn(i00, dx), __fmul_rn(i01, dy));
+        const float oy = __fadd_rn(__fmul_rn(i01, dx), __fmul_rn(i11, dy));
+        rx = __fsub_rn(rx, ox);
+        ry = __fsub_rn(ry, oy);
+      }
+    }
+
+    // stage no longer needed: hand it back to the producer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+    if (lane == 0) {
+      const float s_w = __fmul_rn(sw, a.pixel_std);
+      const float s_h = __fmul_rn(sh, a.pixel_std);
+      if (a.to_original) {
+        const float den_x = a.use_udp ? (float)(W - 1) : (float)W;
+        const float den_y = a.use_udp ? (float)(H - 1) : (float)H;
+        const float kx = __fdiv_rn(s_w, den_x);
+        const float ky = __fdiv_rn(s_h, den_y);
+        rx = __fsub_rn(__fadd_rn(__fmul_rn(rx, kx), cx), __fmul_rn(s_w, 0.5f));
+        ry = __fsub_rn(__fadd_rn(__fmul_rn(ry, ky), cy), __fmul_rn(s_h, 0.5f));
+      }
+      float* o = a.all_preds + item * 3;
+      o[0] = rx;
+      o[1] = ry;
+      o[2] = bv;
+      if (k == 0) {
+        float* b = a.all_boxes + n * 6;
+        b[0] = cx;
+        b[1] = cy;
+        b[2] = sw;
+        b[3] = sh;
+        b[4] = __fmul_rn(s_w, s_h);
+        b[5] = sc;
+      }
+    }
+  }
+}
+
+// Blur kernel exactly as _create_gaussian_kernel builds it
+// (top_down_decoder.py:207-215): fp64 exp, fp64 normalisation, one rounding.
+static void build_dark_kernel(int ks, float* out) {
+  const double sigma = 0.3 * ((ks - 1) * 0.5 - 1) + 0.8;
+  const int r = (ks - 1) / 2;
+  double tmp[PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL];
+  double sum = 0.0;
+  for (int y = 0; y < ks; ++y)
+    for (int x = 0; x < ks; ++x) {
+      const double d2 = (double)((x - r) * (x - r) + (y - r) * (y - r));
+      tmp[y * ks + x] = exp(-d2 / (2 * sigma * sigma));
+    }
+  // numpy's float64 sum over the flattened array is pairwise; 289 terms of
+  // similar magnitude agree with a plain sum to well below float32 rounding.
+  for (int i = 0; i < ks * ks; ++i) sum += tmp[i];
+  for (int i = 0; i < ks * ks; ++i) out[i] = (float)(tmp[i] / sum);
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
+                                 const float* d_center, const float* d_scale,
+                                 const float* d_score, float* d_all_preds, float* d_all_boxes,
+                                 const pc_topdown_decode_params* p, int64_t n, void* stream) {
+  PC_REQUIRE(p != nullptr, PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode: params is NULL");
+  PC_REQUIRE(n >= 0, PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode: n = %lld < 0", (long long)n);
+  PC_REQUIRE(p->num_joints >= 1 && p->num_joints <= PC_MAX_JOINTS, PC_ERR_INVALID_ARGUMENT,
+             "pc_topdown_decode: num_joints %d outside [1, %d]", p->num_joints, PC_MAX_JOINTS);
+  PC_REQUIRE(p->height >= 1 && p->width >= 1, PC_ERR_INVALID_ARGUMENT,
+             "pc_topdown_decode: bad map size %dx%d", p->height, p->width);
+  PC_REQUIRE(!(p->dark_udp_refine && p->shift_coordinate), PC_ERR_INVALID_ARGUMENT,
+             "`udp_refine` and `shift_coordinate` cannot be `true` in the same time.");
+  if (p->dark_udp_refine)
+    PC_REQUIRE(p->kernel_size >= 1 && p->kernel_size <= PC_MAX_DARK_KERNEL &&
+                   (p->kernel_size & 1),
+               PC_ERR_UNSUPPORTED, "pc_topdown_decode: kernel_size %d must be odd and <= %d",
+               p->kernel_size, PC_MAX_DARK_KERNEL);
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(d_heatmap && d_center && d_scale && d_score && d_all_preds && d_all_boxes,
+             PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode: NULL tensor pointer");
+  PC_REQUIRE(!p->flip_test || d_flipped, PC_ERR_INVALID_ARGUMENT,
+             "pc_topdown_decode: flip_test needs the flipped heatmap");
+  const int64_t hw = (int64_t)p->height * p->width;
+  PC_REQUIRE(hw % 4 == 0 && ((uintptr_t)d_heatmap % 16 == 0) &&
+                 (!p->flip_test || (uintptr_t)d_flipped % 16 == 0),
+             PC_ERR_UNSUPPORTED,
+             "pc_topdown_decode: planes must be 16-byte aligned (H*W %% 4 == 0, base %% 16 == 0)");
+  PC_REQUIRE((uint64_t)hw * p->width < 0xffffffffull, PC_ERR_UNSUPPORTED,
+             "pc_topdown_decode: map %dx%d too large", p->height, p->width);
+
+  DecodeTables tab;
+  memset(&tab, 0, sizeof(tab));
+  for (int k = 0; k < p->num_joints; ++k) {
+    tab.flip_index[k] = p->flip_test ? p->flip_index[k] : k;
+    PC_REQUIRE(tab.flip_index[k] >= 0 && tab.flip_index[k] < p->num_joints,
+               PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode: flip_index[%d] = %d out of range", k,
+               tab.flip_index[k]);
+  }
+  if (p->dark_udp_refine) {
+    if (p->dark_kernel_set)
+      memcpy(tab.dark_kernel, p->dark_kernel, sizeof(float) * p->kernel_size * p->kernel_size);
+    else
+      build_dark_kernel(p->kernel_size, tab.dark_kernel);
+  }
+
+  DecodeArgs a;
+  a.heatmap = d_heatmap;
+  a.flipped = d_flipped;
+  a.center = d_center;
+  a.scale = d_scale;
+  a.score = d_score;
+  a.all_preds = d_all_preds;
+  a.all_boxes = d_all_boxes;
+  a.K = p->num_joints;
+  a.H = p->height;
+  a.W = p->width;
+  a.HW = (int32_t)hw;
+  a.num_items = n * a.K;
+  a.divW = make_fastdiv((uint32_t)a.W);
+  a.divK = make_fastdiv((uint32_t)a.K);
+  a.pixel_std = p->pixel_std;
+  a.to_original = p->to_original;
+  a.use_udp = p->use_udp;
+  a.mode = p->shift_coordinate ? 1 : (p->dark_udp_refine ? 2 : 0);
+  a.ks = p->kernel_size;
+  a.shift_heatmap = p->flip_test ? p->shift_heatmap : 0;
+  a.vec_ok = (a.W % 4 == 0);
+  a.stage_floats = (uint32_t)(p->flip_test ? 2 * hw : hw);
+
+  const size_t tail_bytes = 2 * kMaxStages * sizeof(uint64_t) +
+                            sizeof(float) * PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL +
+                            sizeof(float) * kConsumerWarps * kDarkSamples * PC_MAX_DARK_KERNEL;
+  const size_t smem_cap = 227 * 1024;
+  const size_t stage_bytes = (size_t)a.stage_floats * sizeof(float);
+  int stages = (int)((smem_cap - tail_bytes) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  PC_REQUIRE(stages >= 2, PC_ERR_UNSUPPORTED,
+             "pc_topdown_decode: a %dx%d plane%s does not fit two shared-memory stages",
+             p->height, p->width, p->flip_test ? " pair" : "");
+  a.stages = stages;
+  const size_t smem = stages * stage_bytes + tail_bytes;
+
+  const int sms = sm_count_cached();
+  PC_REQUIRE(sms > 0, PC_ERR_NO_DEVICE, "pc_topdown_decode: no CUDA device");
+  int64_t grid = a.num_items < sms ? a.num_items : sms;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->flip_test) {
+    PC_CUDA(cudaFuncSetAttribute(topdown_decode_kernel<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topdown_decode_kernel<true><<<(unsigned)grid, kDecodeThreads, smem, st>>>(a, tab);
+  } else {
+    PC_CUDA(cudaFuncSetAttribute(topdown_decode_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topdown_decode_kernel<false><<<(unsigned)grid, kDecodeThreads, smem, st>>>(a, tab);
+  }
+  PC_CUDA(cudaGetLastError());
+  return PC_OK;
+}

@@ -1,0 +1,376 @@
+// warp_affine.cu -- crop geometry and OpenCV-exact affine crop warp for sm_100a.
+//
+// Replaces, for batches of crops:
+//   TopDownBoxToCenterScale._xywh2cs   (data/transform/topdown_transform.py:131-154)
+//   get_affine_transform               (data/transform/utils.py:44-98)
+//   get_warp_matrix                    (data/transform/utils.py:158-190)
+//   cv2.warpAffine(..., INTER_LINEAR)  (topdown_transform.py:217-222 / :248-253)
+//   keypoint half of TopDownAffine     (topdown_transform.py:224-231 / :255-259)
+//
+// The warp reproduces OpenCV's integer pipeline (third-party, not under the
+// reference tree): fp64 inverse matrix, 10-bit fixed-point coordinates reduced
+// to 1/32 pixel, 15-bit bilinear weights, constant border 0.  With a = fx/32
+// and b = fy/32 the four float32 weight products are exact multiples of 2^-10,
+// so rint(w * 32768) = 32 * (32-fx or fx) * (32-fy or fy) and
+//   dst = (sum(w * p) + 16384) >> 15 = (sum((..)(..) * p) + 512) >> 10.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pc {
+
+// ---------------------------------------------------------------- A1 -------
+__global__ void box_to_center_scale_kernel(const float* __restrict__ boxes,
+                                           float* __restrict__ center,
+                                           float* __restrict__ scale, double aspect,
+                                           float pixel_std, float scale_padding, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = boxes[4 * i], y = boxes[4 * i + 1];
+  const float wf = boxes[4 * i + 2], hf = boxes[4 * i + 3];
+  // centre: float32 box values, x + w * 0.5 evaluated in float32
+  center[2 * i] = __fadd_rn(x, __fmul_rn(wf, 0.5f));
+  center[2 * i + 1] = __fadd_rn(y, __fmul_rn(hf, 0.5f));
+  // aspect fix-up: the float32 box value is compared against a float64 ratio;
+  // the adjusted side becomes float64, the untouched side stays float32, and
+  // each is divided by pixel_std in its own precision before the float32 store.
+  const double ah = __dmul_rn(aspect, (double)hf);
+  float sw, sh;
+  if ((double)wf > ah) {
+    sw = __fdiv_rn(wf, pixel_std);
+    sh = (float)__ddiv_rn(__ddiv_rn((double)wf, aspect), (double)pixel_std);
+  } else if ((double)wf < ah) {
+    sw = (float)__ddiv_rn(__dmul_rn((double)hf, aspect), (double)pixel_std);
+    sh = __fdiv_rn(hf, pixel_std);
+  } else {
+    sw = __fdiv_rn(wf, pixel_std);
+    sh = __fdiv_rn(hf, pixel_std);
+  }
+  scale[2 * i] = __fmul_rn(sw, scale_padding);
+  scale[2 * i + 1] = __fmul_rn(sh, scale_padding);
+}
+
+// ------------------------------------------------------------ A2 / A3 ------
+__device__ __forceinline__ void invert_affine_cv(const double* m, double* o) {
+  // cv::warpAffine's own inversion, op for op
+  double d = __dsub_rn(__dmul_rn(m[0], m[4]), __dmul_rn(m[1], m[3]));
+  d = d != 0.0 ? __ddiv_rn(1.0, d) : 0.0;
+  const double a11 = __dmul_rn(m[4], d), a22 = __dmul_rn(m[0], d);
+  const double i00 = a11;
+  const double i01 = __dmul_rn(m[1], -d);
+  const double i10 = __dmul_rn(m[3], -d);
+  const double i11 = a22;
+  const double b1 = __dsub_rn(__dmul_rn(-i00, m[2]), __dmul_rn(i01, m[5]));
+  const double b2 = __dsub_rn(__dmul_rn(-i10, m[2]), __dmul_rn(i11, m[5]));
+  o[0] = i00;
+  o[1] = i01;
+  o[2] = b1;
+  o[3] = i10;
+  o[4] = i11;
+  o[5] = b2;
+}
+
+// Exact-arithmetic-free 3-point affine solve (Cramer, fp64): M @ [s;1] = d.
+__device__ __forceinline__ void solve_three_points(const double s[3][2], const double d[3][2],
+                                                   double* m) {
+  const double x0 = s[0][0], y0 = s[0][1], x1 = s[1][0], y1 = s[1][1], x2 = s[2][0],
+               y2 = s[2][1];
+  const double det = x0 * (y1 - y2) - y0 * (x1 - x2) + (x1 * y2 - x2 * y1);
+  const double inv = 1.0 / det;
+  for (int r = 0; r < 2; ++r) {
+    const double u0 = d[0][r], u1 = d[1][r], u2 = d[2][r];
+    m[3 * r + 0] = (u0 * (y1 - y2) - y0 * (u1 - u2) + (u1 * y2 - u2 * y1)) * inv;
+    m[3 * r + 1] = (x0 * (u1 - u2) - u0 * (x1 - x2) + (x1 * u2 - x2 * u1)) * inv;
+    m[3 * r + 2] = (x0 * (y1 * u2 - y2 * u1) - y0 * (x1 * u2 - x2 * u1) +
+                    u0 * (x1 * y2 - x2 * y1)) * inv;
+  }
+}
+
+__global__ void affine_matrices_kernel(const float* __restrict__ center,
+                                       const float* __restrict__ scale,
+                                       const float* __restrict__ rot, double* __restrict__ fwd,
+                                       double* __restrict__ inv, int image_w, int image_h,
+                                       float pixel_std, int use_udp, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float cx = center[2 * i], cy = center[2 * i + 1];
+  const float sx = scale[2 * i], sy = scale[2 * i + 1];
+  const double r = rot ? (double)rot[i] : 0.0;
+  double m[6];
+  if (!use_udp) {
+    // get_affine_transform: points are STORED in float32 (utils.py:83-91)
+    const float sw = __fmul_rn(sx, pixel_std);  // scale_tmp[0], float32
+    const double rad = 3.141592653589793 * r / 180.0;
+    const double sn = sin(rad), cs = cos(rad);
+    const double pyv = (double)__fmul_rn(sw, -0.5f);
+    const double dirx = 0.0 * cs - pyv * sn;
+    const double diry = 0.0 * sn + pyv * cs;
+    float s[3][2], d[3][2];
+    // scale_tmp * shift with shift = (0, 0) adds +0.0 in float32: no effect
+    s[0][0] = cx;
+    s[0][1] = cy;
+    s[1][0] = (float)((double)cx + dirx);
+    s[1][1] = (float)((double)cy + diry);
+    s[2][0] = __fadd_rn(s[1][0], -__fsub_rn(s[0][1], s[1][1]));
+    s[2][1] = __fadd_rn(s[1][1], __fsub_rn(s[0][0], s[1][0]));
+    const double dw = (double)image_w, dh = (double)image_h;
+    d[0][0] = (float)(dw * 0.5);
+    d[0][1] = (float)(dh * 0.5);
+    d[1][0] = (float)(dw * 0.5 + 0.0);
+    d[1][1] = (float)(dh * 0.5 + dw * -0.5);
+    d[2][0] = __fadd_rn(d[1][0], -__fsub_rn(d[0][1], d[1][1]));
+    d[2][1] = __fadd_rn(d[1][1], __fsub_rn(d[0][0], d[1][0]));
+    double sd[3][2], dd[3][2];
+    for (int p = 0; p < 3; ++p)
+      for (int c = 0; c < 2; ++c) {
+        sd[p][c] = (double)s[p][c];
+        dd[p][c] = (double)d[p][c];
+      }
+    solve_three_points(sd, dd, m);
+  } else {
+    // get_warp_matrix(rot, center * 2, image_size - 1, scale * pixel_std), float32 result
+    const double theta = r * (3.141592653589793 / 180.0);
+    const double in_w = (double)__fmul_rn(cx, 2.0f), in_h = (double)__fmul_rn(cy, 2.0f);
+    const double tw = (double)__fmul_rn(sx, pixel_std), th = (double)__fmul_rn(sy, pixel_std);
+    const double kx = ((double)image_w - 1.0) / tw, ky = ((double)image_h - 1.0) / th;
+    const double sn = sin(theta), cs = cos(theta);
+    m[0] = (double)(float)(cs * kx);
+    m[1] = (double)(float)(-sn * kx);
+    m[2] = (double)(float)(kx * (__dadd_rn(__dadd_rn(-0.5 * in_w * cs, 0.5 * in_h * sn),
+                                          0.5 * tw)));
+    m[3] = (double)(float)(sn * ky);
+    m[4] = (double)(float)(cs * ky);
+    m[5] = (double)(float)(ky * (__dadd_rn(__dsub_rn(-0.5 * in_w * sn, 0.5 * in_h * cs),
+                                          0.5 * th)));
+  }
+  if (fwd)
+    for (int c = 0; c < 6; ++c) fwd[6 * i + c] = m[c];
+  if (inv) {
+    double o[6];
+    invert_affine_cv(m, o);
+    for (int c = 0; c < 6; ++c) inv[6 * i + c] = o[c];
+  }
+}
+
+__global__ void invert_affine_kernel(const double* __restrict__ fwd, double* __restrict__ inv,
+                                     int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m[6], o[6];
+  for (int c = 0; c < 6; ++c) m[c] = fwd[6 * i + c];
+  invert_affine_cv(m, o);
+  for (int c = 0; c < 6; ++c) inv[6 * i + c] = o[c];
+}
+
+// keypoints through the forward matrix
+__global__ void affine_joints_kernel(float* __restrict__ kps, const double* __restrict__ fwd,
+                                     int K, int use_udp, int64_t total) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int64_t i = t / K;
+  float* kp = kps + t * 3;
+  const double* m = fwd + 6 * i;
+  const float x = kp[0], y = kp[1];
+  if (!use_udp) {
+    // np.array(M) @ [x, y, 1.0] in float64, only when visibility > 0
+    if (!(kp[2] > 0.f)) return;
+    const double xd = (double)x, yd = (double)y;
+    kp[0] = (float)__dadd_rn(__dadd_rn(__dmul_rn(m[0], xd), __dmul_rn(m[1], yd)), m[2]);
+    kp[1] = (float)__dadd_rn(__dadd_rn(__dmul_rn(m[3], xd), __dmul_rn(m[4], yd)), m[5]);
+  } else {
+    // np.dot([x, y, 1] float32, M.T float32): float32 products, float32 sums
+    const float m0 = (float)m[0], m1 = (float)m[1], m2 = (float)m[2];
+    const float m3 = (float)m[3], m4 = (float)m[4], m5 = (float)m[5];
+    kp[0] = __fadd_rn(__fadd_rn(__fmul_rn(x, m0), __fmul_rn(y, m1)), m2);
+    kp[1] = __fadd_rn(__fadd_rn(__fmul_rn(x, m3), __fmul_rn(y, m4)), m5);
+  }
+}
+
+// ---------------------------------------------------------------- A4 -------
+constexpr int kWarpThreads = 256;
+constexpr int kWarpTileRows = 8;
+constexpr int kWarpMaxDstW = 1024;
+
+template <int C>
+__global__ void __launch_bounds__(kWarpThreads)
+    warp_affine_u8_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
+                          const int32_t* __restrict__ src_hw, const double* __restrict__ inv,
+                          uint8_t* __restrict__ dst, int dst_w, int dst_h, int tiles_per_crop,
+                          FastDiv div_w) {
+  __shared__ int s_adelta[kWarpMaxDstW];
+  __shared__ int s_bdelta[kWarpMaxDstW];
+  __shared__ int s_x0[kWarpTileRows];
+  __shared__ int s_y0[kWarpTileRows];
+  extern __shared__ __align__(16) uint8_t s_out[];  // [rows][dst_w * C]
+
+  const int64_t crop = blockIdx.x / tiles_per_crop;
+  const int tile = blockIdx.x - (int)(crop * tiles_per_crop);
+  const int row0 = tile * kWarpTileRows;
+  const int rows = min(kWarpTileRows, dst_h - row0);
+  const double* m = inv + 6 * crop;
+  const double m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5];
+
+  for (int x = threadIdx.x; x < dst_w; x += blockDim.x) {
+    // saturate_cast<int>(M * x * AB_SCALE): round half to even, saturating
+    s_adelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m00, (double)x), 1024.0));
+    s_bdelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m10, (double)x), 1024.0));
+  }
+  if (threadIdx.x < rows) {
+    const double y = (double)(row0 + threadIdx.x);
+    s_x0[threadIdx.x] =
+        __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m01, y), m02), 1024.0)) + 16;
+    s_y0[threadIdx.x] =
+        __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m11, y), m12), 1024.0)) + 16;
+  }
+  __syncthreads();
+
+  const int hs = src_hw[2 * crop], ws = src_hw[2 * crop + 1];
+  const uint8_t* img = src + src_off[crop];
+  const int npix = rows * dst_w;
+  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+    const int ry = (int)fdiv((uint32_t)p, div_w);
+    const int x = p - ry * dst_w;
+    const int X = (s_x0[ry] + s_adelta[x]) >> 5;
+    const int Y = (s_y0[ry] + s_bdelta[x]) >> 5;
+    int sx = X >> 5, sy = Y >> 5;
+    sx = max(-32768, min(32767, sx));  // saturate_cast<short>
+    sy = max(-32768, min(32767, sy));
+    const int fx = X & 31, fy = Y & 31;
+    const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy);
+    const int w10 = (32 - fx) * fy, w11 = fx * fy;
+    uint8_t* o = s_out + (size_t)p * C;
+    if ((unsigned)sx < (unsigned)(ws - 1) && (unsigned)sy < (unsigned)(hs - 1)) {
+      const uint8_t* r0 = img + ((int64_t)sy * ws + sx) * C;
+      const uint8_t* r1 = r0 + (int64_t)ws * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int acc = w00 * r0[c] + w01 * r0[C + c] + w10 * r1[c] + w11 * r1[C + c];
+        o[c] = (uint8_t)((acc + 512) >> 10);
+      }
+    } else if (sx >= ws || sx + 1 < 0 || sy >= hs || sy + 1 < 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) o[c] = 0;
+    } else {
+      const bool x0in = sx >= 0 && sx < ws, x1in = sx + 1 >= 0 && sx + 1 < ws;
+      const bool y0in = sy >= 0 && sy < hs, y1in = sy + 1 >= 0 && sy + 1 < hs;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        int acc = 0;
+        if (y0in && x0in) acc += w00 * img[((int64_t)sy * ws + sx) * C + c];
+        if (y0in && x1in) acc += w01 * img[((int64_t)sy * ws + sx + 1) * C + c];
+        if (y1in && x0in) acc += w10 * img[((int64_t)(sy + 1) * ws + sx) * C + c];
+        if (y1in && x1in) acc += w11 * img[((int64_t)(sy + 1) * ws + sx + 1) * C + c];
+        o[c] = (uint8_t)((acc + 512) >> 10);
+      }
+    }
+  }
+  __syncthreads();
+
+  // the tile is one contiguous span of the destination crop: coalesced copy-out
+  const size_t tile_bytes = (size_t)npix * C;
+  uint8_t* out = dst + ((size_t)crop * dst_h + row0) * dst_w * C;
+  if ((((uintptr_t)out) & 15) == 0) {
+    const int nvec = (int)(tile_bytes >> 4);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x)
+      reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(s_out)[i];
+    for (int i = (nvec << 4) + threadIdx.x; i < (int)tile_bytes; i += blockDim.x)
+      out[i] = s_out[i];
+  } else {
+    for (int i = threadIdx.x; i < (int)tile_bytes; i += blockDim.x) out[i] = s_out[i];
+  }
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+static inline unsigned blocks_for(int64_t n, int threads) {
+  return (unsigned)((n + threads - 1) / threads);
+}
+
+extern "C" int pc_box_to_center_scale(const float* d_boxes, float* d_center, float* d_scale,
+                                      const pc_box_params* p, int64_t n, void* stream) {
+  PC_REQUIRE(p != nullptr, PC_ERR_INVALID_ARGUMENT, "pc_box_to_center_scale: params is NULL");
+  PC_REQUIRE(n >= 0 && p->image_w > 0 && p->image_h > 0, PC_ERR_INVALID_ARGUMENT,
+             "pc_box_to_center_scale: bad n / image size");
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(d_boxes && d_center && d_scale, PC_ERR_INVALID_ARGUMENT,
+             "pc_box_to_center_scale: NULL tensor pointer");
+  const double aspect = (double)p->image_w / (double)p->image_h;
+  box_to_center_scale_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      d_boxes, d_center, d_scale, aspect, p->pixel_std, p->scale_padding, n);
+  PC_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+extern "C" int pc_affine_matrices(const float* d_center, const float* d_scale,
+                                  const float* d_rot, double* d_fwd, double* d_inv,
+                                  const pc_affine_params* p, int64_t n, void* stream) {
+  PC_REQUIRE(p != nullptr, PC_ERR_INVALID_ARGUMENT, "pc_affine_matrices: params is NULL");
+  PC_REQUIRE(n >= 0 && p->image_w > 0 && p->image_h > 0, PC_ERR_INVALID_ARGUMENT,
+             "pc_affine_matrices: bad n / image size");
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(d_center && d_scale && (d_fwd || d_inv), PC_ERR_INVALID_ARGUMENT,
+             "pc_affine_matrices: NULL tensor pointer");
+  affine_matrices_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
+      d_center, d_scale, d_rot, d_fwd, d_inv, p->image_w, p->image_h, p->pixel_std, p->use_udp,
+      n);
+  PC_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+extern "C" int pc_invert_affine(const double* d_fwd, double* d_inv, int64_t n, void* stream) {
+  PC_REQUIRE(n >= 0, PC_ERR_INVALID_ARGUMENT, "pc_invert_affine: n < 0");
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(d_fwd && d_inv, PC_ERR_INVALID_ARGUMENT, "pc_invert_affine: NULL tensor pointer");
+  invert_affine_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(d_fwd, d_inv, n);
+  PC_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+extern "C" int pc_affine_joints(float* d_keypoints, const double* d_fwd, int32_t num_joints,
+                                int32_t use_udp, int64_t n, void* stream) {
+  PC_REQUIRE(n >= 0 && num_joints >= 1, PC_ERR_INVALID_ARGUMENT,
+             "pc_affine_joints: bad n / num_joints");
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(d_keypoints && d_fwd, PC_ERR_INVALID_ARGUMENT,
+             "pc_affine_joints: NULL tensor pointer");
+  const int64_t total = n * num_joints;
+  affine_joints_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      d_keypoints, d_fwd, num_joints, use_udp, total);
+  PC_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offset,
+                                 const int32_t* d_src_hw, const double* d_inv, uint8_t* d_dst,
+                                 const pc_warp_params* p, int64_t n, void* stream) {
+  PC_REQUIRE(p != nullptr, PC_ERR_INVALID_ARGUMENT, "pc_warp_affine_u8: params is NULL");
+  PC_REQUIRE(n >= 0 && p->dst_w >= 1 && p->dst_h >= 1, PC_ERR_INVALID_ARGUMENT,
+             "pc_warp_affine_u8: bad n / destination size");
+  PC_REQUIRE(p->channels >= 1 && p->channels <= 4, PC_ERR_UNSUPPORTED,
+             "pc_warp_affine_u8: channels %d outside [1, 4]", p->channels);
+  PC_REQUIRE(p->dst_w <= kWarpMaxDstW, PC_ERR_UNSUPPORTED,
+             "pc_warp_affine_u8: dst_w %d > %d", p->dst_w, kWarpMaxDstW);
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(d_src && d_src_offset && d_src_hw && d_inv && d_dst, PC_ERR_INVALID_ARGUMENT,
+             "pc_warp_affine_u8: NULL tensor pointer");
+  const int tiles = (p->dst_h + kWarpTileRows - 1) / kWarpTileRows;
+  const int64_t grid = n * tiles;
+  PC_REQUIRE(grid < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_warp_affine_u8: batch too large");
+  const size_t smem = (size_t)kWarpTileRows * p->dst_w * p->channels;
+  const FastDiv dw = make_fastdiv((uint32_t)p->dst_w);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PC_LAUNCH_WARP(CH)                                                              \
+  warp_affine_u8_kernel<CH><<<(unsigned)grid, kWarpThreads, smem, st>>>(               \
+      d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles, dw)
+  switch (p->channels) {
+    case 1: PC_LAUNCH_WARP(1); break;
+    case 2: PC_LAUNCH_WARP(2); break;
+    case 3: PC_LAUNCH_WARP(3); break;
+    default: PC_LAUNCH_WARP(4); break;
+  }
+#undef PC_LAUNCH_WARP
+  PC_CUDA(cudaGetLastError());
+  return PC_OK;
+}

@@ -1,0 +1,184 @@
+"""Drop-in top-down transform classes (registry module ``transform``).
+
+They keep the reference's calling convention -- constructed as
+``cls(is_train=..., config=dataset_setting, **yaml_kwargs)``, invoked per sample
+as ``t(*columns) -> tuple[np.ndarray, ...]`` with the columns of
+``COLUMN_MAP`` (mindpose/data/transform/transform.py:66-79) -- and add batched
+device entry points (``*_batch``), which is how the codec reaches HBM speed: a
+per-sample launch cannot.  Both routes run the same CUDA kernels.
+"""
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import codec
+from .column_names import COLUMN_MAP
+from .register import register
+
+
+def _dev() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "mindpose_b200 transforms run on a CUDA device; none is visible "
+            "(there is no CPU fallback)"
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Transform:
+    """Column tuple <-> state dict adapter (transform.py:6-79)."""
+
+    def __init__(self, is_train: bool = True, config: Optional[Dict[str, Any]] = None) -> None:
+        self.is_train = is_train
+        self.config = config if config else dict()
+        self._transform_cfg = self.load_transform_cfg()
+        self._required_field = self.setup_required_field()
+
+    def load_transform_cfg(self) -> Dict[str, Any]:
+        raise NotImplementedError("Child class must implement this method.")
+
+    def transform(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        raise NotImplementedError("Child class must implement this method.")
+
+    def setup_required_field(self) -> List[str]:
+        raise NotImplementedError("Child class must implement this method.")
+
+    def __call__(self, *args: Any) -> Tuple[np.ndarray, ...]:
+        state = dict(zip(self._required_field, args))
+        state.update(self.transform(state))
+        return tuple(np.asarray(state[name]) for name in self._required_field)
+
+
+class TopDownTransform(Transform):
+    """Shared config parsing of the top-down transforms
+    (topdown_transform.py:32-94)."""
+
+    def setup_required_field(self) -> List[str]:
+        return COLUMN_MAP["topdown"]["train" if self.is_train else "val"]
+
+    def load_transform_cfg(self) -> Dict[str, Any]:
+        cfg = dict()
+        cfg["image_size"] = np.array(self.config["image_size"])
+        cfg["heatmap_size"] = np.array(self.config["heatmap_size"])
+        assert len(cfg["image_size"]) == 2
+        assert len(cfg["heatmap_size"]) == 2
+        pairs = np.array(self.config["flip_pairs"])
+        if pairs.ndim == 2:
+            cfg["flip_index"] = np.insert(pairs[:, ::-1].flatten(), 0, 0)
+        else:
+            cfg["flip_index"] = pairs
+        cfg["flip_pairs"] = pairs
+        cfg["upper_body_ids"] = np.array(self.config["upper_body_ids"])
+        cfg["pixel_std"] = float(self.config["pixel_std"])
+        cfg["scale_padding"] = float(self.config["scale_padding"])
+        jw = self.config.get("joint_weights")
+        cfg["joint_weights"] = None if jw is None else np.array(jw)
+        return cfg
+
+
+@register("transform", extra_name="topdown_box_to_center_scale")
+class TopDownBoxToCenterScale(TopDownTransform):
+    """Box (x, y, w, h) -> center / scale (topdown_transform.py:97-154).
+
+    Required keys: boxes.  Returned keys: center, scale.
+    The training-time random centre shift is host-side augmentation outside the
+    codec; it is applied to the box before the kernel exactly where the
+    reference applies it to the centre (:140-141).
+    """
+
+    def transform(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        boxes = np.asarray(state["boxes"], dtype=np.float32).reshape(1, 4)
+        center, scale = self.box_to_center_scale_batch(torch.from_numpy(boxes).to(_dev()))
+        center = center[0].cpu().numpy()
+        if self.is_train and np.random.rand() < 0.3:
+            w, h = boxes[0, 2], boxes[0, 3]
+            center += np.random.uniform(-0.2, 0.2, size=2) * [w, h]
+        return dict(center=center, scale=scale[0].cpu().numpy())
+
+    def box_to_center_scale_batch(self, boxes: torch.Tensor):
+        return codec.box_to_center_scale(
+            boxes,
+            self._transform_cfg["image_size"],
+            pixel_std=self._transform_cfg["pixel_std"],
+            scale_padding=self._transform_cfg["scale_padding"],
+        )
+
+
+@register("transform", extra_name="topdown_affine")
+class TopDownAffine(TopDownTransform):
+    """Affine crop warp of one instance (topdown_transform.py:157-261).
+
+    Required keys: image, center, scale, rotation, keypoints (optional).
+    Returned keys: image, keypoints (optional).
+    """
+
+    def __init__(self, is_train: bool = True, config: Optional[Dict[str, Any]] = None,
+                 use_udp: bool = False) -> None:
+        super().__init__(is_train=is_train, config=config)
+        self.use_udp = use_udp
+
+    def transform(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        dev = _dev()
+        image = np.ascontiguousarray(state["image"])
+        if image.dtype != np.uint8 or image.ndim != 3:
+            raise ValueError("`image` must be a uint8 HWC array")
+        center = torch.from_numpy(np.asarray(state["center"], np.float32).reshape(1, 2)).to(dev)
+        scale = torch.from_numpy(np.asarray(state["scale"], np.float32).reshape(1, 2)).to(dev)
+        rot = torch.from_numpy(np.asarray(state["rotation"], np.float32).reshape(1)).to(dev)
+        kps = None
+        if "keypoints" in state:
+            kps = torch.from_numpy(
+                np.ascontiguousarray(state["keypoints"], dtype=np.float32)[None]).to(dev)
+        img_t = torch.from_numpy(image[None]).to(dev)
+        crop, kps = self.affine_batch(img_t, center, scale, rot, kps)
+        out = dict(image=crop[0].cpu().numpy())
+        if kps is not None:
+            # the reference mutates state["keypoints"] in place
+            state["keypoints"][...] = kps[0].cpu().numpy().astype(state["keypoints"].dtype)
+            out["keypoints"] = state["keypoints"]
+        return out
+
+    def affine_batch(self, images: torch.Tensor, center, scale, rot=None, keypoints=None):
+        """images u8 [N,Hs,Ws,C] (one per crop) -> (crops u8 [N,h,w,C], keypoints)."""
+        cfg = self._transform_cfg
+        fwd, inv = codec.affine_matrices(center, scale, rot, cfg["image_size"],
+                                         pixel_std=cfg["pixel_std"], use_udp=self.use_udp)
+        crops = codec.warp_affine_uniform(images, inv, cfg["image_size"])
+        if keypoints is not None:
+            keypoints = codec.affine_joints(keypoints.contiguous(), fwd, use_udp=self.use_udp)
+        return crops, keypoints
+
+
+@register("transform", extra_name="topdown_generate_target")
+class TopDownGenerateTarget(TopDownTransform):
+    """Keypoints -> Gaussian heatmap targets (topdown_transform.py:264-430).
+
+    Required keys: keypoints.  Returned keys: target, target_weight.
+    """
+
+    def __init__(self, is_train: bool = True, config: Optional[Dict[str, Any]] = None,
+                 sigma: float = 2.0, use_different_joint_weights: bool = False,
+                 use_udp: bool = False) -> None:
+        super().__init__(is_train=is_train, config=config)
+        self.sigma = sigma
+        self.use_different_joint_weights = use_different_joint_weights
+        self.use_udp = use_udp
+        if self.use_different_joint_weights and self._transform_cfg["joint_weights"] is None:
+            raise ValueError(
+                "`joint_weights` must be provided if `use_different_joint_weights` is True."
+            )
+
+    def transform(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        kps = torch.from_numpy(
+            np.ascontiguousarray(state["keypoints"], dtype=np.float32)[None]).to(_dev())
+        target, weight = self.encode_batch(kps)
+        return dict(target=target[0].cpu().numpy(), target_weight=weight[0].cpu().numpy())
+
+    def encode_batch(self, keypoints: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """keypoints f32 [N,K,3] -> (target [N,K,H,W], target_weight [N,K])."""
+        cfg = self._transform_cfg
+        jw = cfg["joint_weights"] if self.use_different_joint_weights else None
+        return codec.topdown_encode(keypoints, cfg["image_size"], cfg["heatmap_size"],
+                                    sigma=self.sigma, use_udp=self.use_udp, joint_weights=jw,
+                                    out=out)

@@ -1,0 +1,109 @@
+"""The C-ABI library loads and exports every symbol include/posecodec.h declares;
+the ctypes mirrors have the header's struct sizes.  No compute calls (no GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "posecodec.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mindpose_b200.csrc import build
+
+    build.build()
+    from mindpose_b200 import _lib
+
+    return _lib.load()
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_something():
+    names = _declared_functions()
+    assert "pc_topdown_decode" in names and "pc_warp_affine_u8" in names and len(names) >= 14
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from mindpose_b200 import _lib
+
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} declared in posecodec.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
+
+
+def test_version_and_error_string(lib):
+    assert lib.pc_version() == 100
+    assert isinstance(lib.pc_last_error(), bytes)
+
+
+def test_struct_sizes_match_header(tmp_path):
+    from mindpose_b200 import _lib
+
+    structs = {
+        "pc_box_params": _lib.BoxParams,
+        "pc_affine_params": _lib.AffineParams,
+        "pc_warp_params": _lib.WarpParams,
+        "pc_encode_params": _lib.EncodeParams,
+        "pc_topdown_decode_params": _lib.TopDownDecodeParams,
+        "pc_bottomup_decode_params": _lib.BottomUpDecodeParams,
+        "pc_group_params": _lib.GroupParams,
+    }
+    src = tmp_path / "sizes.c"
+    body = "\n".join(f'  printf("{n} %zu\\n", sizeof({n}));' for n in structs)
+    src.write_text(f'#include <stdio.h>\n#include "posecodec.h"\nint main(void) {{\n{body}\n  return 0;\n}}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    for line in out.strip().splitlines():
+        name, size = line.split()
+        assert ctypes.sizeof(structs[name]) == int(size), name
+
+
+def test_argument_errors_raise_value_error_without_gpu(lib):
+    """Validation happens before any CUDA call, so it is checkable on CPU."""
+    from mindpose_b200 import _lib
+
+    p = _lib.TopDownDecodeParams()
+    p.num_joints, p.height, p.width = 17, 64, 48
+    p.shift_coordinate = p.dark_udp_refine = 1
+    p.kernel_size = 11
+    with pytest.raises(ValueError, match="cannot be `true` in the same time"):
+        _lib.call("pc_topdown_decode", 0, 0, 0, 0, 0, 0, 0, ctypes.byref(p), 4, 0)
+    p.shift_coordinate = 0
+    p.num_joints = 1000
+    with pytest.raises(ValueError):
+        _lib.call("pc_topdown_decode", 0, 0, 0, 0, 0, 0, 0, ctypes.byref(p), 4, 0)
+    e = _lib.EncodeParams()
+    e.num_joints, e.image_w, e.image_h, e.heatmap_w, e.heatmap_h = 17, 192, 256, 48, 64
+    e.sigma = 1.5  # 3 * sigma not an integer
+    with pytest.raises(ValueError):
+        _lib.call("pc_topdown_encode", 0, 0, 0, ctypes.byref(e), 1, 0)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from mindpose_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libposecodec.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_host_tensor_is_rejected():
+    import torch
+
+    from mindpose_b200 import codec
+
+    with pytest.raises(ValueError, match="CUDA"):
+        codec.topdown_decode(torch.zeros(1, 17, 64, 48), torch.zeros(1, 2), torch.ones(1, 2),
+                             torch.zeros(1))

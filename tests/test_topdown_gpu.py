@@ -1,0 +1,310 @@
+"""Parity of the CUDA top-down codec against the oracle (B200 only).
+
+Bars (BASELINE.json north_star): argmax indices / maxvals bit-exact; refined
+coordinates within 1e-4 px; encoded targets within 1e-5; warped pixels bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import mindpose_b200 as mp
+from mindpose_b200 import codec, synth
+from oracle import affine, topdown_decode, topdown_encode, warp
+
+pytestmark = pytest.mark.gpu
+
+COORD_TOL = 1e-4
+TARGET_TOL = 1e-5
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# --------------------------------------------------------------------- decode
+def _decode_case(dev, maps, flipped, n, h, w, seed, *, flip, shift_heatmap, shift_coordinate,
+                 dark, use_udp, to_original=True, kernel_size=11):
+    center, scale, score = synth.crop_geometry(n, seed=seed)
+    fidx = synth.flip_index()
+    kw = dict(to_original=to_original, shift_coordinate_flag=shift_coordinate, use_udp=use_udp,
+              dark_udp_refine_flag=dark, kernel_size=kernel_size)
+    if flip:
+        want_p, want_b = topdown_decode.decode_with_flip(maps, flipped, fidx, center, scale, score,
+                                                         shift_heatmap=shift_heatmap, **kw)
+    else:
+        want_p, want_b = topdown_decode.decode(maps, center, scale, score, **kw)
+    dec = mp.create_decoder("topdown_heatmap", to_original=to_original,
+                            shift_coordinate=shift_coordinate, use_udp=use_udp,
+                            dark_udp_refine=dark, kernel_size=kernel_size)
+    if flip:
+        got_p, got_b = dec.decode_flip_pair(_t(maps, dev), _t(flipped, dev), fidx, _t(center, dev),
+                                            _t(scale, dev), _t(score, dev),
+                                            shift_heatmap=shift_heatmap)
+    else:
+        got_p, got_b = dec(_t(maps, dev), _t(center, dev), _t(scale, dev), _t(score, dev))
+    torch.cuda.synchronize()
+    return got_p.cpu().numpy(), got_b.cpu().numpy(), want_p, want_b
+
+
+@pytest.mark.parametrize("h,w", [(64, 48), (96, 72), (48, 64)])
+@pytest.mark.parametrize("flip,shift_heatmap", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("mode", ["plain", "shift", "dark", "dark_udp"])
+def test_decode_blobs(cuda_device, h, w, flip, shift_heatmap, mode):
+    n = 33
+    maps, _ = synth.blob_heatmaps(n, 17, h, w, seed=h + w)
+    flipped = synth.flipped_pair(maps, seed=h)
+    got_p, got_b, want_p, want_b = _decode_case(
+        cuda_device, maps, flipped, n, h, w, seed=3, flip=flip, shift_heatmap=shift_heatmap,
+        shift_coordinate=(mode == "shift"), dark=mode.startswith("dark"),
+        use_udp=(mode == "dark_udp"))
+    assert np.array_equal(got_p[..., 2], want_p[..., 2])  # maxvals bit-exact
+    assert np.array_equal(got_b, want_b)
+    if mode in ("plain", "shift"):
+        assert np.array_equal(got_p, want_p)  # exact-order fp32: bit-exact
+    else:
+        assert np.abs(got_p[..., :2] - want_p[..., :2]).max() <= COORD_TOL
+
+
+@pytest.mark.parametrize("flip", [False, True])
+def test_decode_noise_maps_indices_bit_exact(cuda_device, flip):
+    """What the reference's own tests feed (uniform noise): argmax, maxval and the
+    quarter-offset are exact; DARK offsets are ill-conditioned there and are not compared."""
+    n, h, w = 64, 64, 48
+    maps = synth.noise_heatmaps(n, 17, h, w, seed=0)
+    flipped = synth.noise_heatmaps(n, 17, h, w, seed=1)
+    for to_original in (False, True):
+        got_p, got_b, want_p, want_b = _decode_case(
+            cuda_device, maps, flipped, n, h, w, seed=0, flip=flip, shift_heatmap=True,
+            shift_coordinate=True, dark=False, use_udp=False, to_original=to_original)
+        assert np.array_equal(got_p, want_p)
+        assert np.array_equal(got_b, want_b)
+
+
+def test_decode_ties_take_lowest_index_and_border_peaks(cuda_device):
+    n, k, h, w = 3, 17, 64, 48
+    maps = np.zeros((n, k, h, w), np.float32)
+    maps[0, :, 10, 7] = 1.0
+    maps[0, :, 50, 3] = 1.0           # duplicate maximum later in the plane
+    maps[1, :, 0, 0] = 0.7            # corner peak: DARK reads the zero padding of the log map
+    maps[1, 5, 63, 47] = 0.9
+    maps[2] = 0.25                    # constant plane: argmax 0
+    center, scale, score = synth.crop_geometry(n, seed=5)
+    for dark in (False, True):
+        want_p, want_b = topdown_decode.decode(maps, center, scale, score, to_original=False,
+                                               dark_udp_refine_flag=dark)
+        dec = mp.create_decoder("topdown_heatmap", to_original=False, dark_udp_refine=dark)
+        got_p, got_b = dec(_t(maps, cuda_device), _t(center, cuda_device), _t(scale, cuda_device),
+                           _t(score, cuda_device))
+        got_p = got_p.cpu().numpy()
+        assert np.array_equal(got_p[..., 2], want_p[..., 2])
+        assert np.allclose(got_p, want_p, rtol=0, atol=COORD_TOL)
+    assert got_p.shape == (n, k, 3)
+
+
+def test_decode_reference_test_shapes(cuda_device):
+    """tests/models/decoders/test_top_down_decoder.py: [8,17,48,64] -> (8,17,3), (8,6)."""
+    dev = cuda_device
+    for kwargs in (dict(), dict(shift_coordinate=True), dict(use_udp=True, dark_udp_refine=True)):
+        dec = mp.create_decoder("topdown_heatmap", **kwargs)
+        hm = torch.rand(8, 17, 48, 64, device=dev)
+        p, b = dec(hm, torch.rand(8, 2, device=dev) * 400, torch.rand(8, 2, device=dev) * 3,
+                   torch.rand(8, device=dev))
+        assert p.shape == (8, 17, 3) and b.shape == (8, 6) and p.dtype == torch.float32
+
+
+def test_decode_large_batch_properties(cuda_device):
+    """Full BASELINE size (4096 crops, flip pair): compare against torch reductions
+    (size-independent properties: argmax value/index, idempotence of a second call)."""
+    dev = cuda_device
+    n, k, h, w = 4096, 17, 64, 48
+    g = torch.Generator(device=dev).manual_seed(0)
+    hm = torch.rand(n, k, h, w, device=dev, generator=g)
+    fl = torch.rand(n, k, h, w, device=dev, generator=g)
+    fidx = torch.as_tensor(synth.flip_index(), device=dev)
+    center = torch.rand(n, 2, device=dev) * 400
+    scale = torch.rand(n, 2, device=dev) * 2.8 + 0.2
+    score = torch.rand(n, device=dev)
+    dec = mp.create_decoder("topdown_heatmap", to_original=False)
+    p, b = dec.decode_flip_pair(hm, fl, synth.flip_index(), center, scale, score)
+    avg = (hm + fl[:, fidx].flip(-1)) * 0.5
+    vals, idx = avg.reshape(n, k, -1).max(dim=2)
+    assert torch.equal(p[..., 2], vals)
+    assert torch.equal(p[..., 0], (idx % w).float()) and torch.equal(p[..., 1], (idx // w).float())
+    p2, b2 = dec.decode_flip_pair(hm, fl, synth.flip_index(), center, scale, score)
+    assert torch.equal(p, p2) and torch.equal(b, b2)
+
+
+def test_decode_host_front_end_matches_device_path(cuda_device):
+    n, h, w = 300, 64, 48
+    maps, _ = synth.blob_heatmaps(n, 17, h, w, seed=2)
+    flipped = synth.flipped_pair(maps, seed=2)
+    center, scale, score = synth.crop_geometry(n, seed=2)
+    dec = mp.create_decoder("topdown_heatmap", dark_udp_refine=True)
+    p = dec._params(17, h, w, flip_index=synth.flip_index(), shift_heatmap=False)
+    ctx = codec.HostContext(0, scratch_bytes=64 << 20)
+    hp, hb = ctx.topdown_decode(maps, center, scale, score, flipped=flipped, params=p)
+    ctx.close()
+    dp, db = dec.decode_flip_pair(_t(maps, cuda_device), _t(flipped, cuda_device),
+                                  synth.flip_index(), _t(center, cuda_device),
+                                  _t(scale, cuda_device), _t(score, cuda_device))
+    assert np.array_equal(hp, dp.cpu().numpy()) and np.array_equal(hb, db.cpu().numpy())
+
+
+# --------------------------------------------------------------------- encode
+@pytest.mark.parametrize("cfg", [synth.TOPDOWN_CONFIG, synth.TOPDOWN_CONFIG_384])
+@pytest.mark.parametrize("use_udp", [False, True])
+def test_encode_matches_oracle(cuda_device, cfg, use_udp):
+    n = 64
+    kps = synth.keypoints(n, 17, cfg["image_size"], seed=0)
+    t = mp.create_transform("topdown_generate_target", is_train=True, config=cfg, sigma=2.0,
+                            use_udp=use_udp)
+    target, weight = t.encode_batch(_t(kps, cuda_device))
+    target, weight = target.cpu().numpy(), weight.cpu().numpy()
+    fn = topdown_encode.encode_udp if use_udp else topdown_encode.encode_gaussian
+    for i in range(n):
+        want_t, want_w = fn(kps[i], cfg["image_size"], cfg["heatmap_size"], sigma=2.0)
+        assert np.array_equal(weight[i], want_w)
+        assert np.array_equal(target[i] != 0, want_t != 0)  # same support
+        assert np.abs(target[i] - want_t).max() <= TARGET_TOL
+
+
+def test_encode_matches_reference_golden(cuda_device, golden):
+    g = golden("encode_ref.npz")
+    for tag, cfg in (("64x48", synth.TOPDOWN_CONFIG), ("96x72", synth.TOPDOWN_CONFIG_384)):
+        kps = g[f"kps_{tag}"]
+        for name, udp in (("std", False), ("udp", True)):
+            t = mp.create_transform("topdown_generate_target", config=cfg, use_udp=udp)
+            target, weight = t.encode_batch(_t(kps, cuda_device))
+            assert np.array_equal(weight.cpu().numpy(), g[f"weight_{name}_{tag}"])
+            assert np.abs(target.cpu().numpy() - g[f"target_{name}_{tag}"]).max() <= TARGET_TOL
+    cfg = dict(synth.TOPDOWN_CONFIG, joint_weights=g["joint_weights"].tolist())
+    t = mp.create_transform("topdown_generate_target", config=cfg, sigma=3.0,
+                            use_different_joint_weights=True)
+    target, weight = t.encode_batch(_t(g["kps_64x48"][:4], cuda_device))
+    assert np.abs(target.cpu().numpy() - g["target_std_sigma3"]).max() <= TARGET_TOL
+    assert np.abs(weight.cpu().numpy() - g["weight_std_sigma3"]).max() <= 1e-6
+
+
+def test_encode_per_sample_call_convention(cuda_device):
+    """t(*columns) with the train column order, as MindSpore's dataset.map calls it."""
+    cfg = synth.TOPDOWN_CONFIG
+    t = mp.create_transform("topdown_generate_target", is_train=True, config=cfg)
+    kps = synth.keypoints(1, 17, cfg["image_size"], seed=4)[0]
+    cols = [np.zeros((256, 192, 3), np.uint8), np.zeros(2, np.float32), np.ones(2, np.float32),
+            np.zeros(4, np.float32), kps, np.float32(0), np.zeros(1, np.float32),
+            np.zeros(1, np.float32)]
+    out = t(*cols)
+    want_t, want_w = topdown_encode.encode_gaussian(kps, cfg["image_size"], cfg["heatmap_size"])
+    assert len(out) == 8 and out[6].shape == (17, 64, 48)
+    assert np.abs(out[6] - want_t).max() <= TARGET_TOL and np.array_equal(out[7], want_w)
+
+
+def test_encode_decode_round_trip_full_size(cuda_device):
+    """Property at BASELINE size: decoding an encoded in-bounds keypoint returns its pixel."""
+    n = 2048
+    cfg = synth.TOPDOWN_CONFIG
+    rng = np.random.RandomState(0)
+    kps = np.ones((n, 17, 3), np.float32)
+    kps[..., 0] = rng.uniform(8, 180, (n, 17))
+    kps[..., 1] = rng.uniform(8, 240, (n, 17))
+    t = mp.create_transform("topdown_generate_target", config=cfg)
+    target, weight = t.encode_batch(_t(kps, cuda_device))
+    dec = mp.create_decoder("topdown_heatmap", to_original=False)
+    z = torch.zeros(n, 2, device=cuda_device)
+    p, _ = dec(target, z, z + 1, torch.zeros(n, device=cuda_device))
+    mu = torch.from_numpy(np.rint(kps[..., :2].astype(np.float64) / 4.0).astype(np.float32))
+    assert torch.equal(p[..., :2].cpu(), mu) and torch.all(p[..., 2] == 1.0)
+    assert torch.all(weight == 1.0)
+
+
+# ----------------------------------------------------------------- warp / geometry
+def test_geometry_matches_oracle(cuda_device, golden):
+    g = golden("affine_ref.npz")
+    dev = cuda_device
+    for tag, image_size in (("256x192", [192, 256]), ("384x288", [288, 384])):
+        cfg = dict(synth.TOPDOWN_CONFIG, image_size=image_size)
+        t = mp.create_transform("topdown_box_to_center_scale", is_train=False, config=cfg)
+        c, s = t.box_to_center_scale_batch(_t(g["boxes"], dev))
+        assert np.array_equal(c.cpu().numpy(), g[f"center_{tag}"])
+        assert np.array_equal(s.cpu().numpy(), g[f"scale_{tag}"])
+        rot = _t(g["rots"].astype(np.float32), dev)
+        ref_std = np.stack([affine.affine_matrix(ci, si, float(np.float32(r)), np.array(image_size))
+                            for ci, si, r in zip(g[f"center_{tag}"], g[f"scale_{tag}"], g["rots"])])
+        fwd, inv = codec.affine_matrices(c, s, rot, image_size, use_udp=False)
+        assert np.allclose(fwd.cpu().numpy(), ref_std, rtol=0, atol=1e-9 * np.abs(ref_std).max())
+        want_inv = np.stack([warp.invert_affine(m) for m in fwd.cpu().numpy()])
+        assert np.array_equal(inv.cpu().numpy(), want_inv)
+        ref_udp = np.stack([affine.udp_matrix(ci, si, float(np.float32(r)), np.array(image_size))
+                            for ci, si, r in zip(g[f"center_{tag}"], g[f"scale_{tag}"], g["rots"])])
+        fwd_u, _ = codec.affine_matrices(c, s, rot, image_size, use_udp=True)
+        fu = fwd_u.cpu().numpy()
+        zero_rot = g["rots"] == 0
+        assert np.array_equal(fu[zero_rot], ref_udp[zero_rot].astype(np.float64))
+        assert np.allclose(fu, ref_udp, rtol=2e-7, atol=1e-6)
+        # joints through the reference's own matrices
+        k_std = codec.affine_joints(_t(g["kps_in"], dev).clone(), _t(g[f"std_{tag}"], dev), False)
+        assert np.abs(k_std.cpu().numpy() - g[f"kps_std_{tag}"]).max() == 0
+        k_udp = codec.affine_joints(_t(g["kps_in"], dev).clone(),
+                                    _t(g[f"udp_{tag}"].astype(np.float64), dev), True)
+        assert np.abs(k_udp.cpu().numpy() - g[f"kps_udp_{tag}"]).max() <= 1e-4
+
+
+def test_warp_matches_cv2_golden(cuda_device, golden):
+    g = golden("warp_ref.npz")
+    src, dst, sizes, mats = g["src"], g["dst"], g["sizes"], g["mats"]
+    dev = cuda_device
+    so = do = 0
+    for (hs, ws, dw, dh), m in zip(sizes, mats):
+        s = src[so:so + hs * ws * 3].reshape(1, hs, ws, 3)
+        d = dst[do:do + dh * dw * 3].reshape(dh, dw, 3)
+        so += hs * ws * 3
+        do += dh * dw * 3
+        inv = codec.invert_affine(_t(m[None], dev))
+        out = codec.warp_affine_uniform(_t(s, dev), inv, (int(dw), int(dh)))
+        assert np.array_equal(out[0].cpu().numpy(), d)
+
+
+@pytest.mark.parametrize("use_udp", [False, True])
+def test_warp_batch_matches_oracle(cuda_device, use_udp):
+    n = 24
+    images, boxes = synth.source_images_and_boxes(n, 240, 320, seed=1)
+    cfg = synth.TOPDOWN_CONFIG
+    dev = cuda_device
+    bt = mp.create_transform("topdown_box_to_center_scale", is_train=False, config=cfg)
+    at = mp.create_transform("topdown_affine", is_train=False, config=cfg, use_udp=use_udp)
+    c, s = bt.box_to_center_scale_batch(_t(boxes, dev))
+    rot = torch.zeros(n, device=dev)
+    rot[::3] = 30.0
+    kps = synth.keypoints(n, 17, [320, 240], seed=2)
+    crops, kout = at.affine_batch(_t(images, dev), c, s, rot, _t(kps, dev))
+    fwd, _ = codec.affine_matrices(c, s, rot, cfg["image_size"], use_udp=use_udp)
+    fwd = fwd.cpu().numpy()
+    crops = crops.cpu().numpy()
+    for i in range(n):
+        want = warp.warp_affine_u8(images[i], fwd[i], (192, 256))
+        assert np.array_equal(crops[i], want), i
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    if cv2 is not None:
+        for i in range(0, n, 5):
+            m = fwd[i].astype(np.float32) if use_udp else fwd[i]
+            assert np.array_equal(crops[i], cv2.warpAffine(images[i], m, (192, 256),
+                                                           flags=cv2.INTER_LINEAR))
+    assert kout.shape == (n, 17, 3)
+
+
+def test_affine_per_sample_call_convention(cuda_device):
+    cfg = synth.TOPDOWN_CONFIG
+    images, boxes = synth.source_images_and_boxes(1, 200, 300, seed=3)
+    bt = mp.create_transform("topdown_box_to_center_scale", is_train=False, config=cfg)
+    at = mp.create_transform("topdown_affine", is_train=False, config=cfg)
+    cols = [images[0], np.zeros(2, np.float32), np.ones(2, np.float32), np.float32(0),
+            np.array("x.jpg"), boxes[0], np.int32(0), np.float32(1)]
+    cols = list(bt(*cols))
+    c_want, s_want = affine.box_to_center_scale(tuple(boxes[0]), np.array(cfg["image_size"]))
+    assert np.array_equal(cols[1], c_want) and np.array_equal(cols[2], s_want)
+    out = at(*cols)
+    m = affine.affine_matrix(c_want, s_want, 0.0, np.array(cfg["image_size"]))
+    assert np.array_equal(out[0], warp.warp_affine_u8(images[0], m, (192, 256)))
