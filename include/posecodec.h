@@ -207,6 +207,20 @@ int pc_topdown_decode_host(pc_ctx* ctx, const float* h_heatmap, const float* h_f
                            float* h_all_preds, float* h_all_boxes,
                            const pc_topdown_decode_params* params, int64_t n);
 
+/* Host-buffer crop warp: TopDownBoxToCenterScale + TopDownAffine for N crops, one
+ * dense source image per crop, all of one size (h_images u8 [N, src_h, src_w, C]).
+ * h_boxes f32 [N,4] (x,y,w,h); h_rot f32 [N] or NULL.
+ * -> h_crops u8 [N, image_h, image_w, C]; optional h_center / h_scale f32 [N,2]. */
+typedef struct pc_affine_host_params {
+  int32_t src_h, src_w, channels;
+  int32_t image_w, image_h; /* crop size, dataset_setting.image_size = [w, h] */
+  float pixel_std, scale_padding;
+  int32_t use_udp;
+} pc_affine_host_params;
+int pc_topdown_affine_host(pc_ctx* ctx, const uint8_t* h_images, const float* h_boxes,
+                           const float* h_rot, uint8_t* h_crops, float* h_center,
+                           float* h_scale, const pc_affine_host_params* params, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,6 +120,19 @@ class GroupParams(Structure):
     ]
 
 
+class AffineHostParams(Structure):
+    _fields_ = [
+        ("src_h", c_int32),
+        ("src_w", c_int32),
+        ("channels", c_int32),
+        ("image_w", c_int32),
+        ("image_h", c_int32),
+        ("pixel_std", c_float),
+        ("scale_padding", c_float),
+        ("use_udp", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); one entry per function declared in posecodec.h
 _P = c_void_p
 SIGNATURES = {
@@ -147,6 +160,10 @@ SIGNATURES = {
     ),
     "pc_ctx_create": (c_int, [c_int, c_int64, POINTER(c_void_p)]),
     "pc_ctx_destroy": (c_int, [c_void_p]),
+    "pc_topdown_affine_host": (
+        c_int,
+        [c_void_p, _P, _P, _P, _P, _P, _P, POINTER(AffineHostParams), c_int64],
+    ),
     "pc_topdown_decode_host": (
         c_int,
         [c_void_p, _P, _P, _P, _P, _P, _P, _P, POINTER(TopDownDecodeParams), c_int64],

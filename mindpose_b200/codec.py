@@ -259,3 +259,26 @@ class HostContext:
                   _lib.host_ptr(score), _lib.host_ptr(preds), _lib.host_ptr(boxes),
                   ctypes.byref(params), n)
         return preds, boxes
+
+    def topdown_affine(self, images: np.ndarray, boxes: np.ndarray, image_size,
+                       rot: Optional[np.ndarray] = None, pixel_std: float = 200.0,
+                       scale_padding: float = 1.25, use_udp: bool = False,
+                       out: Optional[np.ndarray] = None):
+        """images u8 [N,Hs,Ws,C] + boxes f32 [N,4] (host) -> (crops u8 [N,h,w,C], center, scale)."""
+        if images.dtype != np.uint8 or images.ndim != 4:
+            raise ValueError("`images` must be uint8 [N, Hs, Ws, C]")
+        images = np.ascontiguousarray(images)
+        n, hs, ws, c = images.shape
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(n, 4)
+        if rot is not None:
+            rot = np.ascontiguousarray(rot, dtype=np.float32).reshape(n)
+        w, h = (int(v) for v in np.asarray(image_size).reshape(-1)[:2])
+        crops = out if out is not None else np.empty((n, h, w, c), np.uint8)
+        center = np.empty((n, 2), np.float32)
+        scale = np.empty((n, 2), np.float32)
+        p = _lib.AffineHostParams(hs, ws, c, w, h, float(pixel_std), float(scale_padding),
+                                  int(bool(use_udp)))
+        _lib.call("pc_topdown_affine_host", self._h, _lib.host_ptr(images), _lib.host_ptr(boxes),
+                  _lib.host_ptr(rot), _lib.host_ptr(crops), _lib.host_ptr(center),
+                  _lib.host_ptr(scale), ctypes.byref(p), n)
+        return crops, center, scale

@@ -1,6 +1,7 @@
 // lib.cu -- library plumbing of libposecodec: errors, device query, and the
 // host-buffer front end (pc_ctx / pc_topdown_decode_host).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -183,6 +184,101 @@ extern "C" int pc_topdown_decode_host(pc_ctx* c, const float* h_heatmap, const f
                             cudaMemcpyDeviceToHost, st));
     PC_CUDA(cudaMemcpyAsync(h_all_boxes + i0 * 6, d_boxes, sizeof(float) * m * 6,
                             cudaMemcpyDeviceToHost, st));
+  }
+  cudaError_t e0 = cudaStreamSynchronize(c->stream[0]);
+  cudaError_t e1 = cudaStreamSynchronize(c->stream[1]);
+  if (rc != PC_OK) return rc;
+  if (e0 != cudaSuccess) return cuda_fail(e0, "cudaStreamSynchronize");
+  if (e1 != cudaSuccess) return cuda_fail(e1, "cudaStreamSynchronize");
+  return PC_OK;
+}
+
+extern "C" int pc_topdown_affine_host(pc_ctx* c, const uint8_t* h_images, const float* h_boxes,
+                                      const float* h_rot, uint8_t* h_crops, float* h_center,
+                                      float* h_scale, const pc_affine_host_params* p,
+                                      int64_t n) {
+  PC_REQUIRE(c != nullptr && p != nullptr, PC_ERR_INVALID_ARGUMENT,
+             "pc_topdown_affine_host: ctx / params is NULL");
+  PC_REQUIRE(n >= 0, PC_ERR_INVALID_ARGUMENT, "pc_topdown_affine_host: n < 0");
+  PC_REQUIRE(p->src_h >= 1 && p->src_w >= 1 && p->channels >= 1 && p->channels <= 4 &&
+                 p->image_w >= 1 && p->image_h >= 1,
+             PC_ERR_INVALID_ARGUMENT, "pc_topdown_affine_host: bad sizes");
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(h_images && h_boxes && h_crops, PC_ERR_INVALID_ARGUMENT,
+             "pc_topdown_affine_host: NULL host pointer");
+  PC_CUDA(cudaSetDevice(c->device));
+  const int64_t src_bytes = (int64_t)p->src_h * p->src_w * p->channels;
+  const int64_t dst_bytes = (int64_t)p->image_h * p->image_w * p->channels;
+  // per crop in the maps scratch: source image, crop, then (16-B aligned) offsets,
+  // sizes and the two matrices
+  const int64_t per_crop = ((src_bytes + dst_bytes + 15) / 16) * 16 + 8 + 8 + 48 + 48;
+  int64_t chunk = (c->scratch_bytes - 64) / per_crop;
+  if (chunk > kMaxChunkCrops) chunk = kMaxChunkCrops;
+  if (chunk > (n + 3) / 4) chunk = (n + 3) / 4;
+  PC_REQUIRE(chunk >= 1, PC_ERR_UNSUPPORTED,
+             "pc_topdown_affine_host: one crop (%lld bytes) exceeds the context scratch",
+             (long long)per_crop);
+  pc_box_params bp = {p->image_w, p->image_h, p->pixel_std, p->scale_padding};
+  pc_affine_params ap = {p->image_w, p->image_h, p->pixel_std, p->use_udp};
+  pc_warp_params wp = {p->image_w, p->image_h, p->channels};
+  // offsets / sizes are the same for every chunk: build once on the host
+  static thread_local int64_t* h_off = nullptr;
+  static thread_local int32_t* h_hw = nullptr;
+  static thread_local int64_t h_cap = 0;
+  if (h_cap < chunk) {
+    free(h_off);
+    free(h_hw);
+    h_off = (int64_t*)malloc(sizeof(int64_t) * chunk);
+    h_hw = (int32_t*)malloc(sizeof(int32_t) * 2 * chunk);
+    h_cap = chunk;
+  }
+  for (int64_t i = 0; i < chunk; ++i) {
+    h_off[i] = i * src_bytes;
+    h_hw[2 * i] = p->src_h;
+    h_hw[2 * i + 1] = p->src_w;
+  }
+  int rc = PC_OK;
+  int slot = 0;
+  for (int64_t i0 = 0; i0 < n && rc == PC_OK; i0 += chunk, slot ^= 1) {
+    const int64_t m = (n - i0 < chunk) ? n - i0 : chunk;
+    cudaStream_t st = c->stream[slot];
+    unsigned char* base = c->d_maps[slot];
+    uint8_t* d_src = base;
+    uint8_t* d_dst = base + ((m * src_bytes + 15) / 16) * 16;
+    unsigned char* q = d_dst + ((m * dst_bytes + 15) / 16) * 16;
+    int64_t* d_off = (int64_t*)q;
+    q += 8 * m;
+    double* d_fwd = (double*)q;
+    q += 48 * m;
+    double* d_inv = (double*)q;
+    q += 48 * m;
+    int32_t* d_hw = (int32_t*)q;
+    float* d_boxes = c->d_small[slot];
+    float* d_center = d_boxes + 4 * m;
+    float* d_scale = d_center + 2 * m;
+    float* d_rot = d_scale + 2 * m;
+    PC_CUDA(cudaMemcpyAsync(d_src, h_images + i0 * src_bytes, (size_t)(m * src_bytes),
+                            cudaMemcpyHostToDevice, st));
+    PC_CUDA(cudaMemcpyAsync(d_boxes, h_boxes + 4 * i0, sizeof(float) * 4 * m,
+                            cudaMemcpyHostToDevice, st));
+    if (h_rot)
+      PC_CUDA(cudaMemcpyAsync(d_rot, h_rot + i0, sizeof(float) * m, cudaMemcpyHostToDevice, st));
+    PC_CUDA(cudaMemcpyAsync(d_off, h_off, sizeof(int64_t) * m, cudaMemcpyHostToDevice, st));
+    PC_CUDA(cudaMemcpyAsync(d_hw, h_hw, sizeof(int32_t) * 2 * m, cudaMemcpyHostToDevice, st));
+    rc = pc_box_to_center_scale(d_boxes, d_center, d_scale, &bp, m, st);
+    if (rc == PC_OK)
+      rc = pc_affine_matrices(d_center, d_scale, h_rot ? d_rot : nullptr, d_fwd, d_inv, &ap, m,
+                              st);
+    if (rc == PC_OK) rc = pc_warp_affine_u8(d_src, d_off, d_hw, d_inv, d_dst, &wp, m, st);
+    if (rc != PC_OK) break;
+    PC_CUDA(cudaMemcpyAsync(h_crops + i0 * dst_bytes, d_dst, (size_t)(m * dst_bytes),
+                            cudaMemcpyDeviceToHost, st));
+    if (h_center)
+      PC_CUDA(cudaMemcpyAsync(h_center + 2 * i0, d_center, sizeof(float) * 2 * m,
+                              cudaMemcpyDeviceToHost, st));
+    if (h_scale)
+      PC_CUDA(cudaMemcpyAsync(h_scale + 2 * i0, d_scale, sizeof(float) * 2 * m,
+                              cudaMemcpyDeviceToHost, st));
   }
   cudaError_t e0 = cudaStreamSynchronize(c->stream[0]);
   cudaError_t e1 = cudaStreamSynchronize(c->stream[1]);

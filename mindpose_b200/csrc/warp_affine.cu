@@ -178,11 +178,12 @@ __global__ void affine_joints_kernel(float* __restrict__ kps, const double* __re
     kp[0] = (float)__dadd_rn(__dadd_rn(__dmul_rn(m[0], xd), __dmul_rn(m[1], yd)), m[2]);
     kp[1] = (float)__dadd_rn(__dadd_rn(__dmul_rn(m[3], xd), __dmul_rn(m[4], yd)), m[5]);
   } else {
-    // np.dot([x, y, 1] float32, M.T float32): float32 products, float32 sums
+    // np.dot([x, y, 1] float32, M.T float32) runs in BLAS sgemm: a k-ordered
+    // chain of float32 fused multiply-adds (verified against numpy/OpenBLAS)
     const float m0 = (float)m[0], m1 = (float)m[1], m2 = (float)m[2];
     const float m3 = (float)m[3], m4 = (float)m[4], m5 = (float)m[5];
-    kp[0] = __fadd_rn(__fadd_rn(__fmul_rn(x, m0), __fmul_rn(y, m1)), m2);
-    kp[1] = __fadd_rn(__fadd_rn(__fmul_rn(x, m3), __fmul_rn(y, m4)), m5);
+    kp[0] = __fmaf_rn(1.0f, m2, __fmaf_rn(y, m1, __fmul_rn(x, m0)));
+    kp[1] = __fmaf_rn(1.0f, m5, __fmaf_rn(y, m4, __fmul_rn(x, m3)));
   }
 }
 

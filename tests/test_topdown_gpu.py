@@ -246,7 +246,8 @@ def test_geometry_matches_oracle(cuda_device, golden):
         assert np.abs(k_std.cpu().numpy() - g[f"kps_std_{tag}"]).max() == 0
         k_udp = codec.affine_joints(_t(g["kps_in"], dev).clone(),
                                     _t(g[f"udp_{tag}"].astype(np.float64), dev), True)
-        assert np.abs(k_udp.cpu().numpy() - g[f"kps_udp_{tag}"]).max() <= 1e-4
+        # sgemm accumulation order is the BLAS build's; 2 ulp is the bar, 0 is what we see
+        assert np.allclose(k_udp.cpu().numpy(), g[f"kps_udp_{tag}"], rtol=3e-7, atol=1e-5)
 
 
 def test_warp_matches_cv2_golden(cuda_device, golden):
