@@ -150,6 +150,12 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
       if (k == 0) sc = __ldg(a.score + n);
     }
 
+    // Stages and consumer warps are decoupled (7 warps, up to 12 stages), and bulk
+    // copies complete out of order, so this warp can reach stage s for round r while
+    // round r-1 of the same stage (another warp's item) has not even landed.  A
+    // parity wait may only ever be one phase ahead of its barrier: first make sure
+    // round r-1 of this stage was consumed, then wait for round r to land.
+    if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
     mbar_wait(&full_bar[s], round & 1);
     const float* hm = stage_base + (size_t)s * a.stage_floats;
     const float* fm = hm + HW;
