@@ -1,13 +1,137 @@
-"""Bottom-up codec entry points (placeholder until the kernels land)."""
+"""Bottom-up codec entry points: fused decode, tag grouping, back-projection
+(torch CUDA tensors; one libposecodec call each)."""
+import ctypes
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
 
 
-def decode(decoder, heatmap, tagging_heatmap, mask, raw=None):
-    raise NotImplementedError("bottom-up decode kernel not built yet")
+def _same_storage_view(view: torch.Tensor, base: torch.Tensor, start_channel: int) -> bool:
+    """True if `view` is `base[:, start_channel:start_channel + C]` of a contiguous base."""
+    if not base.is_contiguous() or view.dim() != 4 or base.dim() != 4:
+        return False
+    plane = base.shape[2] * base.shape[3]
+    return (view.data_ptr() == base.data_ptr() + start_channel * plane * base.element_size()
+            and view.stride() == base.stride() and view.shape[0] == base.shape[0]
+            and view.shape[2:] == base.shape[2:])
 
 
-def group_by_tag(*args, **kwargs):
-    raise NotImplementedError("grouping kernel not built yet")
+def decode(decoder, heatmap: List[torch.Tensor], tagging_heatmap: List[torch.Tensor],
+           mask: torch.Tensor, raw: Optional[List[torch.Tensor]] = None):
+    """``BottomUpHeatMapAEDecoder.decode``.  ``heatmap`` / ``tagging_heatmap`` are the
+    lists ``decouple_output`` returns (channel views of the network outputs); the
+    kernel reads the network outputs in place, so the views must come from
+    ``decouple_output`` (or ``raw`` must hold the outputs they were cut from)."""
+    k = decoder.num_joints
+    stages = decoder.num_stages
+    if stages not in (1, 2):
+        raise ValueError("num_stages must be 1 or 2")
+    if list(decoder.with_ae_loss[:stages]) != ([True, False][:stages]) or not decoder.tag_per_joint:
+        raise ValueError("the CUDA decoder supports with_ae_loss=[True, False], tag_per_joint=True")
+    if len(heatmap) != stages or len(tagging_heatmap) != 1:
+        raise ValueError("expected one heatmap per stage and one tag map")
+    # recover the contiguous network outputs the views were sliced from
+    if raw is not None:
+        out0 = raw[0]
+        out1 = raw[1] if stages == 2 else None
+    else:
+        out0 = heatmap[0]._base if heatmap[0]._base is not None else None
+        out1 = None
+        if stages == 2:
+            out1 = heatmap[1]._base if heatmap[1]._base is not None else heatmap[1]
+    if out0 is None or not _same_storage_view(heatmap[0], out0, 0) \
+            or not _same_storage_view(tagging_heatmap[0], out0, k) or out0.shape[1] != 2 * k:
+        # views of something else: pack heat | tag into one contiguous tensor
+        out0 = torch.cat([heatmap[0], tagging_heatmap[0]], dim=1).contiguous()
+    if stages == 2:
+        if out1 is None or out1.shape[1] != k or not out1.is_contiguous():
+            out1 = heatmap[1].contiguous()
+    for t in (out0, out1):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise ValueError("network outputs must be float32 CUDA tensors")
+    n = out0.shape[0]
+    if stages == 2:
+        h0, w0 = out0.shape[2:]
+        h1, w1 = out1.shape[2:]
+    else:
+        h0 = w0 = 0
+        h1, w1 = out0.shape[2:]
+    if not mask.is_cuda:
+        raise ValueError("`mask` must live on a CUDA device")
+    mask_u8 = (mask != 0).to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
+    mh, mw = mask_u8.shape[1:]
+    m = decoder.max_num
+    dev = out0.device
+    val_k = torch.empty((n, k, m), dtype=torch.float32, device=dev)
+    tag_k = torch.empty((n, k, m, 1), dtype=torch.float32, device=dev)
+    ind_k = torch.empty((n, k, m, 2), dtype=torch.float32, device=dev)
+    raw_map = tag_map = None
+    if getattr(decoder, "return_maps", True):
+        raw_map = torch.empty((n, k, h1, w1), dtype=torch.float32, device=dev)
+        tag_map = torch.empty((n, k, h1, w1, 1), dtype=torch.float32, device=dev)
+    p = _lib.BottomUpDecodeParams(k, stages, h0, w0, h1, w1, mh, mw, int(bool(decoder.use_nms)),
+                                  int(decoder.nms_kernel), m, int(bool(decoder.shift_coordinate)))
+    with torch.cuda.device(dev):
+        _lib.call("pc_bottomup_decode", _lib.device_ptr(out0), _lib.device_ptr(out1),
+                  _lib.device_ptr(mask_u8), _lib.device_ptr(val_k), _lib.device_ptr(tag_k),
+                  _lib.device_ptr(ind_k), _lib.device_ptr(raw_map), _lib.device_ptr(tag_map),
+                  ctypes.byref(p), n, _lib.current_stream())
+    return val_k, tag_k, ind_k, raw_map, tag_map
 
 
-def transform_keypoints(*args, **kwargs):
-    raise NotImplementedError("grouping kernel not built yet")
+def group_by_tag(val_k: torch.Tensor, tag_k: torch.Tensor, ind_k: torch.Tensor,
+                 joint_order: Sequence[int], vis_thr: float = 0.1, tag_thr: float = 1.0,
+                 ignore_too_much: bool = False, use_rounded_norm: bool = True):
+    """Batched ``match_by_tag`` + instance score.
+
+    -> (ans f32 [N, PC_MAX_GROUPS, K, 4], num_groups i32 [N], scores f32 [N, PC_MAX_GROUPS]);
+    image i has ``num_groups[i]`` people in ``ans[i, :num_groups[i]]`` (insertion order);
+    -1 flags more people than PC_MAX_GROUPS."""
+    for t in (val_k, tag_k, ind_k):
+        if not (t.is_cuda and t.dtype == torch.float32):
+            raise ValueError("val_k / tag_k / ind_k must be float32 CUDA tensors")
+    n, k, m = val_k.shape
+    if tag_k.shape != (n, k, m, 1):
+        raise ValueError("the CUDA grouping supports one tag channel (tag_k [N,K,M,1])")
+    val_k, tag_k, ind_k = val_k.contiguous(), tag_k.contiguous(), ind_k.contiguous()
+    dev = val_k.device
+    g = _lib.PC_MAX_GROUPS
+    ans = torch.empty((n, g, k, 4), dtype=torch.float32, device=dev)
+    num = torch.empty((n,), dtype=torch.int32, device=dev)
+    scores = torch.zeros((n, g), dtype=torch.float32, device=dev)
+    p = _lib.GroupParams()
+    p.num_joints, p.max_num = k, m
+    p.vis_thr, p.tag_thr = float(vis_thr), float(tag_thr)
+    p.ignore_too_much, p.use_rounded_norm = int(bool(ignore_too_much)), int(bool(use_rounded_norm))
+    order = list(joint_order)
+    if len(order) != k:
+        raise ValueError("`joint_order` must list every joint once")
+    for i, j in enumerate(order):
+        p.joint_order[i] = int(j)
+    with torch.cuda.device(dev):
+        _lib.call("pc_group_by_tag", _lib.device_ptr(val_k), _lib.device_ptr(tag_k),
+                  _lib.device_ptr(ind_k), _lib.device_ptr(ans), _lib.device_ptr(num),
+                  _lib.device_ptr(scores), ctypes.byref(p), n, _lib.current_stream())
+    return ans, num, scores
+
+
+def transform_keypoints(ans: torch.Tensor, num_groups: torch.Tensor, center, scale, heatmap_wh,
+                        pixel_std: float = 200.0) -> torch.Tensor:
+    """In-place back-projection of grouped people (utils.py:235-274). center / scale /
+    heatmap_wh: [N,2] (any float dtype; used as float64 like the reference's numpy)."""
+    dev = ans.device
+
+    def f64(x):
+        return torch.as_tensor(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x),
+                               dtype=torch.float64).reshape(-1, 2).to(dev).contiguous()
+
+    n, _, k, _ = ans.shape
+    c, s, hw = f64(center), f64(scale), f64(heatmap_wh)
+    with torch.cuda.device(dev):
+        _lib.call("pc_transform_keypoints", _lib.device_ptr(ans), _lib.device_ptr(num_groups),
+                  _lib.device_ptr(c), _lib.device_ptr(s), _lib.device_ptr(hw), float(pixel_std),
+                  k, n, _lib.current_stream())
+    return ans

@@ -1,0 +1,99 @@
+"""Bottom-up half of oracle/gen_golden.py (see there)."""
+import os
+
+import numpy as np
+
+from mindpose_b200 import synth
+
+
+def grouping_inputs(seed, n, k=17, m=30, mode="people"):
+    """Synthetic (val_k, tag_k, ind_k) batches that exercise match_by_tag."""
+    rng = np.random.RandomState(seed)
+    val = np.zeros((n, k, m), np.float32)
+    tag = np.zeros((n, k, m, 1), np.float32)
+    ind = np.zeros((n, k, m, 2), np.float32)
+    for i in range(n):
+        people = rng.randint(0, 14)
+        for j in range(k):
+            ids = rng.permutation(people)
+            ndet = 0
+            for pid in ids:
+                if rng.random_sample() < 0.2 or ndet >= m:
+                    continue
+                if mode == "people":
+                    t = pid * 3.0 + rng.normal(0, 0.15)
+                elif mode == "ties":      # integer tags: rounded distances tie everywhere
+                    t = float(pid % 5) + (0.0 if rng.random_sample() < 0.7 else 0.5)
+                else:                      # "crowded": tags close together
+                    t = pid * 0.6 + rng.normal(0, 0.2)
+                val[i, j, ndet] = rng.uniform(0.05, 1.0)
+                tag[i, j, ndet, 0] = t
+                ind[i, j, ndet] = rng.randint(0, 256, 2)
+                ndet += 1
+            # spurious low / high detections
+            extra = rng.randint(0, 4)
+            for _ in range(extra):
+                if ndet >= m:
+                    break
+                val[i, j, ndet] = rng.uniform(0.0, 0.5)
+                tag[i, j, ndet, 0] = rng.uniform(-1, 40) if mode != "ties" else float(rng.randint(0, 6))
+                ind[i, j, ndet] = rng.randint(0, 256, 2)
+                ndet += 1
+            order = np.argsort(-val[i, j], kind="stable")
+            val[i, j] = val[i, j][order]
+            tag[i, j] = tag[i, j][order]
+            ind[i, j] = ind[i, j][order]
+    return val, tag, ind
+
+
+def main(ns, golden_dir):
+    import scipy.optimize
+
+    # ---- scipy LSAP on tie-heavy matrices
+    rng = np.random.RandomState(3)
+    shapes, flat, rows, cols = [], [], [], []
+    for it in range(300):
+        nr, nc = rng.randint(1, 14), rng.randint(1, 16)
+        if it % 3 == 0:
+            c = rng.randint(0, 3, (nr, nc)).astype(np.float64)
+        elif it % 3 == 1:
+            c = np.round(rng.uniform(0, 5, (nr, nc)))
+            if nc < nr:
+                c = np.concatenate([c, np.zeros((nr, nr - nc)) + 1e10], axis=1)
+        else:
+            c = rng.uniform(0, 5, (nr, nc))
+        r, cc = scipy.optimize.linear_sum_assignment(c)
+        shapes.append(c.shape)
+        flat.append(c.reshape(-1))
+        rows.append(r)
+        cols.append(cc)
+    np.savez_compressed(
+        os.path.join(golden_dir, "lsap_ref.npz"), shapes=np.array(shapes),
+        cost=np.concatenate(flat), rows=np.concatenate(rows), cols=np.concatenate(cols),
+        scipy_version=np.array(scipy.__version__))
+
+    # ---- reference match_by_tag
+    out = {}
+    for mode, seed in (("people", 1), ("ties", 2), ("crowded", 3)):
+        val, tag, ind = grouping_inputs(seed, 24, mode=mode)
+        out[f"val_{mode}"], out[f"tag_{mode}"], out[f"ind_{mode}"] = val, tag, ind
+        for rounded in (True, False):
+            res = [ns.match.match_by_tag(v, t, x, synth.COCO_JOINT_ORDER, vis_thr=0.1, tag_thr=1.0,
+                                         ignore_too_much=False, use_rounded_norm=rounded)
+                   for v, t, x in zip(val, tag, ind)]
+            counts = np.array([0 if r.ndim == 1 else r.shape[0] for r in res])
+            body = [r.reshape(-1) for r in res if r.ndim == 3]
+            name = f"{mode}_{'rounded' if rounded else 'exact'}"
+            out[f"counts_{name}"] = counts
+            out[f"ans_{name}"] = np.concatenate(body) if body else np.zeros(0, np.float32)
+    np.savez_compressed(os.path.join(golden_dir, "match_ref.npz"), **out)
+
+    # ---- restated bottom-up decode, frozen
+    from oracle import bottomup_decode as bd
+
+    d = synth.bottomup_outputs(2, 17, 32, 32, mask_hw=(128, 128), seed=4, max_people=4)
+    val_k, tag_k, ind_k, raw, tagging = bd.decode([d["out0"], d["out1"]], d["mask"], use_nms=True,
+                                                  nms_kernel=3, max_num=30)
+    np.savez_compressed(os.path.join(golden_dir, "bottomup_decode_restated.npz"),
+                        val_k=val_k, tag_k=tag_k, ind_k=ind_k,
+                        raw_sum=raw.sum(axis=(2, 3)), tag_sum=tagging.sum(axis=(2, 3, 4)))

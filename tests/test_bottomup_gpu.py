@@ -1,0 +1,208 @@
+"""Parity of the CUDA bottom-up codec (decode, grouping, back-projection) against the
+oracle (B200 only).  Bars: top-k values / indices and grouping assignments bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import mindpose_b200 as mp
+from mindpose_b200 import bottomup, synth
+from oracle import bottomup_decode as bd
+from oracle import grouping
+from oracle.gen_golden_bottomup import grouping_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _split_counts(flat, counts, k=17, width=4):
+    out, off = [], 0
+    for c in counts:
+        size = int(c) * k * width
+        out.append(flat[off:off + size].reshape(int(c), k, width))
+        off += size
+    return out
+
+
+@pytest.mark.parametrize("h0,mask_hw,use_nms,nms_kernel", [
+    (32, (128, 128), True, 3), (32, (128, 128), False, 5), (64, (256, 256), True, 5),
+    (48, (100, 210), True, 3)])
+def test_decode_matches_oracle(cuda_device, h0, mask_hw, use_nms, nms_kernel):
+    n = 3
+    d = synth.bottomup_outputs(n, 17, h0, h0, mask_hw=mask_hw, seed=h0, max_people=5)
+    want = bd.decode([d["out0"], d["out1"]], d["mask"], use_nms=use_nms, nms_kernel=nms_kernel,
+                     max_num=30)
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=use_nms, nms_kernel=nms_kernel,
+                            max_num=30)
+    got = dec([_t(d["out0"], cuda_device), _t(d["out1"], cuda_device)], _t(d["mask"], cuda_device))
+    names = ["val_k", "tag_k", "ind_k", "heatmap_raw", "tagging_heatmap"]
+    assert len(got) == 5
+    for name, g, w in zip(names, got, want):
+        assert g.shape == w.shape, name
+        assert np.array_equal(g.cpu().numpy(), w), name
+
+
+def test_decode_single_stage_and_public_decode(cuda_device):
+    n, k, h = 2, 17, 64
+    rng = np.random.RandomState(0)
+    out0 = rng.uniform(-0.2, 1, (n, 2 * k, h, h)).astype(np.float32)
+    mask = (rng.random_sample((n, 128, 128)) > 0.1).astype(np.uint8)
+    want = bd.decode([out0], mask, num_stages=1, with_ae_loss=(True,), use_nms=True,
+                     nms_kernel=3, max_num=20)
+    dec = mp.create_decoder("bottomup_heatmap_ae", num_stages=1, with_ae_loss=[True],
+                            use_nms=True, nms_kernel=3, max_num=20)
+    t0 = _t(out0, cuda_device)
+    heat, tag = dec.decouple_output([t0])
+    assert heat[0].shape == (n, k, h, h) and tag[0].shape == (n, k, h, h)
+    got = dec.decode(heat, tag, _t(mask, cuda_device))
+    for g, w in zip(got[:3], want[:3]):
+        assert np.array_equal(g.cpu().numpy(), w)
+
+
+def test_decode_ties_and_flat_maps(cuda_device):
+    """Constant / all-zero planes: every pixel survives NMS, top-k = lowest indices."""
+    n, k, h0 = 1, 17, 16
+    out0 = np.zeros((n, 2 * k, h0, h0), np.float32)
+    out1 = np.zeros((n, k, 2 * h0, 2 * h0), np.float32)
+    out1[0, 1] = 0.5
+    out1[0, 2, 5, 7] = out1[0, 2, 20, 3] = 0.9
+    out1[0, 3] = -0.3                        # negative plateau: zeros outrank it nowhere
+    out0[0, k:] = np.arange(h0 * h0, dtype=np.float32).reshape(h0, h0)
+    mask = np.ones((n, 4 * h0, 4 * h0), np.uint8)
+    mask[0, :8, :] = 0
+    want = bd.decode([out0, out1], mask, use_nms=True, nms_kernel=3, max_num=30)
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3, max_num=30)
+    got = dec([_t(out0, cuda_device), _t(out1, cuda_device)], _t(mask, cuda_device))
+    for g, w in zip(got[:3], want[:3]):
+        assert np.array_equal(g.cpu().numpy(), w)
+
+
+def test_decode_full_size_properties(cuda_device):
+    """BASELINE config 4 shapes (64 x [34,128,128] + [17,256,256], 512^2 mask): values sorted,
+    indices in range and consistent with heatmap_raw; spot-check 2 images against the oracle."""
+    n = 64
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(0)
+    out0 = torch.rand(n, 34, 128, 128, device=dev, generator=g) * 0.02
+    out1 = torch.rand(n, 17, 256, 256, device=dev, generator=g) * 0.02
+    ys = torch.randint(8, 248, (n, 17, 6), device=dev, generator=g)
+    xs = torch.randint(8, 248, (n, 17, 6), device=dev, generator=g)
+    for j in range(6):
+        out1[torch.arange(n)[:, None], torch.arange(17)[None, :], ys[..., j], xs[..., j]] += 0.5 + 0.05 * j
+    mask = torch.ones(n, 512, 512, dtype=torch.uint8, device=dev)
+    mask[:, 100:140, 200:260] = 0
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3, max_num=30)
+    val_k, tag_k, ind_k, raw, tagging = dec([out0, out1], mask)
+    assert torch.all(val_k[..., :-1] >= val_k[..., 1:])
+    x, y = ind_k[..., 0].long(), ind_k[..., 1].long()
+    assert x.min() >= 0 and x.max() < 256 and y.min() >= 0 and y.max() < 256
+    picked = raw.reshape(n, 17, -1).gather(2, y * 256 + x)
+    assert torch.equal(picked, val_k)          # survivors keep their raw value
+    assert torch.equal(tagging.reshape(n, 17, -1).gather(2, y * 256 + x), tag_k[..., 0])
+    sel = [0, 63]
+    want = bd.decode([out0[sel].cpu().numpy(), out1[sel].cpu().numpy()], mask[sel].cpu().numpy(),
+                     use_nms=True, nms_kernel=3, max_num=30)
+    for gt, w in zip((val_k, tag_k, ind_k), want[:3]):
+        assert np.array_equal(gt[sel].cpu().numpy(), w)
+
+
+def test_decode_rejects_unsupported(cuda_device):
+    dec = mp.create_decoder("bottomup_heatmap_ae", shift_coordinate=True)
+    z0 = torch.zeros(1, 34, 16, 16, device=cuda_device)
+    z1 = torch.zeros(1, 17, 32, 32, device=cuda_device)
+    with pytest.raises(ValueError, match="shift_coordinate"):
+        dec([z0, z1], torch.ones(1, 64, 64, dtype=torch.uint8, device=cuda_device))
+
+
+# ------------------------------------------------------------------- grouping
+@pytest.mark.parametrize("mode", ["people", "ties", "crowded"])
+@pytest.mark.parametrize("rounded", [True, False])
+def test_grouping_matches_reference_golden(cuda_device, golden, mode, rounded):
+    g = golden("match_ref.npz")
+    name = f"{mode}_{'rounded' if rounded else 'exact'}"
+    want = _split_counts(g[f"ans_{name}"], g[f"counts_{name}"])
+    val, tag, ind = g[f"val_{mode}"], g[f"tag_{mode}"], g[f"ind_{mode}"]
+    ans, num, scores = bottomup.group_by_tag(
+        _t(val, cuda_device), _t(tag, cuda_device), _t(ind, cuda_device),
+        synth.COCO_JOINT_ORDER, vis_thr=0.1, tag_thr=1.0, use_rounded_norm=rounded)
+    ans, num, scores = ans.cpu().numpy(), num.cpu().numpy(), scores.cpu().numpy()
+    for i in range(val.shape[0]):
+        assert num[i] == want[i].shape[0], (mode, rounded, i)
+        assert np.array_equal(ans[i, :num[i]], want[i]), (mode, rounded, i)
+        assert scores[i, :num[i]].tolist() == [y[:, 2].mean() for y in want[i]]
+
+
+def test_grouping_matches_oracle_on_fresh_inputs(cuda_device):
+    for mode, seed in (("people", 101), ("ties", 102), ("crowded", 103)):
+        val, tag, ind = grouping_inputs(seed, 40, mode=mode)
+        ans, num, scores = bottomup.group_by_tag(
+            _t(val, cuda_device), _t(tag, cuda_device), _t(ind, cuda_device),
+            synth.COCO_JOINT_ORDER, ignore_too_much=(mode == "crowded"))
+        ans, num = ans.cpu().numpy(), num.cpu().numpy()
+        for i in range(val.shape[0]):
+            want = grouping.match_by_tag(val[i], tag[i], ind[i], synth.COCO_JOINT_ORDER,
+                                         ignore_too_much=(mode == "crowded"))
+            p = 0 if want.ndim == 1 else want.shape[0]
+            assert num[i] == p
+            if p:
+                assert np.array_equal(ans[i, :p], want)
+
+
+def test_grouping_empty_and_collisions(cuda_device):
+    val = np.zeros((2, 17, 30), np.float32)
+    tag = np.zeros((2, 17, 30, 1), np.float32)
+    ind = np.zeros((2, 17, 30, 2), np.float32)
+    val[1, 0, :2] = [0.9, 0.8]
+    tag[1, 0, :2, 0] = [5.0, 5.0]          # equal keys: one group, later detection wins
+    ind[1, 0, 0] = [1, 2]
+    ind[1, 0, 1] = [3, 4]
+    ans, num, _ = bottomup.group_by_tag(_t(val, cuda_device), _t(tag, cuda_device),
+                                        _t(ind, cuda_device), synth.COCO_JOINT_ORDER)
+    assert num.tolist() == [0, 1]
+    assert ans[1, 0, 0].tolist() == [3.0, 4.0, np.float32(0.8), 5.0]
+
+
+def test_transform_keypoints_matches_oracle(cuda_device):
+    val, tag, ind = grouping_inputs(7, 6, mode="people")
+    ans, num, _ = bottomup.group_by_tag(_t(val, cuda_device), _t(tag, cuda_device),
+                                        _t(ind, cuda_device), synth.COCO_JOINT_ORDER)
+    rng = np.random.RandomState(0)
+    center = rng.uniform(100, 400, (6, 2))
+    scale = rng.uniform(1, 3.2, (6, 2))
+    hw = np.tile(np.array([[256.0, 256.0]]), (6, 1))
+    before = [ans[i, :int(num[i])].cpu().numpy() for i in range(6)]
+    want = grouping.transform_keypoints(before, center, scale, hw, pixel_std=200.0)
+    bottomup.transform_keypoints(ans, num, center, scale, hw, pixel_std=200.0)
+    for i in range(6):
+        assert np.array_equal(ans[i, :int(num[i])].cpu().numpy(), want[i])
+
+
+def test_bottomup_inferencer_end_to_end(cuda_device):
+    """decode -> group -> score -> back-project through the registry classes."""
+    d = synth.bottomup_outputs(2, 17, 32, 32, mask_hw=(128, 128), seed=11, max_people=4)
+    dev = cuda_device
+    out = [_t(d["out0"], dev), _t(d["out1"], dev)]
+    cfg = dict(has_heatmap_output=True, hflip_tta=False, joint_order=synth.COCO_JOINT_ORDER,
+               vis_thr=0.1, ignore_too_much=False, use_rounded_norm=True, tag_thr=1.0,
+               pixel_std=200.0, downsample_scale=2, refine_missing_joint=False,
+               flip_pairs=synth.COCO_FLIP_PAIRS)
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3)
+    inf = mp.create_inferencer(lambda image: out, "bottomup_heatmap_ae", config=cfg, decoder=dec)
+    center = np.array([[64.0, 64.0], [60.0, 70.0]])
+    scale = np.array([[0.64, 0.64], [0.7, 0.7]])
+    shape = np.array([[128.0, 128.0], [128.0, 128.0]])
+    data = dict(image=None, mask=_t(d["mask"], dev), center=center, scale=scale,
+                image_shape=shape, image_file=["a.jpg", "b.jpg"])
+    records = inf([data])
+    val_k, tag_k, ind_k, _, _ = bd.decode([d["out0"], d["out1"]], d["mask"], use_nms=True,
+                                          nms_kernel=3, max_num=30)
+    people = [grouping.match_by_tag(val_k[i], tag_k[i], ind_k[i], synth.COCO_JOINT_ORDER)
+              for i in range(2)]
+    people = [p if p.ndim == 3 else np.zeros((0, 17, 4), np.float32) for p in people]
+    want = grouping.transform_keypoints(people, center, scale, shape / 2, pixel_std=200.0)
+    assert len(records) == 2
+    for rec, w, p in zip(records, want, people):
+        assert np.array_equal(rec["pred"], w)
+        assert rec["score"] == [y[:, 2].mean() for y in p]
