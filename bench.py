@@ -189,6 +189,7 @@ def run_ours(args, wl):
 
     import mindpose_b200 as mp
     from mindpose_b200 import _lib, codec, synth
+    from mindpose_b200 import dist as pdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -245,7 +246,6 @@ def run_ours(args, wl):
     crops = torch.empty(n, ih, iw, 3, device=dev, dtype=torch.uint8)
     off = torch.arange(n, device=dev, dtype=torch.int64) * (hs * ws * 3)
     src_hw = torch.tensor([hs, ws], device=dev, dtype=torch.int32).repeat(n, 1).contiguous()
-    gathered = torch.empty(world * n, k * 3 + 6, device=dev) if world > 1 else None
 
     stream = torch.cuda.current_stream()
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -265,8 +265,7 @@ def run_ours(args, wl):
             e2.record(stream)
             marks.append((e0, e1, e2))
         if world > 1:
-            local = torch.cat([preds.reshape(n, -1), bxs], dim=1)
-            dist.all_gather_into_tensor(gathered, local)
+            pdist.all_gather_keypoints(preds, bxs, world * n)
         return preds, bxs
 
     def fence():

@@ -70,20 +70,50 @@ __device__ __forceinline__ void invert_affine_cv(const double* m, double* o) {
   o[5] = b2;
 }
 
-// Exact-arithmetic-free 3-point affine solve (Cramer, fp64): M @ [s;1] = d.
-__device__ __forceinline__ void solve_three_points(const double s[3][2], const double d[3][2],
-                                                   double* m) {
-  const double x0 = s[0][0], y0 = s[0][1], x1 = s[1][0], y1 = s[1][1], x2 = s[2][0],
-               y2 = s[2][1];
-  const double det = x0 * (y1 - y2) - y0 * (x1 - x2) + (x1 * y2 - x2 * y1);
-  const double inv = 1.0 / det;
-  for (int r = 0; r < 2; ++r) {
-    const double u0 = d[0][r], u1 = d[1][r], u2 = d[2][r];
-    m[3 * r + 0] = (u0 * (y1 - y2) - y0 * (u1 - u2) + (u1 * y2 - u2 * y1)) * inv;
-    m[3 * r + 1] = (x0 * (u1 - u2) - u0 * (x1 - x2) + (x1 * u2 - x2 * u1)) * inv;
-    m[3 * r + 2] = (x0 * (y1 * u2 - y2 * u1) - y0 * (x1 * u2 - x2 * u1) +
-                    u0 * (x1 * y2 - x2 * y1)) * inv;
+// cv2.getAffineTransform, op for op: the 6x6 system [x y 1 0 0 0; 0 0 0 x y 1] m = d
+// solved by OpenCV's in-house LU (partial pivoting, no fused multiply-add).  The
+// crop translation often makes the warp's fixed-point rounding an exact tie (the
+// inverse translation is a float32 value, so b * 1024 has only ~6 fractional
+// bits), and a last-bit difference in the matrix then moves every pixel of the
+// crop; reproducing the solver bit for bit is what makes the warp bit-exact.
+__device__ void solve_three_points(const double s[3][2], const double d[3][2], double* m) {
+  double A[6][6], b[6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) A[i][j] = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    A[2 * i][0] = A[2 * i + 1][3] = s[i][0];
+    A[2 * i][1] = A[2 * i + 1][4] = s[i][1];
+    A[2 * i][2] = A[2 * i + 1][5] = 1.0;
+    b[2 * i] = d[i][0];
+    b[2 * i + 1] = d[i][1];
   }
+  for (int i = 0; i < 6; ++i) {
+    int k = i;
+    for (int j = i + 1; j < 6; ++j)
+      if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+    if (k != i) {
+      for (int j = i; j < 6; ++j) {
+        const double t = A[i][j];
+        A[i][j] = A[k][j];
+        A[k][j] = t;
+      }
+      const double t = b[i];
+      b[i] = b[k];
+      b[k] = t;
+    }
+    const double dd = __ddiv_rn(-1.0, A[i][i]);
+    for (int j = i + 1; j < 6; ++j) {
+      const double alpha = __dmul_rn(A[j][i], dd);
+      for (int c = i + 1; c < 6; ++c) A[j][c] = __dadd_rn(A[j][c], __dmul_rn(alpha, A[i][c]));
+      b[j] = __dadd_rn(b[j], __dmul_rn(alpha, b[i]));
+    }
+  }
+  for (int i = 5; i >= 0; --i) {
+    double acc = b[i];
+    for (int c = i + 1; c < 6; ++c) acc = __dsub_rn(acc, __dmul_rn(A[i][c], b[c]));
+    b[i] = __ddiv_rn(acc, A[i][i]);
+  }
+  for (int c = 0; c < 6; ++c) m[c] = b[c];
 }
 
 __global__ void affine_matrices_kernel(const float* __restrict__ center,

@@ -9,8 +9,8 @@ Restates, in numpy, the scalar geometry the reference does on the host:
   (mindpose/data/transform/utils.py:44-98, with ``rotate_point`` :117 and
   ``_get_3rd_point`` :136).  The three source / destination points are stored
   in float32 exactly as the reference does (:83-91); the 3-point solve that the
-  reference delegates to ``cv2.getAffineTransform`` (third-party, SVD solve in
-  fp64) is done here with ``numpy.linalg.solve`` in fp64.
+  reference delegates to ``cv2.getAffineTransform`` (third-party) is restated
+  op for op (6x6 LU with partial pivoting, fp64).
 * ``udp_matrix``           -- ``get_warp_matrix`` (utils.py:158-190), float32
   result, as called by ``TopDownAffine._udp_affine``
   (topdown_transform.py:239-244).
@@ -43,10 +43,40 @@ def _third_point(a, b):
 
 
 def _solve_three_points(src, dst):
-    """2x3 fp64 matrix M with M @ [sx, sy, 1] = [dx, dy] for the 3 pairs."""
-    a = np.concatenate([src.astype(np.float64), np.ones((3, 1))], axis=1)
-    sol = np.linalg.solve(a, dst.astype(np.float64))  # [3, 2]
-    return np.ascontiguousarray(sol.T)
+    """``cv2.getAffineTransform`` restated: the 6x6 system
+    ``[x y 1 0 0 0; 0 0 0 x y 1] m = d`` solved by OpenCV's in-house LU with partial
+    pivoting in fp64 (third-party algorithm, modules/core matrix_decomp ``LUImpl``).
+    Bit-identical to cv2 4.13.0 on the golden matrices; the last bit matters
+    because the warp's fixed-point rounding frequently sits on an exact tie."""
+    a = np.zeros((6, 6), dtype=np.float64)
+    b = np.zeros(6, dtype=np.float64)
+    for i in range(3):
+        a[2 * i, 0] = a[2 * i + 1, 3] = src[i, 0]
+        a[2 * i, 1] = a[2 * i + 1, 4] = src[i, 1]
+        a[2 * i, 2] = a[2 * i + 1, 5] = 1.0
+        b[2 * i] = dst[i, 0]
+        b[2 * i + 1] = dst[i, 1]
+    m = 6
+    for i in range(m):
+        k = i
+        for j in range(i + 1, m):
+            if abs(a[j, i]) > abs(a[k, i]):
+                k = j
+        if k != i:
+            a[[i, k], i:] = a[[k, i], i:]
+            b[[i, k]] = b[[k, i]]
+        d = -1.0 / a[i, i]
+        for j in range(i + 1, m):
+            alpha = a[j, i] * d
+            for c in range(i + 1, m):
+                a[j, c] = a[j, c] + alpha * a[i, c]
+            b[j] = b[j] + alpha * b[i]
+    for i in range(m - 1, -1, -1):
+        s = b[i]
+        for c in range(i + 1, m):
+            s = s - a[i, c] * b[c]
+        b[i] = s / a[i, i]
+    return b.reshape(2, 3).copy()
 
 
 def affine_matrix(center, scale, rot, output_size, pixel_std=200.0, inv=False):

@@ -1,0 +1,155 @@
+"""Per-kernel timing table (CUDA events, inputs >> L2, 3 warm-up + N timed launches).
+
+    python scripts/kbench.py [--iters 10] [--only decode,encode,warp,bottomup,group] [--json out]
+
+Reports algorithmic GB/s (SURVEY.md section 8(d) bytes per unit) and the fraction of the
+measured HBM copy peak (MEASURED_PEAKS.json).  Development aid; bench.py is the contract.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mindpose_b200 as mp  # noqa: E402
+from mindpose_b200 import bottomup, codec, synth  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def timeit(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(iters)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in evs]
+    return float(np.median(ms)), float(np.min(ms))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="decode,encode,warp,bottomup,group")
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    dev = torch.device("cuda", 0)
+    pk = peak()
+    rows = []
+
+    def report(name, units, unit_name, bytes_per_unit, ms_med, ms_min):
+        gbs = units * bytes_per_unit / (ms_med * 1e-3) / 1e9
+        rows.append(dict(kernel=name, units=units, unit=unit_name, ms=ms_med, ms_min=ms_min,
+                         per_s=units / (ms_med * 1e-3), gbs=gbs, frac=gbs / pk))
+        print(f"{name:46s} {ms_med:8.3f} ms  {units / (ms_med * 1e-3) / 1e6:8.3f} M{unit_name}/s "
+              f"{gbs:8.1f} GB/s  {gbs / pk:5.3f} of measured peak", flush=True)
+
+    k = 17
+    if "decode" in only:
+        for (h, w, n) in ((64, 48, 4096), (96, 72, 2048)):
+            hm = torch.rand(n, k, h, w, device=dev) * 0.02
+            fl = torch.rand(n, k, h, w, device=dev) * 0.02
+            ys = torch.randint(4, h - 4, (n, k), device=dev)
+            xs = torch.randint(4, w - 4, (n, k), device=dev)
+            ni = torch.arange(n, device=dev)[:, None]
+            ki = torch.arange(k, device=dev)[None, :]
+            for dy in range(-3, 4):
+                for dx in range(-3, 4):
+                    g = float(np.exp(-(dx * dx + dy * dy) / 8.0))
+                    hm[ni, ki, ys + dy, xs + dx] += 0.8 * g
+            center = torch.rand(n, 2, device=dev) * 400
+            scale = torch.rand(n, 2, device=dev) * 2.8 + 0.2
+            score = torch.rand(n, device=dev)
+            for mode, kw in (("plain", {}), ("quarter", dict(shift_coordinate=True)),
+                             ("dark", dict(dark_udp_refine=True))):
+                dec = mp.create_decoder("topdown_heatmap", **kw)
+                for flip in (False, True):
+                    if flip:
+                        p = dec._params(k, h, w, flip_index=synth.flip_index(), shift_heatmap=True)
+                        fn = lambda: codec.topdown_decode(hm, center, scale, score, flipped=fl, params=p)  # noqa: E731
+                    else:
+                        p = dec._params(k, h, w)
+                        fn = lambda: codec.topdown_decode(hm, center, scale, score, params=p)  # noqa: E731
+                    med, mn = timeit(fn, args.iters)
+                    bpu = k * h * w * 4 * (2 if flip else 1) + 228
+                    report(f"topdown_decode {h}x{w} {mode}{' flip' if flip else ''}", n, "crops",
+                           bpu, med, mn)
+            del hm, fl
+    if "encode" in only:
+        for cfg, n in ((synth.TOPDOWN_CONFIG, 8192), (synth.TOPDOWN_CONFIG_384, 4096)):
+            w, h = cfg["heatmap_size"]
+            kps = torch.from_numpy(synth.keypoints(n, k, cfg["image_size"], seed=0)).to(dev)
+            out = torch.empty(n, k, h, w, device=dev)
+            for udp in (False, True):
+                fn = lambda: codec.topdown_encode(kps, cfg["image_size"], cfg["heatmap_size"],  # noqa: E731
+                                                  sigma=2.0, use_udp=udp, out=out)
+                med, mn = timeit(fn, args.iters)
+                report(f"topdown_encode {h}x{w} {'udp' if udp else 'gaussian'}", n, "crops",
+                       k * h * w * 4 + 272, med, mn)
+            del out
+    if "warp" in only:
+        n, hs, ws = 4096, 480, 640
+        images = torch.randint(0, 256, (n, hs, ws, 3), device=dev, dtype=torch.uint8)
+        rng = np.random.RandomState(0)
+        bw, bh = rng.uniform(40, 400, n), rng.uniform(60, 440, n)
+        boxes = torch.from_numpy(np.stack([rng.uniform(0, 1, n) * (ws - bw),
+                                           rng.uniform(0, 1, n) * (hs - bh), bw, bh], 1)
+                                 .astype(np.float32)).to(dev)
+        center, scale = codec.box_to_center_scale(boxes, [192, 256])
+        _, inv = codec.affine_matrices(center, scale, None, [192, 256])
+        off = torch.arange(n, device=dev, dtype=torch.int64) * (hs * ws * 3)
+        hw = torch.tensor([hs, ws], device=dev, dtype=torch.int32).repeat(n, 1).contiguous()
+        out = torch.empty(n, 256, 192, 3, device=dev, dtype=torch.uint8)
+        fn = lambda: codec.warp_affine(images, off, hw, inv, [192, 256], out=out)  # noqa: E731
+        med, mn = timeit(fn, args.iters)
+        # source ROI = scale * 200 in each direction, clipped to the image
+        s = scale.cpu().numpy() * 200.0
+        c = center.cpu().numpy()
+        x0 = np.clip(c[:, 0] - s[:, 0] / 2, 0, ws)
+        x1 = np.clip(c[:, 0] + s[:, 0] / 2, 0, ws)
+        y0 = np.clip(c[:, 1] - s[:, 1] / 2, 0, hs)
+        y1 = np.clip(c[:, 1] + s[:, 1] / 2, 0, hs)
+        roi = float(np.mean((x1 - x0) * (y1 - y0) * 3))
+        report("warp_affine_u8 480x640 -> 256x192 (dst+ROI)", n, "crops", 147456 + roi, med, mn)
+        report("warp_affine_u8 (dst bytes only)", n, "crops", 147456, med, mn)
+        del images, out
+    if "bottomup" in only:
+        n = 64
+        g = torch.Generator(device=dev).manual_seed(0)
+        out0 = torch.rand(n, 34, 128, 128, device=dev, generator=g) * 0.02
+        out1 = torch.rand(n, 17, 256, 256, device=dev, generator=g) * 0.02
+        ys = torch.randint(8, 248, (n, 17, 8), device=dev, generator=g)
+        xs = torch.randint(8, 248, (n, 17, 8), device=dev, generator=g)
+        for j in range(8):
+            out1[torch.arange(n)[:, None], torch.arange(17)[None, :], ys[..., j], xs[..., j]] += 0.5
+        mask = torch.ones(n, 512, 512, dtype=torch.uint8, device=dev)
+        dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3, max_num=30)
+        dec.return_maps = False
+        fn = lambda: dec([out0, out1], mask)  # noqa: E731
+        med, mn = timeit(fn, args.iters)
+        report("bottomup_decode 64 x (34x128^2 + 17x256^2)", n, "images", 6946816 + 8160, med, mn)
+        if "group" in only:
+            val_k, tag_k, ind_k, _, _ = dec([out0, out1], mask)
+            fn = lambda: bottomup.group_by_tag(val_k, tag_k, ind_k, synth.COCO_JOINT_ORDER)  # noqa: E731
+            med, mn = timeit(fn, args.iters)
+            report("group_by_tag 64 images (latency bound)", n, "images", 8160, med, mn)
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(rows, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

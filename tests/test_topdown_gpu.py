@@ -231,6 +231,10 @@ def test_geometry_matches_oracle(cuda_device, golden):
         ref_std = np.stack([affine.affine_matrix(ci, si, float(np.float32(r)), np.array(image_size))
                             for ci, si, r in zip(g[f"center_{tag}"], g[f"scale_{tag}"], g["rots"])])
         fwd, inv = codec.affine_matrices(c, s, rot, image_size, use_udp=False)
+        zero_rot = g["rots"] == 0
+        # rot = 0 (the eval path): bit-identical to cv2.getAffineTransform; rot != 0 goes
+        # through the device's sin/cos (<= 1 ulp from numpy's before the float32 point store)
+        assert np.array_equal(fwd.cpu().numpy()[zero_rot], g[f"std_{tag}"][zero_rot])
         assert np.allclose(fwd.cpu().numpy(), ref_std, rtol=0, atol=1e-9 * np.abs(ref_std).max())
         want_inv = np.stack([warp.invert_affine(m) for m in fwd.cpu().numpy()])
         assert np.array_equal(inv.cpu().numpy(), want_inv)
@@ -238,7 +242,6 @@ def test_geometry_matches_oracle(cuda_device, golden):
                             for ci, si, r in zip(g[f"center_{tag}"], g[f"scale_{tag}"], g["rots"])])
         fwd_u, _ = codec.affine_matrices(c, s, rot, image_size, use_udp=True)
         fu = fwd_u.cpu().numpy()
-        zero_rot = g["rots"] == 0
         assert np.array_equal(fu[zero_rot], ref_udp[zero_rot].astype(np.float64))
         assert np.allclose(fu, ref_udp, rtol=2e-7, atol=1e-6)
         # joints through the reference's own matrices
