@@ -24,6 +24,7 @@ constexpr int kDecodeThreads = 256;
 constexpr int kConsumerWarps = kDecodeThreads / 32 - 1;
 constexpr int kMaxStages = 12;
 constexpr int kDarkSamples = 7;
+constexpr int kDarkWinMax = (PC_MAX_DARK_KERNEL + 2) * (PC_MAX_DARK_KERNEL + 2);
 
 struct DecodeArgs {
   const float* heatmap;
@@ -36,6 +37,9 @@ struct DecodeArgs {
   int64_t num_items;  // n * K
   int32_t K, H, W, HW;
   FastDiv divW, divK;
+  FastDiv divWq;           // W / 4 (float4 groups per row)
+  FastDiv divKs, divWin;   // DARK kernel size, window size ks + 2
+  int32_t step_xq, step_y;  // 32 float4 groups ahead = step_y rows + step_xq groups
   float pixel_std;
   int32_t to_original, use_udp;
   int32_t mode;  // 0 none, 1 quarter offset, 2 DARK/UDP
@@ -70,6 +74,49 @@ __device__ __forceinline__ void take_max(float v, int i, float& bv, int& bi) {
   }
 }
 
+// Four consecutive elements (row y, columns x0 .. x0+3, x0 % 4 == 0) of
+//   FLIP ? heatmap + flip_back(flipped)   (the SUM: the * 0.5 is applied by the caller)
+//        : heatmap
+// read as 128-bit shared-memory loads.  The flipped plane is stored as it came from
+// HBM; flip_back reverses x (fh[x] = fm[W-1-x]) and the optional 1-px shift makes
+// fh[x] = fm[W-x] for x >= 1, fh[0] = fm[W-1] (topdown_inferencer.py:180-187).
+template <bool FLIP>
+__device__ __forceinline__ float4 quad_at(const float* hm, const float* fm, int W, int q, int y,
+                                          int xq, int wq, int shift) {
+  float4 v = reinterpret_cast<const float4*>(hm)[q];
+  if (FLIP) {
+    const int fq = q + wq - 1 - 2 * xq;  // same row, mirrored float4 column
+    const float4 f = reinterpret_cast<const float4*>(fm)[fq];
+    float f0 = f.w, f1 = f.z, f2 = f.y, f3 = f.x;
+    if (shift) {
+      f3 = f.y;
+      f2 = f.z;
+      f1 = f.w;
+      f0 = xq == 0 ? f.w : fm[(fq << 2) + 4];
+    }
+    v.x = __fadd_rn(v.x, f0);
+    v.y = __fadd_rn(v.y, f1);
+    v.z = __fadd_rn(v.z, f2);
+    v.w = __fadd_rn(v.w, f3);
+  }
+  return v;
+}
+
+// One row of the blur: sum over kx of kernel[ky][kx] * win[row][col0 + kx], the
+// products added left to right in float32 (the oracle's order).
+template <int KS>
+__device__ __forceinline__ float blur_row(const float* __restrict__ wrow,
+                                          const float* __restrict__ vrow, int ks) {
+  float acc = __fmul_rn(wrow[0], vrow[0]);
+  if (KS > 0) {
+#pragma unroll
+    for (int kx = 1; kx < KS; ++kx) acc = __fadd_rn(acc, __fmul_rn(wrow[kx], vrow[kx]));
+  } else {
+    for (int kx = 1; kx < ks; ++kx) acc = __fadd_rn(acc, __fmul_rn(wrow[kx], vrow[kx]));
+  }
+  return acc;
+}
+
 template <bool FLIP>
 __global__ void __launch_bounds__(kDecodeThreads, 1)
     topdown_decode_kernel(const DecodeArgs a, const __grid_constant__ DecodeTables tab) {
@@ -78,8 +125,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
   const size_t stage_bytes_total = (size_t)a.stages * a.stage_floats * sizeof(float);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + stage_bytes_total);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  float* s_kernel = reinterpret_cast<float*>(empty_bar + kMaxStages);
+  volatile uint32_t* s_done = reinterpret_cast<volatile uint32_t*>(empty_bar + kMaxStages);
+  float* s_kernel = reinterpret_cast<float*>(const_cast<uint32_t*>(s_done) + kMaxStages);
   float* s_rows = s_kernel + PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL;  // [warps][7][17]
+  float* s_win = s_rows + kConsumerWarps * kDarkSamples * PC_MAX_DARK_KERNEL;  // [warps][19*19]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,6 +138,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      s_done[s] = 0;
     }
     fence_mbar_init();
   }
@@ -105,12 +155,13 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
 
   if (warp == 0) {
     // ---------------- producer: one thread issues all bulk copies -----------
+    // In order, so a parity wait on empty_bar is never more than one phase ahead.
     if (lane == 0) {
       const uint64_t pol = l2_evict_first_policy();
+      int s = 0;
+      uint32_t round = 0;
       for (int64_t j = 0; j < count; ++j) {
-        const int s = (int)(j % S);
-        const uint32_t round = (uint32_t)(j / S);
-        if (j >= S) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
         const int64_t item = first + j * gridDim.x;
         const int64_t n = item / a.K;
         const int k = (int)(item - n * a.K);
@@ -122,6 +173,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
           bulk_g2s(dst + a.HW, a.flipped + (n * a.K + kf) * a.HW, plane_bytes, &full_bar[s],
                    pol);
         }
+        if (++s == S) {
+          s = 0;
+          ++round;
+        }
       }
     }
     return;
@@ -132,6 +187,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
   const int W = a.W, H = a.H, HW = a.HW;
   const int shift = a.shift_heatmap;
   float* my_rows = s_rows + cw * (kDarkSamples * PC_MAX_DARK_KERNEL);
+  float* my_win = s_win + cw * kDarkWinMax;
 
   for (int64_t j = cw; j < count; j += kConsumerWarps) {
     const int s = (int)(j % S);
@@ -150,12 +206,15 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
       if (k == 0) sc = __ldg(a.score + n);
     }
 
-    // Stages and consumer warps are decoupled (7 warps, up to 12 stages), and bulk
-    // copies complete out of order, so this warp can reach stage s for round r while
-    // round r-1 of the same stage (another warp's item) has not even landed.  A
-    // parity wait may only ever be one phase ahead of its barrier: first make sure
-    // round r-1 of this stage was consumed, then wait for round r to land.
-    if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+    // Consumer warps and stages are decoupled (7 warps, 2..12 stages) and bulk copies
+    // complete out of order, so this warp can get here while an EARLIER round of the
+    // same stage is still being read by another warp -- possibly two or more rounds
+    // back when there are fewer stages than warps.  A parity wait is only meaningful
+    // one phase ahead, so the rounds of a stage are first put in order with a plain
+    // counter (s_done[s] = number of rounds of stage s consumed so far); once round-1
+    // has been consumed, full_bar[s] is in phase `round` or has just completed it, and
+    // the parity wait is exact.
+    while (s_done[s] != round) __nanosleep(32);
     mbar_wait(&full_bar[s], round & 1);
     const float* hm = stage_base + (size_t)s * a.stage_floats;
     const float* fm = hm + HW;
@@ -164,43 +223,45 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
     float bv = -INFINITY;
     int bi = 0x7fffffff;
     if (a.vec_ok) {
-      const int nvec = HW >> 2;
+      // Each lane keeps the maximum of its float4 groups and the FIRST group that
+      // reached it; the element inside the group is resolved after the loop.  With the
+      // flip test the comparison runs on the sums h + fh: halving is exact (and so
+      // order preserving) unless the result is subnormal, which is redone below.
+      const int nvec = HW >> 2, wq = W >> 2;
+      int y = (int)fdiv((uint32_t)lane, a.divWq);
+      int xq = lane - y * wq;
+      int bq = -1;
 #pragma unroll 4
       for (int q = lane; q < nvec; q += 32) {
-        const int idx = q << 2;
-        float4 v = reinterpret_cast<const float4*>(hm)[q];
-        if (FLIP) {
-          const int y = (int)fdiv((uint32_t)idx, a.divW);
-          const int x0 = idx - y * W;
-          const float* frow = fm + y * W;
-          const float4 f = *reinterpret_cast<const float4*>(frow + (W - 4 - x0));
-          float f0, f1, f2, f3;
-          if (shift) {
-            f0 = x0 == 0 ? f.w : frow[W - x0];
-            f1 = f.w;
-            f2 = f.z;
-            f3 = f.y;
-          } else {
-            f0 = f.w;
-            f1 = f.z;
-            f2 = f.y;
-            f3 = f.x;
-          }
-          v.x = __fmul_rn(__fadd_rn(v.x, f0), 0.5f);
-          v.y = __fmul_rn(__fadd_rn(v.y, f1), 0.5f);
-          v.z = __fmul_rn(__fadd_rn(v.z, f2), 0.5f);
-          v.w = __fmul_rn(__fadd_rn(v.w, f3), 0.5f);
+        const float4 v = quad_at<FLIP>(hm, fm, W, q, y, xq, wq, shift);
+        const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (m > bv) {
+          bv = m;
+          bq = q;
         }
-        take_max(v.x, idx, bv, bi);
-        take_max(v.y, idx + 1, bv, bi);
-        take_max(v.z, idx + 2, bv, bi);
-        take_max(v.w, idx + 3, bv, bi);
+        xq += a.step_xq;
+        y += a.step_y;
+        if (xq >= wq) {
+          xq -= wq;
+          ++y;
+        }
+      }
+      if (bq >= 0) {
+        const int yb = (int)fdiv((uint32_t)bq, a.divWq);
+        const float4 v = quad_at<FLIP>(hm, fm, W, bq, yb, bq - yb * wq, wq, shift);
+        const int c = v.x == bv ? 0 : (v.y == bv ? 1 : (v.z == bv ? 2 : 3));
+        bi = (bq << 2) + c;
       }
     } else {
       for (int idx = lane; idx < HW; idx += 32) {
         const int y = (int)fdiv((uint32_t)idx, a.divW);
         const int x = idx - y * W;
-        take_max(map_at<FLIP>(hm, fm, W, y, x, shift), idx, bv, bi);
+        float v = hm[idx];
+        if (FLIP) {
+          const int xs = shift ? (x == 0 ? W - 1 : W - x) : (W - 1 - x);
+          v = __fadd_rn(v, fm[y * W + xs]);
+        }
+        take_max(v, idx, bv, bi);
       }
     }
 #pragma unroll
@@ -210,6 +271,28 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
       if (ov > bv || (ov == bv && oi < bi)) {
         bv = ov;
         bi = oi;
+      }
+    }
+    if (FLIP) {
+      if (bi != 0x7fffffff && fabsf(bv) < 4.7019774e-38f /* 2^-124 */) {
+        // halves of sums this small can round: redo the scan on the exact averages
+        bv = -INFINITY;
+        bi = 0x7fffffff;
+        for (int idx = lane; idx < HW; idx += 32) {
+          const int y = (int)fdiv((uint32_t)idx, a.divW);
+          take_max(map_at<true>(hm, fm, W, y, idx - y * W, shift), idx, bv, bi);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+          }
+        }
+      } else {
+        bv = __fmul_rn(bv, 0.5f);
       }
     }
     if (bi == 0x7fffffff) {  // no element compared greater than -inf: index 0, as numpy.argmax
@@ -237,26 +320,32 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
       }
     } else if (a.mode == 2) {
       // ---- DARK / UDP Taylor step (top_down_decoder.py:171-205) -------------
+      // (1) the (ks+2)^2 window of the averaged map around the peak, zero outside the
+      //     map (the blur's "same" padding), goes to a per-warp scratch once;
+      // (2) 7 samples x ks kernel rows = 7*ks independent row sums out of the scratch;
+      // (3) lanes 0..6 add their rows top to bottom, clip, log; out-of-map samples are
+      //     the zero padding of the LOG map.
       // samples: 0:i  1:ix1  2:iy1  3:ix1y1  4:ix1_y1_  5:ix1_  6:iy1_
-      const int ks = a.ks, r = (ks - 1) >> 1;
+      const int ks = a.ks, r = (ks - 1) >> 1, wsz = ks + 2;
+      const int oy = py - r - 1, ox = px - r - 1;
+      for (int e = lane; e < wsz * wsz; e += 32) {
+        const int wy = (int)fdiv((uint32_t)e, a.divWin);
+        const int wx = e - wy * wsz;
+        const int yy = oy + wy, xx = ox + wx;
+        float v = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = map_at<FLIP>(hm, fm, W, yy, xx, shift);
+        my_win[e] = v;
+      }
+      __syncwarp();
       const int ntask = kDarkSamples * ks;
       for (int t = lane; t < ntask; t += 32) {
-        const int smp = t / ks, ky = t - smp * ks;
+        const int smp = (int)fdiv((uint32_t)t, a.divKs), ky = t - smp * ks;
         const int dxs = (smp == 1 || smp == 3) ? 1 : ((smp == 4 || smp == 5) ? -1 : 0);
         const int dys = (smp == 2 || smp == 3) ? 1 : ((smp == 4 || smp == 6) ? -1 : 0);
-        const int sy = py + dys, sx = px + dxs;
-        float acc = 0.f;
-        const int yy = sy + ky - r;
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W && yy >= 0 && yy < H) {
-          const float* wrow = s_kernel + ky * ks;
-          for (int kx = 0; kx < ks; ++kx) {
-            const int xx = sx + kx - r;
-            const float v = (xx >= 0 && xx < W) ? map_at<FLIP>(hm, fm, W, yy, xx, shift) : 0.f;
-            const float p = __fmul_rn(wrow[kx], v);
-            acc = kx == 0 ? p : __fadd_rn(acc, p);
-          }
-        }
-        my_rows[smp * PC_MAX_DARK_KERNEL + ky] = acc;
+        const float* vrow = my_win + (1 + dys + ky) * wsz + (1 + dxs);
+        const float* wrow = s_kernel + ky * ks;
+        my_rows[smp * PC_MAX_DARK_KERNEL + ky] =
+            ks == 11 ? blur_row<11>(wrow, vrow, ks) : blur_row<0>(wrow, vrow, ks);
       }
       __syncwarp();
       float lg = 0.f;
@@ -273,7 +362,6 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
           lg = (float)log((double)tot);  // correctly rounded float32 log
         }  // else: the reference zero-pads the LOG map -> 0.0
       }
-      __syncwarp();
       const float i_ = __shfl_sync(0xffffffffu, lg, 0);
       const float ix1 = __shfl_sync(0xffffffffu, lg, 1);
       const float iy1 = __shfl_sync(0xffffffffu, lg, 2);
@@ -300,16 +388,19 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
         const float i00 = __fdiv_rn(hd, det);
         const float i01 = __fdiv_rn(-hb, det);
         const float i11 = __fdiv_rn(ha, det);
-        const float ox = __fadd_rn(__fmul_rn(i00, dx), __fmul_rn(i01, dy));
-        const float oy = __fadd_rn(__fmul_rn(i01, dx), __fmul_rn(i11, dy));
-        rx = __fsub_rn(rx, ox);
-        ry = __fsub_rn(ry, oy);
+        const float ox_ = __fadd_rn(__fmul_rn(i00, dx), __fmul_rn(i01, dy));
+        const float oy_ = __fadd_rn(__fmul_rn(i01, dx), __fmul_rn(i11, dy));
+        rx = __fsub_rn(rx, ox_);
+        ry = __fsub_rn(ry, oy_);
       }
     }
 
-    // stage no longer needed: hand it back to the producer
+    // stage no longer needed: let the next round's consumer in, hand it back to the producer
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (lane == 0) {
+      s_done[s] = round + 1;
+      mbar_arrive(&empty_bar[s]);
+    }
 
     if (lane == 0) {
       const float s_w = __fmul_rn(sw, a.pixel_std);
@@ -428,11 +519,17 @@ extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
   a.ks = p->kernel_size;
   a.shift_heatmap = p->flip_test ? p->shift_heatmap : 0;
   a.vec_ok = (a.W % 4 == 0);
+  a.divWq = make_fastdiv((uint32_t)(a.vec_ok ? a.W / 4 : 1));
+  a.step_xq = a.vec_ok ? 32 % (a.W / 4) : 0;
+  a.step_y = a.vec_ok ? 32 / (a.W / 4) : 0;
+  a.divKs = make_fastdiv((uint32_t)(p->dark_udp_refine ? p->kernel_size : 1));
+  a.divWin = make_fastdiv((uint32_t)(p->dark_udp_refine ? p->kernel_size + 2 : 1));
   a.stage_floats = (uint32_t)(p->flip_test ? 2 * hw : hw);
 
-  const size_t tail_bytes = 2 * kMaxStages * sizeof(uint64_t) +
+  const size_t tail_bytes = 2 * kMaxStages * sizeof(uint64_t) + kMaxStages * sizeof(uint32_t) +
                             sizeof(float) * PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL +
-                            sizeof(float) * kConsumerWarps * kDarkSamples * PC_MAX_DARK_KERNEL;
+                            sizeof(float) * kConsumerWarps * kDarkSamples * PC_MAX_DARK_KERNEL +
+                            sizeof(float) * kConsumerWarps * kDarkWinMax;
   const size_t smem_cap = 227 * 1024;
   const size_t stage_bytes = (size_t)a.stage_floats * sizeof(float);
   int stages = (int)((smem_cap - tail_bytes) / stage_bytes);

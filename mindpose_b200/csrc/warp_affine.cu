@@ -311,6 +311,144 @@ __global__ void __launch_bounds__(kWarpThreads)
   }
 }
 
+
+// ---- 3-channel fast path ----------------------------------------------------
+// The generic kernel above issues 12 byte loads per output pixel and is bound by
+// load-instruction issue, not by HBM.  For interleaved RGB the two horizontally
+// adjacent source pixels are 6 contiguous bytes: they are fetched as two (three
+// when the run starts at byte 3 of a word) ALIGNED 32-bit words per source row and
+// realigned with a funnel shift, each thread produces four consecutive output
+// pixels (12 bytes = three packed words), and a warp's 384 output bytes are
+// transposed through shared memory into 24 full 16-byte stores.
+constexpr int kWarp3TileRows = 16;
+
+struct Six {
+  uint32_t lo, hi;  // bytes 0..3, bytes 4..7 of the run (6 are used)
+};
+__device__ __forceinline__ Six load_six(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t sh = ((uint32_t)a & 3u) << 3;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+  const uint32_t w2 = sh == 24u ? __ldg(w + 2) : 0u;
+  Six r;
+  r.lo = __funnelshift_r(w0, w1, sh);
+  r.hi = __funnelshift_r(w1, w2, sh);
+  return r;
+}
+
+// One output pixel (3 channels packed r | g << 8 | b << 16) at fixed-point source (X, Y).
+__device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img, int hs, int ws,
+                                                int X, int Y) {
+  int sx = X >> 5, sy = Y >> 5;
+  sx = max(-32768, min(32767, sx));  // saturate_cast<short>
+  sy = max(-32768, min(32767, sy));
+  const int fx = X & 31, fy = Y & 31;
+  const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy);
+  const int w10 = (32 - fx) * fy, w11 = fx * fy;
+  const bool interior = (unsigned)sx < (unsigned)(ws - 1) && (unsigned)sy < (unsigned)(hs - 1);
+  // aligned words may reach 3 bytes before / 2 bytes after the 6-byte run: keep them
+  // inside the image (excludes only its first and last pixel pair)
+  if (interior && (sx | sy) != 0 && (sx + 2 < ws || sy + 2 < hs)) {
+    const uint8_t* r0 = img + ((int64_t)sy * ws + sx) * 3;
+    const Six a = load_six(r0);
+    const Six b = load_six(r0 + (int64_t)ws * 3);
+    const int c0 = w00 * (int)(a.lo & 255u) + w01 * (int)(a.lo >> 24) +
+                   w10 * (int)(b.lo & 255u) + w11 * (int)(b.lo >> 24);
+    const int c1 = w00 * (int)((a.lo >> 8) & 255u) + w01 * (int)(a.hi & 255u) +
+                   w10 * (int)((b.lo >> 8) & 255u) + w11 * (int)(b.hi & 255u);
+    const int c2 = w00 * (int)((a.lo >> 16) & 255u) + w01 * (int)((a.hi >> 8) & 255u) +
+                   w10 * (int)((b.lo >> 16) & 255u) + w11 * (int)((b.hi >> 8) & 255u);
+    return (uint32_t)((c0 + 512) >> 10) | ((uint32_t)((c1 + 512) >> 10) << 8) |
+           ((uint32_t)((c2 + 512) >> 10) << 16);
+  }
+  if (sx >= ws || sx + 1 < 0 || sy >= hs || sy + 1 < 0) return 0u;
+  const bool x0in = sx >= 0 && sx < ws, x1in = sx + 1 >= 0 && sx + 1 < ws;
+  const bool y0in = sy >= 0 && sy < hs, y1in = sy + 1 >= 0 && sy + 1 < hs;
+  uint32_t out = 0u;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int acc = 0;
+    if (y0in && x0in) acc += w00 * img[((int64_t)sy * ws + sx) * 3 + c];
+    if (y0in && x1in) acc += w01 * img[((int64_t)sy * ws + sx + 1) * 3 + c];
+    if (y1in && x0in) acc += w10 * img[((int64_t)(sy + 1) * ws + sx) * 3 + c];
+    if (y1in && x1in) acc += w11 * img[((int64_t)(sy + 1) * ws + sx + 1) * 3 + c];
+    out |= (uint32_t)((acc + 512) >> 10) << (8 * c);
+  }
+  return out;
+}
+
+// dst_w % 16 == 0, dst 16-byte aligned: every warp's 32 quads are 384 contiguous,
+// 16-byte aligned output bytes.
+__global__ void __launch_bounds__(kWarpThreads)
+    warp_affine_u8x3_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
+                            const int32_t* __restrict__ src_hw, const double* __restrict__ inv,
+                            uint8_t* __restrict__ dst, int dst_w, int dst_h, int tiles_per_crop,
+                            FastDiv div_wq) {
+  __shared__ __align__(16) int s_adelta[kWarpMaxDstW];
+  __shared__ __align__(16) int s_bdelta[kWarpMaxDstW];
+  __shared__ int s_x0[kWarp3TileRows];
+  __shared__ int s_y0[kWarp3TileRows];
+  __shared__ __align__(16) uint32_t s_stage[kWarpThreads / 32][96];
+
+  const int64_t crop = blockIdx.x / tiles_per_crop;
+  const int tile = blockIdx.x - (int)(crop * tiles_per_crop);
+  const int row0 = tile * kWarp3TileRows;
+  const int rows = min(kWarp3TileRows, dst_h - row0);
+  const double* m = inv + 6 * crop;
+  const double m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5];
+
+  for (int x = threadIdx.x; x < dst_w; x += blockDim.x) {
+    s_adelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m00, (double)x), 1024.0));
+    s_bdelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m10, (double)x), 1024.0));
+  }
+  if (threadIdx.x < rows) {
+    const double y = (double)(row0 + threadIdx.x);
+    s_x0[threadIdx.x] =
+        __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m01, y), m02), 1024.0)) + 16;
+    s_y0[threadIdx.x] =
+        __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m11, y), m12), 1024.0)) + 16;
+  }
+  __syncthreads();
+
+  const int hs = src_hw[2 * crop], ws = src_hw[2 * crop + 1];
+  const uint8_t* img = src + src_off[crop];
+  const int wq = dst_w >> 2;
+  const int nquads = rows * wq;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* out = dst + ((size_t)crop * dst_h + row0) * dst_w * 3;
+  uint32_t* stage = s_stage[warp];
+
+  for (int base = warp * 32; base < nquads; base += kWarpThreads) {
+    const int t = base + lane;
+    uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    if (t < nquads) {
+      const int ry = (int)fdiv((uint32_t)t, div_wq);
+      const int x = (t - ry * wq) << 2;
+      const int X0 = s_x0[ry], Y0 = s_y0[ry];
+      const int4 ad = *reinterpret_cast<const int4*>(&s_adelta[x]);
+      const int4 bd = *reinterpret_cast<const int4*>(&s_bdelta[x]);
+      p0 = warp_pixel3(img, hs, ws, (X0 + ad.x) >> 5, (Y0 + bd.x) >> 5);
+      p1 = warp_pixel3(img, hs, ws, (X0 + ad.y) >> 5, (Y0 + bd.y) >> 5);
+      p2 = warp_pixel3(img, hs, ws, (X0 + ad.z) >> 5, (Y0 + bd.z) >> 5);
+      p3 = warp_pixel3(img, hs, ws, (X0 + ad.w) >> 5, (Y0 + bd.w) >> 5);
+    }
+    stage[3 * lane] = p0 | (p1 << 24);
+    stage[3 * lane + 1] = (p1 >> 8) | (p2 << 16);
+    stage[3 * lane + 2] = (p2 >> 16) | (p3 << 8);
+    __syncwarp();
+    const int nq = min(32, nquads - base);  // quads this warp produced
+    if (lane * 4 < nq * 3) {                // nq * 12 bytes = nq * 3 words; nq % 4 == 0
+      const uint4 v = reinterpret_cast<const uint4*>(stage)[lane];
+      asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(out + (size_t)base * 12 +
+                                                                           lane * 16),
+                   "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                   : "memory");
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace pc
 
 using namespace pc;
@@ -386,12 +524,22 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
   if (n == 0) return PC_OK;
   PC_REQUIRE(d_src && d_src_offset && d_src_hw && d_inv && d_dst, PC_ERR_INVALID_ARGUMENT,
              "pc_warp_affine_u8: NULL tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->channels == 3 && p->dst_w % 16 == 0 && ((uintptr_t)d_dst & 15) == 0) {
+    const int tiles3 = (p->dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
+    const int64_t grid3 = n * tiles3;
+    PC_REQUIRE(grid3 < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_warp_affine_u8: batch too large");
+    warp_affine_u8x3_kernel<<<(unsigned)grid3, kWarpThreads, 0, st>>>(
+        d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3,
+        make_fastdiv((uint32_t)(p->dst_w >> 2)));
+    PC_CUDA(cudaGetLastError());
+    return PC_OK;
+  }
   const int tiles = (p->dst_h + kWarpTileRows - 1) / kWarpTileRows;
   const int64_t grid = n * tiles;
   PC_REQUIRE(grid < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_warp_affine_u8: batch too large");
   const size_t smem = (size_t)kWarpTileRows * p->dst_w * p->channels;
   const FastDiv dw = make_fastdiv((uint32_t)p->dst_w);
-  cudaStream_t st = (cudaStream_t)stream;
 #define PC_LAUNCH_WARP(CH)                                                              \
   warp_affine_u8_kernel<CH><<<(unsigned)grid, kWarpThreads, smem, st>>>(               \
       d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles, dw)

@@ -112,11 +112,19 @@ def test_decode_reference_test_shapes(cuda_device):
         assert p.shape == (8, 17, 3) and b.shape == (8, 6) and p.dtype == torch.float32
 
 
-def test_decode_large_batch_properties(cuda_device):
-    """Full BASELINE size (4096 crops, flip pair): compare against torch reductions
-    (size-independent properties: argmax value/index, idempotence of a second call)."""
+@pytest.mark.parametrize("n,h,w,dark,shift_heatmap", [
+    (4096, 64, 48, False, False),   # BASELINE config 2 size, 9 stages
+    (4096, 64, 48, True, True),
+    (2048, 96, 72, True, False),    # BASELINE config 3 size: 4 stages < 7 consumer warps
+    (2048, 96, 72, False, True),
+    (1000, 128, 96, False, False),  # 2 stages
+])
+def test_decode_large_batch_properties(cuda_device, n, h, w, dark, shift_heatmap):
+    """Full BASELINE sizes (flip pair): compare against torch reductions
+    (size-independent properties: argmax value/index, idempotence of a second call).
+    The stage counts differ per map size, which exercises every pipeline depth."""
     dev = cuda_device
-    n, k, h, w = 4096, 17, 64, 48
+    k = 17
     g = torch.Generator(device=dev).manual_seed(0)
     hm = torch.rand(n, k, h, w, device=dev, generator=g)
     fl = torch.rand(n, k, h, w, device=dev, generator=g)
@@ -124,14 +132,48 @@ def test_decode_large_batch_properties(cuda_device):
     center = torch.rand(n, 2, device=dev) * 400
     scale = torch.rand(n, 2, device=dev) * 2.8 + 0.2
     score = torch.rand(n, device=dev)
-    dec = mp.create_decoder("topdown_heatmap", to_original=False)
-    p, b = dec.decode_flip_pair(hm, fl, synth.flip_index(), center, scale, score)
-    avg = (hm + fl[:, fidx].flip(-1)) * 0.5
+    dec = mp.create_decoder("topdown_heatmap", to_original=False, dark_udp_refine=dark)
+    p, b = dec.decode_flip_pair(hm, fl, synth.flip_index(), center, scale, score,
+                                shift_heatmap=shift_heatmap)
+    fb = fl[:, fidx].flip(-1)
+    if shift_heatmap:
+        fb = torch.cat([fb[..., :1], fb[..., :-1]], dim=-1)
+    avg = (hm + fb) * 0.5
     vals, idx = avg.reshape(n, k, -1).max(dim=2)
     assert torch.equal(p[..., 2], vals)
-    assert torch.equal(p[..., 0], (idx % w).float()) and torch.equal(p[..., 1], (idx // w).float())
-    p2, b2 = dec.decode_flip_pair(hm, fl, synth.flip_index(), center, scale, score)
+    if not dark:
+        assert torch.equal(p[..., 0], (idx % w).float())
+        assert torch.equal(p[..., 1], (idx // w).float())
+    p2, b2 = dec.decode_flip_pair(hm, fl, synth.flip_index(), center, scale, score,
+                                  shift_heatmap=shift_heatmap)
     assert torch.equal(p, p2) and torch.equal(b, b2)
+    # no-flip path at the same size
+    p3, _ = mp.create_decoder("topdown_heatmap", to_original=False)(hm, center, scale, score)
+    vals, idx = hm.reshape(n, k, -1).max(dim=2)
+    assert torch.equal(p3[..., 2], vals)
+    assert torch.equal(p3[..., 0], (idx % w).float()) and torch.equal(p3[..., 1], (idx // w).float())
+
+
+def test_decode_subnormal_and_zero_maps(cuda_device):
+    """Flip averaging of values whose halves are subnormal (the kernel compares sums and
+    must fall back to exact averages there), all-zero and all-negative planes."""
+    dev = cuda_device
+    n, k, h, w = 4, 17, 64, 48
+    rng = np.random.RandomState(7)
+    tiny = np.float32(2.0 ** -149)
+    maps = (rng.randint(0, 8, (n, k, h, w)).astype(np.float32) * tiny)
+    flipped = (rng.randint(0, 8, (n, k, h, w)).astype(np.float32) * tiny)
+    maps[1] = 0.0
+    flipped[1] = 0.0
+    maps[2] = -rng.random_sample((k, h, w)).astype(np.float32) - 1.0
+    center, scale, score = synth.crop_geometry(n, seed=1)
+    want_p, want_b = topdown_decode.decode_with_flip(maps, flipped, synth.flip_index(), center,
+                                                     scale, score, to_original=False)
+    dec = mp.create_decoder("topdown_heatmap", to_original=False)
+    got_p, got_b = dec.decode_flip_pair(_t(maps, dev), _t(flipped, dev), synth.flip_index(),
+                                        _t(center, dev), _t(scale, dev), _t(score, dev))
+    assert np.array_equal(got_p.cpu().numpy(), want_p)
+    assert np.array_equal(got_b.cpu().numpy(), want_b)
 
 
 def test_decode_host_front_end_matches_device_path(cuda_device):
@@ -312,3 +354,35 @@ def test_affine_per_sample_call_convention(cuda_device):
     out = at(*cols)
     m = affine.affine_matrix(c_want, s_want, 0.0, np.array(cfg["image_size"]))
     assert np.array_equal(out[0], warp.warp_affine_u8(images[0], m, (192, 256)))
+
+
+@pytest.mark.parametrize("channels", [1, 3, 4])
+def test_warp_image_corners_and_unaligned_sources(cuda_device, channels):
+    """Identity-like matrices sample the first and last pixel pair of the source (the
+    3-channel fast path reads aligned words and must not leave the image), and source
+    images that start at odd byte offsets inside a shared buffer."""
+    dev = cuda_device
+    rng = np.random.RandomState(11)
+    hs, ws, dw, dh = 37, 53, 48, 64
+    mats = np.array([[[1, 0, 0], [0, 1, 0]],
+                     [[1, 0, 0.5], [0, 1, 0.5]],
+                     [[1, 0, -3.25], [0, 1, 2.75]],
+                     [[0.9, 0.1, 1.0], [-0.1, 0.9, 2.0]],
+                     [[1.7, 0, -20.0], [0, 1.7, -10.0]]], np.float64)
+    n = len(mats)
+    pad = [0, 1, 2, 3, 5]
+    buf = rng.randint(0, 256, size=n * (hs * ws * channels + 8), dtype=np.uint8)
+    offs, imgs, pos = [], [], 0
+    for i in range(n):
+        pos += pad[i]
+        offs.append(pos)
+        imgs.append(buf[pos:pos + hs * ws * channels].reshape(hs, ws, channels))
+        pos += hs * ws * channels
+    inv = codec.invert_affine(_t(mats, dev))
+    out = codec.warp_affine(_t(buf, dev), torch.tensor(offs, device=dev),
+                            torch.tensor([[hs, ws]] * n, device=dev, dtype=torch.int32), inv,
+                            (dw, dh), channels=channels)
+    out = out.cpu().numpy()
+    for i in range(n):
+        want = warp.warp_affine_u8(imgs[i], mats[i], (dw, dh))
+        assert np.array_equal(out[i], want.reshape(dh, dw, channels)), i
