@@ -257,6 +257,330 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Fast path: register-resident NMS, warp-local top-M, one merge per plane.
+//
+// The generic kernel above walks a plane tile by tile with several block-wide
+// barriers per tile and funnels every candidate through warp 0; it reaches only a
+// few percent of the HBM roofline.  Here one CTA of 16 warps owns one (image,
+// joint) plane and every warp owns a band of rows on its own -- no block barrier
+// until the final merge:
+//   * lane l holds C consecutive columns (32 * C >= W); a row of the aggregated map
+//     is 128-bit loads of the high-resolution plane, the two low-resolution rows it
+//     is interpolated from (the right neighbour comes from the next lane by
+//     shuffle) and the mask bytes, combined in registers;
+//   * the 3x3 max-pool is separable: the horizontal 3-max of each row (neighbour
+//     columns by shuffle) is kept for the previous, current and next row, the
+//     vertical max of the three decides the current row -- no shared memory;
+//   * survivors go into the warp's own sorted top-M list (lane i = rank i);
+//   * after the band the 16 lists are merged: every entry finds its global rank by
+//     binary search in the other 15 sorted lists, ranks < M write the outputs.
+// Taken when nms_kernel is 1 or 3 (or NMS is off), W % C == 0, and (two stages) the
+// low-resolution map is exactly half the size; anything else uses the generic kernel.
+constexpr int kFastWarps = 16;
+constexpr int kFastThreads = kFastWarps * 32;
+
+template <int C>
+struct RowRegs {
+  float v[C];
+};
+
+__device__ __forceinline__ void topm_insert(float v, int idx, float& top_v, int& top_i,
+                                            int& count, int M, int lane) {
+  const bool mine_beats = lane < count && beats(top_v, top_i, v, idx);
+  const int p = __popc(__ballot_sync(0xffffffffu, mine_beats));
+  if (p < M) {
+    const float uv = __shfl_up_sync(0xffffffffu, top_v, 1);
+    const int ui = __shfl_up_sync(0xffffffffu, top_i, 1);
+    if (lane > p) {
+      top_v = uv;
+      top_i = ui;
+    } else if (lane == p) {
+      top_v = v;
+      top_i = idx;
+    }
+    count = min(count + 1, M);
+  }
+}
+
+// C columns (x0 .. x0+C-1) of row y of the aggregated, masked map.
+template <int C, bool TWO_STAGE, bool MASK2X>
+__device__ __forceinline__ void aggregate_row(const BuArgs& a, const float* __restrict__ heat_hi,
+                                              const float* __restrict__ heat_lo,
+                                              const uint8_t* __restrict__ mask, int y, int x0,
+                                              bool active, bool last_lane, float (&v)[C]) {
+  const int W = a.w1;
+#pragma unroll
+  for (int c = 0; c < C; ++c) v[c] = -INFINITY;
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+      const float4 t = ld_stream_f4(heat_hi + (size_t)y * W + x0 + 4 * q);
+      v[4 * q] = t.x;
+      v[4 * q + 1] = t.y;
+      v[4 * q + 2] = t.z;
+      v[4 * q + 3] = t.w;
+    }
+  }
+  if (TWO_STAGE) {
+    // legacy asymmetric bilinear, scale exactly 1/2: src = dst * 0.5
+    const int w0 = a.w0, h0 = a.h0;
+    const float ys = __fmul_rn((float)y, 0.5f);
+    const float y0f = floorf(ys);
+    const int y0 = (int)y0f, y1 = min(y0 + 1, h0 - 1);
+    const float fy = __fsub_rn(ys, y0f);
+    constexpr int L = C / 2;  // low-resolution columns owned by this lane
+    float la[L + 1], lb[L + 1];
+#pragma unroll
+    for (int j = 0; j <= L; ++j) la[j] = lb[j] = 0.f;
+    if (active) {
+      const float* ra = heat_lo + (size_t)y0 * w0 + (x0 >> 1);
+      const float* rb = heat_lo + (size_t)y1 * w0 + (x0 >> 1);
+      if (L % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < L / 4; ++q) {
+          const float4 ta = __ldg(reinterpret_cast<const float4*>(ra) + q);
+          const float4 tb = __ldg(reinterpret_cast<const float4*>(rb) + q);
+          la[4 * q] = ta.x, la[4 * q + 1] = ta.y, la[4 * q + 2] = ta.z, la[4 * q + 3] = ta.w;
+          lb[4 * q] = tb.x, lb[4 * q + 1] = tb.y, lb[4 * q + 2] = tb.z, lb[4 * q + 3] = tb.w;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < L / 2; ++q) {
+          const float2 ta = __ldg(reinterpret_cast<const float2*>(ra) + q);
+          const float2 tb = __ldg(reinterpret_cast<const float2*>(rb) + q);
+          la[2 * q] = ta.x, la[2 * q + 1] = ta.y;
+          lb[2 * q] = tb.x, lb[2 * q + 1] = tb.y;
+        }
+      }
+    }
+    // right neighbour: first low-res column of the next lane, clamped at the edge
+    const float na = __shfl_down_sync(0xffffffffu, la[0], 1);
+    const float nb = __shfl_down_sync(0xffffffffu, lb[0], 1);
+    la[L] = last_lane ? la[L - 1] : na;
+    lb[L] = last_lane ? lb[L - 1] : nb;
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int j = c >> 1;
+        const float fx = (c & 1) ? 0.5f : 0.f;
+        const float top = __fadd_rn(la[j], __fmul_rn(__fsub_rn(la[j + 1], la[j]), fx));
+        const float bot = __fadd_rn(lb[j], __fmul_rn(__fsub_rn(lb[j + 1], lb[j]), fx));
+        const float up = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), fy));
+        v[c] = __fmul_rn(__fadd_rn(v[c], up), 0.5f);  // / num_stages (2): exact
+      }
+    }
+  }
+  if (active) {
+    const int my = min((int)floorf(__fmul_rn((float)y, a.msy)), a.mh - 1);
+    const uint8_t* mrow = mask + (size_t)my * a.mw;
+    if (MASK2X) {  // mask is exactly twice as wide: nearest source column = 2 * x
+#pragma unroll
+      for (int q = 0; q < C / 8; ++q) {
+        const uint4 mb = __ldg(reinterpret_cast<const uint4*>(mrow + 2 * x0) + q);
+        const uint32_t w[4] = {mb.x, mb.y, mb.z, mb.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if ((w[t] & 0xffu) == 0) v[8 * q + 2 * t] = 0.f;
+          if ((w[t] & 0xff0000u) == 0) v[8 * q + 2 * t + 1] = 0.f;
+        }
+      }
+      if (C % 8 == 4) {
+        const uint2 mb = __ldg(reinterpret_cast<const uint2*>(mrow + 2 * x0 + (C / 8) * 16));
+        const uint32_t w[2] = {mb.x, mb.y};
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if ((w[t] & 0xffu) == 0) v[(C / 8) * 8 + 2 * t] = 0.f;
+          if ((w[t] & 0xff0000u) == 0) v[(C / 8) * 8 + 2 * t + 1] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int mx = min((int)floorf(__fmul_rn((float)(x0 + c), a.msx)), a.mw - 1);
+        if (__ldg(mrow + mx) == 0) v[c] = 0.f;
+      }
+    }
+  }
+}
+
+// horizontal 3-max of a row held C columns per lane
+template <int C>
+__device__ __forceinline__ void hmax3(const float (&v)[C], bool first_lane, bool last_lane,
+                                      float (&h)[C]) {
+  float left = __shfl_up_sync(0xffffffffu, v[C - 1], 1);
+  float right = __shfl_down_sync(0xffffffffu, v[0], 1);
+  if (first_lane) left = -INFINITY;
+  if (last_lane) right = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float l = c == 0 ? left : v[c - 1];
+    const float r = c == C - 1 ? right : v[c + 1];
+    h[c] = fmaxf(fmaxf(l, v[c]), r);
+  }
+}
+
+template <int C, bool TWO_STAGE, bool MASK2X>
+__global__ void __launch_bounds__(kFastThreads)
+    bottomup_decode_fast_kernel(const BuArgs a) {
+  __shared__ float s_lv[kFastWarps][32];
+  __shared__ int s_li[kFastWarps][32];
+  __shared__ int s_cnt[kFastWarps];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.x / a.K, k = blockIdx.x - n * a.K;
+  const int H = a.h1, W = a.w1, M = a.M;
+  const bool nms = a.use_nms && a.nms_k == 3;
+
+  const float* heat_hi;
+  const float* heat_lo = nullptr;
+  const float* tag_src;
+  int th, tw;
+  float tsy, tsx;
+  if (TWO_STAGE) {
+    heat_lo = a.out0 + ((size_t)n * 2 * a.K + k) * a.h0 * a.w0;
+    tag_src = a.out0 + ((size_t)n * 2 * a.K + a.K + k) * a.h0 * a.w0;
+    heat_hi = a.out1 + ((size_t)n * a.K + k) * H * W;
+    th = a.h0, tw = a.w0, tsy = a.sy, tsx = a.sx;
+  } else {
+    heat_hi = a.out0 + ((size_t)n * 2 * a.K + k) * H * W;
+    tag_src = a.out0 + ((size_t)n * 2 * a.K + a.K + k) * H * W;
+    th = H, tw = W, tsy = 1.f, tsx = 1.f;
+  }
+  const uint8_t* mask = a.mask + (size_t)n * a.mh * a.mw;
+  float* raw_out = a.heatmap_raw ? a.heatmap_raw + ((size_t)n * a.K + k) * H * W : nullptr;
+
+  const int x0 = lane * C;
+  const bool active = x0 < W;
+  const bool first_lane = lane == 0;
+  const bool last_lane = x0 + C >= W;  // also true for inactive lanes
+
+  const int R = (H + kFastWarps - 1) / kFastWarps;
+  const int rb = min(H, warp * R), re = min(H, rb + R);
+
+  float top_v = -INFINITY;
+  int top_i = 0x7fffffff;
+  int count = 0;
+
+  if (rb < re) {
+    float hm_prev[C], hm_cur[C], hm_new[C], v_cur[C], v_new[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) hm_prev[c] = hm_new[c] = v_new[c] = -INFINITY;
+    if (nms && rb > 0) {
+      aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, rb - 1, x0, active,
+                                          last_lane, v_cur);
+      hmax3<C>(v_cur, first_lane, last_lane, hm_prev);
+    }
+    aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, rb, x0, active, last_lane,
+                                        v_cur);
+    if (nms) hmax3<C>(v_cur, first_lane, last_lane, hm_cur);
+    float last_v = -INFINITY;
+    int last_i = 0x7fffffff;
+    for (int y = rb; y < re; ++y) {
+      if (raw_out && active) {
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q)
+          st_stream_f4(raw_out + (size_t)y * W + x0 + 4 * q,
+                       make_float4(v_cur[4 * q], v_cur[4 * q + 1], v_cur[4 * q + 2],
+                                   v_cur[4 * q + 3]));
+      }
+      const bool more = y + 1 < re || (nms && y + 1 < H);
+      if (more) {
+        aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, y + 1, x0, active,
+                                            last_lane, v_new);
+        if (nms) hmax3<C>(v_new, first_lane, last_lane, hm_new);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) hm_new[c] = -INFINITY;
+      }
+      const int row_base = y * W + x0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float m = v_cur[c];
+        if (nms) {
+          const float pooled = fmaxf(fmaxf(hm_prev[c], hm_cur[c]), hm_new[c]);
+          m = __fmul_rn(m, pooled == m ? 1.f : 0.f);
+        }
+        const int idx = row_base + c;
+        const bool cand = active && (count < M || beats(m, idx, last_v, last_i));
+        unsigned bits = __ballot_sync(0xffffffffu, cand);
+        while (bits) {
+          const int src = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const float cv = __shfl_sync(0xffffffffu, m, src);
+          const int ci = __shfl_sync(0xffffffffu, idx, src);
+          topm_insert(cv, ci, top_v, top_i, count, M, lane);
+        }
+        last_v = __shfl_sync(0xffffffffu, top_v, M - 1);
+        last_i = __shfl_sync(0xffffffffu, top_i, M - 1);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        hm_prev[c] = hm_cur[c];
+        hm_cur[c] = hm_new[c];
+        v_cur[c] = v_new[c];
+      }
+    }
+  }
+
+  // ---- merge the 16 sorted lists ------------------------------------------------
+  s_lv[warp][lane] = top_v;
+  s_li[warp][lane] = top_i;
+  if (lane == 0) s_cnt[warp] = count;
+  __syncthreads();
+  if (lane < count) {
+    int rank = lane;
+    for (int w = 0; w < kFastWarps; ++w) {
+      if (w == warp) continue;
+      // entries of list w that beat (top_v, top_i): the list is sorted, so this is the
+      // first position whose entry does not beat it
+      int lo = 0, hi = s_cnt[w];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (beats(s_lv[w][mid], s_li[w][mid], top_v, top_i))
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < M) {
+      const size_t o = ((size_t)n * a.K + k) * M + rank;
+      const int y = (int)fdiv((uint32_t)top_i, a.div_w1);
+      const int x = top_i - y * W;
+      a.val_k[o] = top_v;
+      a.ind_k[2 * o] = (float)x;
+      a.ind_k[2 * o + 1] = (float)y;
+      a.tag_k[o] = bilinear_legacy(tag_src, th, tw, tsy, tsx, y, x);
+    }
+  }
+}
+
+// tagging_heatmap output (bottom_up_decoder.py:118-120): the tag planes resized to the
+// output resolution; only _refine_missing and the visualiser read it.
+__global__ void __launch_bounds__(256)
+    resize_tags_kernel(const float* __restrict__ out0, float* __restrict__ tagging, int K,
+                       int planes_per_image, int tag_first, int th, int tw, int H, int W,
+                       float sy, float sx, FastDiv div_w, int64_t total_quads) {
+  const int wq = W >> 2;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_quads;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t plane = t / ((int64_t)H * wq);
+    const int r = (int)(t - plane * (int64_t)H * wq);
+    const int y = r / wq, x = (r - y * wq) << 2;
+    const int64_t n = plane / K;
+    const int k = (int)(plane - n * K);
+    const float* src = out0 + ((size_t)n * planes_per_image + tag_first + k) * th * tw;
+    float4 o;
+    o.x = bilinear_legacy(src, th, tw, sy, sx, y, x);
+    o.y = bilinear_legacy(src, th, tw, sy, sx, y, x + 1);
+    o.z = bilinear_legacy(src, th, tw, sy, sx, y, x + 2);
+    o.w = bilinear_legacy(src, th, tw, sy, sx, y, x + 3);
+    st_stream_f4(tagging + ((size_t)plane * H + y) * W + x, o);
+  }
+}
+
 }  // namespace pc
 
 using namespace pc;
@@ -320,12 +644,63 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
   a.sx = p->num_stages == 2 ? (float)p->w0 / (float)p->w1 : 1.f;
   a.msy = (float)p->mask_h / (float)p->h1;
   a.msx = (float)p->mask_w / (float)p->w1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)(n * p->num_joints);
+
+  // ---- fast path selection ----------------------------------------------------
+  const bool nms_ok = !p->use_nms || p->nms_kernel == 1 || p->nms_kernel == 3;
+  const bool two = p->num_stages == 2;
+  const bool half = !two || (p->h1 == 2 * p->h0 && p->w1 == 2 * p->w0);
+  int C = 0;
+  if (p->w1 % 4 == 0) {
+    if (p->w1 <= 128 && p->w1 % 4 == 0) C = 4;
+    if (p->w1 > 128 && p->w1 <= 256 && p->w1 % 8 == 0) C = 8;
+    if (p->w1 > 256 && p->w1 <= 512 && p->w1 % 16 == 0) C = 16;
+  }
+  const bool aligned = ((uintptr_t)d_out0 % 16 == 0) && (!two || (uintptr_t)d_out1 % 16 == 0) &&
+                       (!d_heatmap_raw || (uintptr_t)d_heatmap_raw % 16 == 0) &&
+                       (!two || (p->w0 % 4 == 0));
+  if (nms_ok && half && C != 0 && aligned) {
+    const bool mask2x = p->mask_w == 2 * p->w1 && (uintptr_t)d_mask % 16 == 0;
+    BuArgs b = a;
+    if (p->use_nms && p->nms_kernel == 1) b.use_nms = 0;  // a 1x1 pool keeps every value
+#define PC_BU_LAUNCH(CC, TWO, M2X) \
+  bottomup_decode_fast_kernel<CC, TWO, M2X><<<grid, kFastThreads, 0, st>>>(b)
+#define PC_BU_PICK(CC)                                 \
+  do {                                                 \
+    if (two) {                                         \
+      if (mask2x) PC_BU_LAUNCH(CC, true, true);        \
+      else PC_BU_LAUNCH(CC, true, false);              \
+    } else {                                           \
+      if (mask2x) PC_BU_LAUNCH(CC, false, true);       \
+      else PC_BU_LAUNCH(CC, false, false);             \
+    }                                                  \
+  } while (0)
+    if (C == 4) PC_BU_PICK(4);
+    else if (C == 8) PC_BU_PICK(8);
+    else PC_BU_PICK(16);
+#undef PC_BU_PICK
+#undef PC_BU_LAUNCH
+    PC_CUDA(cudaGetLastError());
+    if (d_tagging) {
+      const int th = two ? p->h0 : p->h1, tw = two ? p->w0 : p->w1;
+      const int64_t quads = n * p->num_joints * (int64_t)p->h1 * (p->w1 / 4);
+      int64_t blocks = (quads + 255) / 256;
+      const int64_t cap = (int64_t)sm_count_cached() * 16;
+      if (blocks > cap) blocks = cap;
+      resize_tags_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+          d_out0, d_tagging, p->num_joints, 2 * p->num_joints, p->num_joints, th, tw, p->h1,
+          p->w1, two ? a.sy : 1.f, two ? a.sx : 1.f, a.div_w1, quads);
+      PC_CUDA(cudaGetLastError());
+    }
+    return PC_OK;
+  }
+
   const size_t smem = sizeof(float) * ((size_t)(kBuRing + 2 * kBuTileRows) * p->w1 + kBuThreads);
   if (smem > 48 * 1024)
     PC_CUDA(cudaFuncSetAttribute(bottomup_decode_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  bottomup_decode_kernel<<<(unsigned)(n * p->num_joints), kBuThreads, smem,
-                           (cudaStream_t)stream>>>(a);
+  bottomup_decode_kernel<<<grid, kBuThreads, smem, st>>>(a);
   PC_CUDA(cudaGetLastError());
   return PC_OK;
 }

@@ -337,32 +337,58 @@ __device__ __forceinline__ Six load_six(const uint8_t* p) {
   return r;
 }
 
-// One output pixel (3 channels packed r | g << 8 | b << 16) at fixed-point source (X, Y).
+// Source row pair of one output pixel: shared by the four pixels of a thread when the
+// matrix has no rotation (then Y does not depend on x).
+struct RowCtx {
+  int sy, fy;
+  uint32_t off;  // byte offset of row sy inside the image (valid rows only)
+  bool y_interior;
+};
+__device__ __forceinline__ RowCtx make_row(int Y, int hs, uint32_t ws3) {
+  RowCtx r;
+  r.sy = max(-32768, min(32767, Y >> 5));  // saturate_cast<short>
+  r.fy = Y & 31;
+  r.y_interior = (unsigned)r.sy < (unsigned)(hs - 1);
+  r.off = (uint32_t)r.sy * ws3;
+  return r;
+}
+
+// One output pixel (3 channels packed r | g << 8 | b << 16) at fixed-point source X in
+// the row pair rc.  OpenCV's sum of four 15-bit weighted taps equals, exactly (integer
+// arithmetic), a horizontal blend with weights (32-fx, fx) followed by a vertical blend
+// with (32-fy, fy); the horizontal blends are byte dot products (dp4a) taken straight
+// from the realigned words, with zero weights on the bytes of the other channels.
 __device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img, int hs, int ws,
-                                                int X, int Y) {
-  int sx = X >> 5, sy = Y >> 5;
-  sx = max(-32768, min(32767, sx));  // saturate_cast<short>
-  sy = max(-32768, min(32767, sy));
-  const int fx = X & 31, fy = Y & 31;
-  const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy);
-  const int w10 = (32 - fx) * fy, w11 = fx * fy;
-  const bool interior = (unsigned)sx < (unsigned)(ws - 1) && (unsigned)sy < (unsigned)(hs - 1);
+                                                uint32_t ws3, int X, const RowCtx rc) {
+  const int sx = max(-32768, min(32767, X >> 5));
+  const int fx = X & 31, fy = rc.fy, sy = rc.sy;
+  const bool interior = (unsigned)sx < (unsigned)(ws - 1) && rc.y_interior;
   // aligned words may reach 3 bytes before / 2 bytes after the 6-byte run: keep them
   // inside the image (excludes only its first and last pixel pair)
   if (interior && (sx | sy) != 0 && (sx + 2 < ws || sy + 2 < hs)) {
-    const uint8_t* r0 = img + ((int64_t)sy * ws + sx) * 3;
+    const uint8_t* r0 = img + (rc.off + (uint32_t)sx * 3u);
     const Six a = load_six(r0);
-    const Six b = load_six(r0 + (int64_t)ws * 3);
-    const int c0 = w00 * (int)(a.lo & 255u) + w01 * (int)(a.lo >> 24) +
-                   w10 * (int)(b.lo & 255u) + w11 * (int)(b.lo >> 24);
-    const int c1 = w00 * (int)((a.lo >> 8) & 255u) + w01 * (int)(a.hi & 255u) +
-                   w10 * (int)((b.lo >> 8) & 255u) + w11 * (int)(b.hi & 255u);
-    const int c2 = w00 * (int)((a.lo >> 16) & 255u) + w01 * (int)((a.hi >> 8) & 255u) +
-                   w10 * (int)((b.lo >> 16) & 255u) + w11 * (int)((b.hi >> 8) & 255u);
-    return (uint32_t)((c0 + 512) >> 10) | ((uint32_t)((c1 + 512) >> 10) << 8) |
-           ((uint32_t)((c2 + 512) >> 10) << 16);
+    const Six b = load_six(r0 + ws3);
+    const uint32_t gx = 32u - (uint32_t)fx, ux = (uint32_t)fx;
+    const uint32_t k0 = gx | (ux << 24);  // channel 0: bytes 0 and 3 of lo
+    const uint32_t k1l = gx << 8;         // channel 1: byte 1 of lo, byte 0 of hi
+    const uint32_t k2l = gx << 16;        // channel 2: byte 2 of lo, byte 1 of hi
+    const uint32_t k2h = ux << 8;
+    const uint32_t a0 = __dp4a(a.lo, k0, 0u);
+    const uint32_t a1 = __dp4a(a.hi, ux, __dp4a(a.lo, k1l, 0u));
+    const uint32_t a2 = __dp4a(a.hi, k2h, __dp4a(a.lo, k2l, 0u));
+    const uint32_t b0 = __dp4a(b.lo, k0, 0u);
+    const uint32_t b1 = __dp4a(b.hi, ux, __dp4a(b.lo, k1l, 0u));
+    const uint32_t b2 = __dp4a(b.hi, k2h, __dp4a(b.lo, k2l, 0u));
+    const uint32_t gy = 32u - (uint32_t)fy, uy = (uint32_t)fy;
+    const uint32_t c0 = (gy * a0 + uy * b0 + 512u) >> 10;
+    const uint32_t c1 = (gy * a1 + uy * b1 + 512u) >> 10;
+    const uint32_t c2 = (gy * a2 + uy * b2 + 512u) >> 10;
+    return c0 | (c1 << 8) | (c2 << 16);
   }
   if (sx >= ws || sx + 1 < 0 || sy >= hs || sy + 1 < 0) return 0u;
+  const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy);
+  const int w10 = (32 - fx) * fy, w11 = fx * fy;
   const bool x0in = sx >= 0 && sx < ws, x1in = sx + 1 >= 0 && sx + 1 < ws;
   const bool y0in = sy >= 0 && sy < hs, y1in = sy + 1 >= 0 && sy + 1 < hs;
   uint32_t out = 0u;
@@ -413,6 +439,7 @@ __global__ void __launch_bounds__(kWarpThreads)
 
   const int hs = src_hw[2 * crop], ws = src_hw[2 * crop + 1];
   const uint8_t* img = src + src_off[crop];
+  const uint32_t ws3 = (uint32_t)ws * 3u;
   const int wq = dst_w >> 2;
   const int nquads = rows * wq;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -428,10 +455,20 @@ __global__ void __launch_bounds__(kWarpThreads)
       const int X0 = s_x0[ry], Y0 = s_y0[ry];
       const int4 ad = *reinterpret_cast<const int4*>(&s_adelta[x]);
       const int4 bd = *reinterpret_cast<const int4*>(&s_bdelta[x]);
-      p0 = warp_pixel3(img, hs, ws, (X0 + ad.x) >> 5, (Y0 + bd.x) >> 5);
-      p1 = warp_pixel3(img, hs, ws, (X0 + ad.y) >> 5, (Y0 + bd.y) >> 5);
-      p2 = warp_pixel3(img, hs, ws, (X0 + ad.z) >> 5, (Y0 + bd.z) >> 5);
-      p3 = warp_pixel3(img, hs, ws, (X0 + ad.w) >> 5, (Y0 + bd.w) >> 5);
+      const int Ya = (Y0 + bd.x) >> 5, Yb = (Y0 + bd.y) >> 5;
+      const int Yc = (Y0 + bd.z) >> 5, Yd = (Y0 + bd.w) >> 5;
+      const RowCtx ra = make_row(Ya, hs, ws3);
+      if (Ya == Yb && Ya == Yc && Ya == Yd) {  // no rotation: one source row pair
+        p0 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
+        p1 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.y) >> 5, ra);
+        p2 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.z) >> 5, ra);
+        p3 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.w) >> 5, ra);
+      } else {
+        p0 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
+        p1 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.y) >> 5, make_row(Yb, hs, ws3));
+        p2 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.z) >> 5, make_row(Yc, hs, ws3));
+        p3 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.w) >> 5, make_row(Yd, hs, ws3));
+      }
     }
     stage[3 * lane] = p0 | (p1 << 24);
     stage[3 * lane + 1] = (p1 >> 8) | (p2 << 16);

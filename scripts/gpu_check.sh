@@ -32,3 +32,10 @@ if [ "$2" = "ncu" ]; then
   echo "ncu warp exit $?"
   ls -la $out
 fi
+if [ "$2" = "ncu_bottomup" ]; then
+  CMD="python scripts/kbench.py --iters 3 --only bottomup"
+  timeout 300 $CMD > $out/${tag}_plain_bu.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on \
+      -k regex:bottomup_decode -s 3 -c 1 -f -o $out/${tag}_bottomup $CMD > $out/${tag}_ncu_bu.log 2>&1
+  echo "ncu bottomup exit $?"
+fi

@@ -28,7 +28,11 @@ def _split_counts(flat, counts, k=17, width=4):
 
 @pytest.mark.parametrize("h0,mask_hw,use_nms,nms_kernel", [
     (32, (128, 128), True, 3), (32, (128, 128), False, 5), (64, (256, 256), True, 5),
-    (48, (100, 210), True, 3)])
+    (48, (100, 210), True, 3),
+    (160, (640, 640), True, 3),     # W = 320: 16 columns per lane
+    (160, (200, 300), False, 3),
+    (20, (80, 80), True, 3),        # H = 40 < 3 rows per warp band, W = 40 (generic: 40 % 4 == 0, C = 4)
+    (128, (512, 512), True, 1)])    # BASELINE config 4 shape, 1x1 pool
 def test_decode_matches_oracle(cuda_device, h0, mask_hw, use_nms, nms_kernel):
     n = 3
     d = synth.bottomup_outputs(n, 17, h0, h0, mask_hw=mask_hw, seed=h0, max_people=5)
