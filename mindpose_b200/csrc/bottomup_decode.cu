@@ -259,13 +259,13 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
 
 
 // ---------------------------------------------------------------------------
-// Fast path: register-resident NMS, warp-local top-M, one merge per plane.
+// Fast path: register-resident NMS, per-lane top-3, one merge per plane.
 //
 // The generic kernel above walks a plane tile by tile with several block-wide
 // barriers per tile and funnels every candidate through warp 0; it reaches only a
-// few percent of the HBM roofline.  Here one CTA of 16 warps owns one (image,
-// joint) plane and every warp owns a band of rows on its own -- no block barrier
-// until the final merge:
+// few percent of the HBM roofline.  Here one CTA of 8 warps owns one (image, joint)
+// plane and every warp owns a band of rows on its own -- no block barrier until the
+// merge:
 //   * lane l holds C consecutive columns (32 * C >= W); a row of the aggregated map
 //     is 128-bit loads of the high-resolution plane, the two low-resolution rows it
 //     is interpolated from (the right neighbour comes from the next lane by
@@ -273,12 +273,19 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
 //   * the 3x3 max-pool is separable: the horizontal 3-max of each row (neighbour
 //     columns by shuffle) is kept for the previous, current and next row, the
 //     vertical max of the three decides the current row -- no shared memory;
-//   * survivors go into the warp's own sorted top-M list (lane i = rank i);
-//   * after the band the 16 lists are merged: every entry finds its global rank by
-//     binary search in the other 15 sorted lists, ranks < M write the outputs.
+//   * pass 1: every lane keeps the best THREE survivors of its own C x R pixel
+//     region in registers (~4 instructions per pixel).  The union of these (768
+//     entries) holds the plane's top M unless one lane owns four or more of them;
+//   * merge: the lane bests are sorted per warp, ranked across warps by binary
+//     search, the M-th gives a threshold T; the few entries >= T are compacted and
+//     ranked exactly (value desc, flat index asc);
+//   * check: if some lane's third entry beats the M-th result a fourth may have
+//     been dropped -> pass 2 re-scans the plane (it is in L2) with exact per-warp
+//     sorted lists (lane i = rank i), pre-filtered by the M-th result, and merges
+//     those.  Rare on real maps (< 1 % of planes), bounded on any input.
 // Taken when nms_kernel is 1 or 3 (or NMS is off), W % C == 0, and (two stages) the
 // low-resolution map is exactly half the size; anything else uses the generic kernel.
-constexpr int kFastWarps = 16;
+constexpr int kFastWarps = 8;
 constexpr int kFastThreads = kFastWarps * 32;
 
 template <int C>
@@ -421,12 +428,163 @@ __device__ __forceinline__ void hmax3(const float (&v)[C], bool first_lane, bool
   }
 }
 
+
+struct Top3 {
+  float v1, v2, v3;
+  int i1, i2, i3;
+};
+
+struct ExactList {
+  float top_v;  // lane i = rank i
+  int top_i;
+  int count;
+  float last_v;
+  int last_i;
+  float pre_v;  // only candidates that are not beaten by (pre_v, pre_i) matter
+  int pre_i;
+};
+
+// Scan rows [rb, re) of the plane: aggregate, NMS, feed survivors to the sink.
+template <int C, bool TWO_STAGE, bool MASK2X, bool EXACT>
+__device__ __forceinline__ void scan_band(const BuArgs& a, const float* __restrict__ heat_hi,
+                                          const float* __restrict__ heat_lo,
+                                          const uint8_t* __restrict__ mask, float* raw_out,
+                                          int rb, int re, int lane, bool nms, int M, Top3& t3,
+                                          ExactList& ex) {
+  const int H = a.h1, W = a.w1;
+  const int x0 = lane * C;
+  const bool active = x0 < W;
+  const bool first_lane = lane == 0;
+  const bool last_lane = x0 + C >= W;  // also true for inactive lanes
+  float hm_prev[C], hm_cur[C], hm_new[C], v_cur[C], v_new[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) hm_prev[c] = hm_cur[c] = hm_new[c] = v_new[c] = -INFINITY;
+  if (nms && rb > 0) {
+    aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, rb - 1, x0, active, last_lane,
+                                        v_cur);
+    hmax3<C>(v_cur, first_lane, last_lane, hm_prev);
+  }
+  aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, rb, x0, active, last_lane,
+                                      v_cur);
+  if (nms) hmax3<C>(v_cur, first_lane, last_lane, hm_cur);
+  for (int y = rb; y < re; ++y) {
+    if (!EXACT && raw_out && active) {
+#pragma unroll
+      for (int q = 0; q < C / 4; ++q)
+        st_stream_f4(raw_out + (size_t)y * W + x0 + 4 * q,
+                     make_float4(v_cur[4 * q], v_cur[4 * q + 1], v_cur[4 * q + 2],
+                                 v_cur[4 * q + 3]));
+    }
+    const bool more = y + 1 < re || (nms && y + 1 < H);
+    if (more) {
+      aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, y + 1, x0, active,
+                                          last_lane, v_new);
+      if (nms) hmax3<C>(v_new, first_lane, last_lane, hm_new);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) hm_new[c] = -INFINITY;
+    }
+    const int row_base = y * W + x0;
+    float m[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      m[c] = v_cur[c];
+      if (nms) {
+        const float pooled = fmaxf(fmaxf(hm_prev[c], hm_cur[c]), hm_new[c]);
+        m[c] = __fmul_rn(m[c], pooled == m[c] ? 1.f : 0.f);
+      }
+    }
+    if (!EXACT) {
+      // a lane sees its pixels in increasing flat index, so an equal value never
+      // displaces an entry (the i-test only matters for -inf against the empty slot)
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float mv = m[c];
+          const int idx = row_base + c;
+          if (mv > t3.v3 || (mv == t3.v3 && idx < t3.i3)) {
+            if (mv > t3.v1 || (mv == t3.v1 && idx < t3.i1)) {
+              t3.v3 = t3.v2, t3.i3 = t3.i2;
+              t3.v2 = t3.v1, t3.i2 = t3.i1;
+              t3.v1 = mv, t3.i1 = idx;
+            } else if (mv > t3.v2 || (mv == t3.v2 && idx < t3.i2)) {
+              t3.v3 = t3.v2, t3.i3 = t3.i2;
+              t3.v2 = mv, t3.i2 = idx;
+            } else {
+              t3.v3 = mv, t3.i3 = idx;
+            }
+          }
+        }
+      }
+    } else {
+      bool cand[C];
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int idx = row_base + c;
+        cand[c] = active && !beats(ex.pre_v, ex.pre_i, m[c], idx) &&
+                  (ex.count < M || beats(m[c], idx, ex.last_v, ex.last_i));
+        any |= cand[c];
+      }
+      if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int idx = row_base + c;
+          // the list may have moved since cand[c] was taken: test again
+          const bool cnow = cand[c] &&
+                            (ex.count < M || beats(m[c], idx, ex.last_v, ex.last_i));
+          unsigned bits = __ballot_sync(0xffffffffu, cnow);
+          if (bits) {
+            while (bits) {
+              const int src = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const float cv = __shfl_sync(0xffffffffu, m[c], src);
+              const int ci = __shfl_sync(0xffffffffu, idx, src);
+              topm_insert(cv, ci, ex.top_v, ex.top_i, ex.count, M, lane);
+            }
+            ex.last_v = __shfl_sync(0xffffffffu, ex.top_v, M - 1);
+            ex.last_i = __shfl_sync(0xffffffffu, ex.top_i, M - 1);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      hm_prev[c] = hm_cur[c];
+      hm_cur[c] = hm_new[c];
+      v_cur[c] = v_new[c];
+    }
+  }
+}
+
+// entries of the sorted list (lv, li)[0..n) that beat (v, i)
+__device__ __forceinline__ int count_beating(const float* lv, const int* li, int n, float v,
+                                             int i) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (beats(lv[mid], li[mid], v, i))
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+constexpr int kFastBuf = 3 * kFastThreads;
+
 template <int C, bool TWO_STAGE, bool MASK2X>
 __global__ void __launch_bounds__(kFastThreads)
     bottomup_decode_fast_kernel(const BuArgs a) {
   __shared__ float s_lv[kFastWarps][32];
   __shared__ int s_li[kFastWarps][32];
   __shared__ int s_cnt[kFastWarps];
+  __shared__ float s_bv[kFastBuf];
+  __shared__ int s_bi[kFastBuf];
+  __shared__ float s_ov[32];
+  __shared__ int s_oi[32];
+  __shared__ int s_nbuf, s_nout, s_ti;
+  __shared__ float s_tv;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.x / a.K, k = blockIdx.x - n * a.K;
@@ -451,105 +609,137 @@ __global__ void __launch_bounds__(kFastThreads)
   const uint8_t* mask = a.mask + (size_t)n * a.mh * a.mw;
   float* raw_out = a.heatmap_raw ? a.heatmap_raw + ((size_t)n * a.K + k) * H * W : nullptr;
 
-  const int x0 = lane * C;
-  const bool active = x0 < W;
-  const bool first_lane = lane == 0;
-  const bool last_lane = x0 + C >= W;  // also true for inactive lanes
-
   const int R = (H + kFastWarps - 1) / kFastWarps;
   const int rb = min(H, warp * R), re = min(H, rb + R);
 
-  float top_v = -INFINITY;
-  int top_i = 0x7fffffff;
-  int count = 0;
+  if (tid == 0) {
+    s_nbuf = 0;
+    s_nout = 0;
+    s_tv = -INFINITY;  // threshold "nothing is excluded"
+    s_ti = 0x7fffffff;
+  }
 
-  if (rb < re) {
-    float hm_prev[C], hm_cur[C], hm_new[C], v_cur[C], v_new[C];
+  // ---- pass 1: per-lane top 3 ---------------------------------------------------
+  Top3 t3;
+  t3.v1 = t3.v2 = t3.v3 = -INFINITY;
+  t3.i1 = t3.i2 = t3.i3 = 0x7fffffff;
+  ExactList ex;
+  ex.top_v = -INFINITY, ex.top_i = 0x7fffffff, ex.count = 0;
+  ex.last_v = -INFINITY, ex.last_i = 0x7fffffff;
+  ex.pre_v = -INFINITY, ex.pre_i = 0x7fffffff;
+  if (rb < re)
+    scan_band<C, TWO_STAGE, MASK2X, false>(a, heat_hi, heat_lo, mask, raw_out, rb, re, lane, nms,
+                                           M, t3, ex);
+
+  // ---- merge (1): sort the lane bests of each warp (bitonic, descending) ----------
+  float sv = t3.v1;
+  int si = t3.i1;
 #pragma unroll
-    for (int c = 0; c < C; ++c) hm_prev[c] = hm_new[c] = v_new[c] = -INFINITY;
-    if (nms && rb > 0) {
-      aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, rb - 1, x0, active,
-                                          last_lane, v_cur);
-      hmax3<C>(v_cur, first_lane, last_lane, hm_prev);
-    }
-    aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, rb, x0, active, last_lane,
-                                        v_cur);
-    if (nms) hmax3<C>(v_cur, first_lane, last_lane, hm_cur);
-    float last_v = -INFINITY;
-    int last_i = 0x7fffffff;
-    for (int y = rb; y < re; ++y) {
-      if (raw_out && active) {
+  for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
-        for (int q = 0; q < C / 4; ++q)
-          st_stream_f4(raw_out + (size_t)y * W + x0 + 4 * q,
-                       make_float4(v_cur[4 * q], v_cur[4 * q + 1], v_cur[4 * q + 2],
-                                   v_cur[4 * q + 3]));
-      }
-      const bool more = y + 1 < re || (nms && y + 1 < H);
-      if (more) {
-        aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, y + 1, x0, active,
-                                            last_lane, v_new);
-        if (nms) hmax3<C>(v_new, first_lane, last_lane, hm_new);
-      } else {
-#pragma unroll
-        for (int c = 0; c < C; ++c) hm_new[c] = -INFINITY;
-      }
-      const int row_base = y * W + x0;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float m = v_cur[c];
-        if (nms) {
-          const float pooled = fmaxf(fmaxf(hm_prev[c], hm_cur[c]), hm_new[c]);
-          m = __fmul_rn(m, pooled == m ? 1.f : 0.f);
-        }
-        const int idx = row_base + c;
-        const bool cand = active && (count < M || beats(m, idx, last_v, last_i));
-        unsigned bits = __ballot_sync(0xffffffffu, cand);
-        while (bits) {
-          const int src = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const float cv = __shfl_sync(0xffffffffu, m, src);
-          const int ci = __shfl_sync(0xffffffffu, idx, src);
-          topm_insert(cv, ci, top_v, top_i, count, M, lane);
-        }
-        last_v = __shfl_sync(0xffffffffu, top_v, M - 1);
-        last_i = __shfl_sync(0xffffffffu, top_i, M - 1);
-      }
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        hm_prev[c] = hm_cur[c];
-        hm_cur[c] = hm_new[c];
-        v_cur[c] = v_new[c];
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, sv, j);
+      const int oi = __shfl_xor_sync(0xffffffffu, si, j);
+      const bool desc = (lane & kk) == 0;       // direction of this lane's block
+      const bool lower = (lane & j) == 0;       // lower index of the pair
+      const bool other_beats = beats(ov, oi, sv, si);
+      // descending block: the lower index keeps the winner
+      const bool take = (desc == lower) ? other_beats : !other_beats && (ov != sv || oi != si);
+      if (take) {
+        sv = ov;
+        si = oi;
       }
     }
   }
-
-  // ---- merge the 16 sorted lists ------------------------------------------------
-  s_lv[warp][lane] = top_v;
-  s_li[warp][lane] = top_i;
-  if (lane == 0) s_cnt[warp] = count;
+  s_lv[warp][lane] = sv;
+  s_li[warp][lane] = si;
   __syncthreads();
-  if (lane < count) {
-    int rank = lane;
-    for (int w = 0; w < kFastWarps; ++w) {
-      if (w == warp) continue;
-      // entries of list w that beat (top_v, top_i): the list is sorted, so this is the
-      // first position whose entry does not beat it
-      int lo = 0, hi = s_cnt[w];
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (beats(s_lv[w][mid], s_li[w][mid], top_v, top_i))
-          lo = mid + 1;
-        else
-          hi = mid;
+  // ---- merge (2): global rank of every lane best; rank M-1 is the threshold -------
+  {
+    const bool valid = si != 0x7fffffff;
+    if (valid) {
+      int rank = lane;
+      for (int w = 0; w < kFastWarps; ++w)
+        if (w != warp) rank += count_beating(s_lv[w], s_li[w], 32, sv, si);
+      if (rank == M - 1) {
+        s_tv = sv;
+        s_ti = si;
       }
-      rank += lo;
     }
+  }
+  __syncthreads();
+  // ---- merge (3): compact the entries that T does not beat -------------------------
+  {
+    const float tv = s_tv;
+    const int ti = s_ti;
+    const float ev[3] = {t3.v1, t3.v2, t3.v3};
+    const int ei[3] = {t3.i1, t3.i2, t3.i3};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      if (ei[e] != 0x7fffffff && !beats(tv, ti, ev[e], ei[e])) {
+        const int pos = atomicAdd(&s_nbuf, 1);
+        s_bv[pos] = ev[e];
+        s_bi[pos] = ei[e];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- merge (4): exact rank among the survivors ------------------------------------
+  const int nb = s_nbuf;
+  for (int t = tid; t < nb; t += kFastThreads) {
+    const float v = s_bv[t];
+    const int i = s_bi[t];
+    int rank = 0;
+    for (int j = 0; j < nb; ++j) rank += beats(s_bv[j], s_bi[j], v, i) ? 1 : 0;
+    if (rank < M) {
+      s_ov[rank] = v;
+      s_oi[rank] = i;
+    }
+  }
+  if (tid == 0) s_nout = min(nb, M);
+  __syncthreads();
+  // ---- check: could a lane have dropped a fourth entry that belongs to the top M? ----
+  const int nout = s_nout;
+  const bool has3 = t3.i3 != 0x7fffffff;
+  const bool risk = has3 && (nout < M || beats(t3.v3, t3.i3, s_ov[M - 1], s_oi[M - 1]));
+  const bool fallback = __syncthreads_or(risk ? 1 : 0) != 0;
+
+  if (!fallback) {
+    if (tid < nout) {
+      const size_t o = ((size_t)n * a.K + k) * M + tid;
+      const int ti = s_oi[tid];
+      const int y = (int)fdiv((uint32_t)ti, a.div_w1);
+      const int x = ti - y * W;
+      a.val_k[o] = s_ov[tid];
+      a.ind_k[2 * o] = (float)x;
+      a.ind_k[2 * o + 1] = (float)y;
+      a.tag_k[o] = bilinear_legacy(tag_src, th, tw, tsy, tsx, y, x);
+    }
+    return;
+  }
+
+  // ---- pass 2 (rare): exact per-warp lists, pre-filtered by the M-th result ---------
+  if (nout == M) {
+    ex.pre_v = s_ov[M - 1];
+    ex.pre_i = s_oi[M - 1];
+  }
+  if (rb < re)
+    scan_band<C, TWO_STAGE, MASK2X, true>(a, heat_hi, heat_lo, mask, nullptr, rb, re, lane, nms,
+                                          M, t3, ex);
+  __syncthreads();  // everyone has read s_ov / s_oi
+  s_lv[warp][lane] = ex.top_v;
+  s_li[warp][lane] = ex.top_i;
+  if (lane == 0) s_cnt[warp] = ex.count;
+  __syncthreads();
+  if (lane < ex.count) {
+    int rank = lane;
+    for (int w = 0; w < kFastWarps; ++w)
+      if (w != warp) rank += count_beating(s_lv[w], s_li[w], s_cnt[w], ex.top_v, ex.top_i);
     if (rank < M) {
       const size_t o = ((size_t)n * a.K + k) * M + rank;
-      const int y = (int)fdiv((uint32_t)top_i, a.div_w1);
-      const int x = top_i - y * W;
-      a.val_k[o] = top_v;
+      const int y = (int)fdiv((uint32_t)ex.top_i, a.div_w1);
+      const int x = ex.top_i - y * W;
+      a.val_k[o] = ex.top_v;
       a.ind_k[2 * o] = (float)x;
       a.ind_k[2 * o + 1] = (float)y;
       a.tag_k[o] = bilinear_legacy(tag_src, th, tw, tsy, tsx, y, x);
