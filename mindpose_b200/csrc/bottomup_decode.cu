@@ -450,8 +450,10 @@ __device__ __forceinline__ void scan_band(const BuArgs& a, const float* __restri
                                           const float* __restrict__ heat_lo,
                                           const uint8_t* __restrict__ mask, float* raw_out,
                                           int rb, int re, int lane, bool nms, int M, Top3& t3,
-                                          ExactList& ex) {
+                                          ExactList& ex, volatile float* s_kth, int warp_id) {
   const int H = a.h1, W = a.w1;
+  const int kth_rank = (M + kFastWarps - 1) / kFastWarps;
+  float t_lb = -INFINITY;
   const int x0 = lane * C;
   const bool active = x0 < W;
   const bool first_lane = lane == 0;
@@ -495,26 +497,51 @@ __device__ __forceinline__ void scan_band(const BuArgs& a, const float* __restri
       }
     }
     if (!EXACT) {
-      // a lane sees its pixels in increasing flat index, so an equal value never
-      // displaces an entry (the i-test only matters for -inf against the empty slot)
-      if (active) {
+      // A lane sees its pixels in increasing flat index, so an equal value never
+      // displaces an entry: strict compares.  t_lb is a lower bound of the plane's
+      // M-th best VALUE (see below), so values under it cannot matter; values equal
+      // to it can (ties are resolved by index), hence >=.
+      float rowmax = m[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) rowmax = fmaxf(rowmax, m[c]);
+      const bool want = active && rowmax > t3.v3 && rowmax >= t_lb;
+      if (__any_sync(0xffffffffu, want)) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           const float mv = m[c];
           const int idx = row_base + c;
-          if (mv > t3.v3 || (mv == t3.v3 && idx < t3.i3)) {
-            if (mv > t3.v1 || (mv == t3.v1 && idx < t3.i1)) {
-              t3.v3 = t3.v2, t3.i3 = t3.i2;
-              t3.v2 = t3.v1, t3.i2 = t3.i1;
-              t3.v1 = mv, t3.i1 = idx;
-            } else if (mv > t3.v2 || (mv == t3.v2 && idx < t3.i2)) {
-              t3.v3 = t3.v2, t3.i3 = t3.i2;
-              t3.v2 = mv, t3.i2 = idx;
-            } else {
-              t3.v3 = mv, t3.i3 = idx;
-            }
-          }
+          const bool g3 = active && mv > t3.v3 && mv >= t_lb;
+          const bool g2 = g3 && mv > t3.v2;
+          const bool g1 = g3 && mv > t3.v1;
+          t3.v3 = g2 ? t3.v2 : (g3 ? mv : t3.v3);
+          t3.i3 = g2 ? t3.i2 : (g3 ? idx : t3.i3);
+          t3.v2 = g1 ? t3.v1 : (g2 ? mv : t3.v2);
+          t3.i2 = g1 ? t3.i1 : (g2 ? idx : t3.i2);
+          t3.v1 = g1 ? mv : t3.v1;
+          t3.i1 = g1 ? idx : t3.i1;
         }
+      }
+      // Every 4 rows: each warp publishes the kth largest of its lane bests with
+      // k = ceil(M / warps); at least k elements of every band are >= its value, so the
+      // minimum over the bands is a lower bound of the plane's M-th best value.  Stale
+      // reads are only smaller, i.e. still valid.
+      if (((y - rb) & 3) == 3) {
+        float x = t3.v1, kth = -INFINITY;
+        for (int r = 0; r < kth_rank; ++r) {
+          float mx = x;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          const unsigned b = __ballot_sync(0xffffffffu, x == mx);
+          if (lane == __ffs(b) - 1) x = -INFINITY;
+          kth = mx;
+        }
+        if (lane == 0) s_kth[warp_id] = kth;
+        float o8 = lane < kFastWarps ? s_kth[lane] : INFINITY;
+#pragma unroll
+        for (int o = kFastWarps / 2; o > 0; o >>= 1)
+          o8 = fminf(o8, __shfl_xor_sync(0xffffffffu, o8, o));
+        o8 = __shfl_sync(0xffffffffu, o8, 0);
+        t_lb = fmaxf(t_lb, o8);
       }
     } else {
       bool cand[C];
@@ -585,6 +612,7 @@ __global__ void __launch_bounds__(kFastThreads)
   __shared__ int s_oi[32];
   __shared__ int s_nbuf, s_nout, s_ti;
   __shared__ float s_tv;
+  __shared__ float s_kth[kFastWarps];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.x / a.K, k = blockIdx.x - n * a.K;
@@ -618,6 +646,8 @@ __global__ void __launch_bounds__(kFastThreads)
     s_tv = -INFINITY;  // threshold "nothing is excluded"
     s_ti = 0x7fffffff;
   }
+  if (tid < kFastWarps) s_kth[tid] = -INFINITY;
+  __syncthreads();
 
   // ---- pass 1: per-lane top 3 ---------------------------------------------------
   Top3 t3;
@@ -629,7 +659,7 @@ __global__ void __launch_bounds__(kFastThreads)
   ex.pre_v = -INFINITY, ex.pre_i = 0x7fffffff;
   if (rb < re)
     scan_band<C, TWO_STAGE, MASK2X, false>(a, heat_hi, heat_lo, mask, raw_out, rb, re, lane, nms,
-                                           M, t3, ex);
+                                           M, t3, ex, s_kth, warp);
 
   // ---- merge (1): sort the lane bests of each warp (bitonic, descending) ----------
   float sv = t3.v1;
@@ -701,7 +731,9 @@ __global__ void __launch_bounds__(kFastThreads)
   // ---- check: could a lane have dropped a fourth entry that belongs to the top M? ----
   const int nout = s_nout;
   const bool has3 = t3.i3 != 0x7fffffff;
-  const bool risk = has3 && (nout < M || beats(t3.v3, t3.i3, s_ov[M - 1], s_oi[M - 1]));
+  // (a short union -- e.g. -inf pixels, which the strict compares never keep -- also
+  // goes to the exact pass)
+  const bool risk = nout < M || (has3 && beats(t3.v3, t3.i3, s_ov[M - 1], s_oi[M - 1]));
   const bool fallback = __syncthreads_or(risk ? 1 : 0) != 0;
 
   if (!fallback) {
@@ -725,7 +757,7 @@ __global__ void __launch_bounds__(kFastThreads)
   }
   if (rb < re)
     scan_band<C, TWO_STAGE, MASK2X, true>(a, heat_hi, heat_lo, mask, nullptr, rb, re, lane, nms,
-                                          M, t3, ex);
+                                          M, t3, ex, s_kth, warp);
   __syncthreads();  // everyone has read s_ov / s_oi
   s_lv[warp][lane] = ex.top_v;
   s_li[warp][lane] = ex.top_i;
