@@ -412,6 +412,102 @@ __device__ __forceinline__ void aggregate_row(const BuArgs& a, const float* __re
   }
 }
 
+// ---- lane-private cp.async ring (C = 8, two stages, 2x mask) ---------------------
+// Every lane needs exactly 80 bytes of a row: its 8 high-resolution columns (2 x 16 B),
+// its 4 low-resolution columns of the two source rows (2 x 16 B) and its 16 mask bytes.
+// They are copied global -> shared with cp.async one row ahead, so the DRAM round trip
+// of row r+1 overlaps the arithmetic of row r at no register cost.  A lane only ever
+// reads back what it copied itself: no barrier, just cp.async.wait_group.
+constexpr int kStageSeg = 512;                 // 32 lanes x 16 B
+constexpr int kStageSlot = 5 * kStageSeg;      // hi0 | hi1 | lowA | lowB | mask
+constexpr int kStageWarp = 2 * kStageSlot;     // two rows in flight per warp
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_1() {
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+}
+
+struct StagedRows {
+  unsigned char* ring;  // this warp's kStageWarp bytes
+  int first, last;      // rows are consumed in order first .. last
+};
+
+__device__ __forceinline__ void staged_issue(const BuArgs& a, const float* __restrict__ heat_hi,
+                                             const float* __restrict__ heat_lo,
+                                             const uint8_t* __restrict__ mask,
+                                             const StagedRows& st, int r, int lane, bool active) {
+  if (r <= st.last && active) {
+    unsigned char* slot = st.ring + ((r - st.first) & 1) * kStageSlot + lane * 16;
+    const int x0 = lane * 8;
+    const float* hi = heat_hi + (size_t)r * a.w1 + x0;
+    cp_async16(slot, hi);
+    cp_async16(slot + kStageSeg, hi + 4);
+    const int y0 = r >> 1, y1 = min(y0 + 1, a.h0 - 1);
+    cp_async16(slot + 2 * kStageSeg, heat_lo + (size_t)y0 * a.w0 + (x0 >> 1));
+    cp_async16(slot + 3 * kStageSeg, heat_lo + (size_t)y1 * a.w0 + (x0 >> 1));
+    const int my = min((int)floorf(__fmul_rn((float)r, a.msy)), a.mh - 1);
+    cp_async16(slot + 4 * kStageSeg, mask + (size_t)my * a.mw + 2 * x0);
+  }
+  cp_async_commit();  // one group per row, empty past the end: wait_group 1 stays exact
+}
+
+// Row r (the oldest row in flight) of the aggregated, masked map; then re-arms its slot
+// with row r + 2.  Same arithmetic as aggregate_row<8, true, true>; for the exact 1/2
+// scale the interpolation weights are 0 or 0.5 and "a + (b - a) * 0" is written as "a"
+// (identical for finite maps; only the sign of an exact zero can differ).
+__device__ __forceinline__ void staged_row(const BuArgs& a, const float* __restrict__ heat_hi,
+                                           const float* __restrict__ heat_lo,
+                                           const uint8_t* __restrict__ mask,
+                                           const StagedRows& st, int r, int lane, bool active,
+                                           bool last_lane, float (&v)[8]) {
+  cp_async_wait_1();
+  const unsigned char* slot = st.ring + ((r - st.first) & 1) * kStageSlot + lane * 16;
+  float4 h0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), h1 = h0;
+  float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+  uint4 mb = make_uint4(0, 0, 0, 0);
+  if (active) {
+    h0 = *reinterpret_cast<const float4*>(slot);
+    h1 = *reinterpret_cast<const float4*>(slot + kStageSeg);
+    qa = *reinterpret_cast<const float4*>(slot + 2 * kStageSeg);
+    qb = *reinterpret_cast<const float4*>(slot + 3 * kStageSeg);
+    mb = *reinterpret_cast<const uint4*>(slot + 4 * kStageSeg);
+  }
+  staged_issue(a, heat_hi, heat_lo, mask, st, r + 2, lane, active);
+  float la[5] = {qa.x, qa.y, qa.z, qa.w, 0.f}, lb[5] = {qb.x, qb.y, qb.z, qb.w, 0.f};
+  const float na = __shfl_down_sync(0xffffffffu, la[0], 1);
+  const float nb = __shfl_down_sync(0xffffffffu, lb[0], 1);
+  la[4] = last_lane ? la[3] : na;
+  lb[4] = last_lane ? lb[3] : nb;
+  v[0] = h0.x, v[1] = h0.y, v[2] = h0.z, v[3] = h0.w;
+  v[4] = h1.x, v[5] = h1.y, v[6] = h1.z, v[7] = h1.w;
+  if (active) {
+    const bool odd_row = r & 1;  // fy = 0.5 on odd rows, 0 on even rows
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = c >> 1;
+      float top = la[j], bot = lb[j];
+      if (c & 1) {
+        top = __fadd_rn(la[j], __fmul_rn(__fsub_rn(la[j + 1], la[j]), 0.5f));
+        bot = __fadd_rn(lb[j], __fmul_rn(__fsub_rn(lb[j + 1], lb[j]), 0.5f));
+      }
+      const float up = odd_row ? __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), 0.5f)) : top;
+      v[c] = __fmul_rn(__fadd_rn(v[c], up), 0.5f);
+    }
+    const uint32_t w[4] = {mb.x, mb.y, mb.z, mb.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if ((w[t] & 0xffu) == 0) v[2 * t] = 0.f;
+      if ((w[t] & 0xff0000u) == 0) v[2 * t + 1] = 0.f;
+    }
+  }
+}
+
 // horizontal 3-max of a row held C columns per lane
 template <int C>
 __device__ __forceinline__ void hmax3(const float (&v)[C], bool first_lane, bool last_lane,
@@ -445,12 +541,17 @@ struct ExactList {
 };
 
 // Scan rows [rb, re) of the plane: aggregate, NMS, feed survivors to the sink.
-template <int C, bool TWO_STAGE, bool MASK2X, bool EXACT>
+//
+// NMS state per lane: A = max(hm[y-1], hm[y]) and hm[y] (hm = horizontal 3-max of a row),
+// v[y]; when row y+1 arrives, pooled(y) = max(A, hm[y+1]) and A becomes max(hm[y], hm[y+1]).
+// The row loop is unrolled by two so the (v, hm) buffers swap roles without register moves.
+template <int C, bool TWO_STAGE, bool MASK2X, bool EXACT, bool STAGED>
 __device__ __forceinline__ void scan_band(const BuArgs& a, const float* __restrict__ heat_hi,
                                           const float* __restrict__ heat_lo,
                                           const uint8_t* __restrict__ mask, float* raw_out,
                                           int rb, int re, int lane, bool nms, int M, Top3& t3,
-                                          ExactList& ex, volatile float* s_kth, int warp_id) {
+                                          ExactList& ex, volatile float* s_kth, int warp_id,
+                                          unsigned char* ring) {
   const int H = a.h1, W = a.w1;
   const int kth_rank = (M + kFastWarps - 1) / kFastWarps;
   float t_lb = -INFINITY;
@@ -458,91 +559,113 @@ __device__ __forceinline__ void scan_band(const BuArgs& a, const float* __restri
   const bool active = x0 < W;
   const bool first_lane = lane == 0;
   const bool last_lane = x0 + C >= W;  // also true for inactive lanes
-  float hm_prev[C], hm_cur[C], hm_new[C], v_cur[C], v_new[C];
+  float A[C], hA[C], hB[C], vA[C], vB[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) hm_prev[c] = hm_cur[c] = hm_new[c] = v_new[c] = -INFINITY;
-  if (nms && rb > 0) {
-    aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, rb - 1, x0, active, last_lane,
-                                        v_cur);
-    hmax3<C>(v_cur, first_lane, last_lane, hm_prev);
+  for (int c = 0; c < C; ++c) A[c] = hA[c] = hB[c] = vA[c] = vB[c] = -INFINITY;
+  StagedRows st;
+  st.ring = ring;
+  st.first = (nms && rb > 0) ? rb - 1 : rb;
+  st.last = (nms && re < H) ? re : re - 1;
+  if (STAGED) {
+    staged_issue(a, heat_hi, heat_lo, mask, st, st.first, lane, active);
+    staged_issue(a, heat_hi, heat_lo, mask, st, st.first + 1, lane, active);
   }
-  aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, rb, x0, active, last_lane,
-                                      v_cur);
-  if (nms) hmax3<C>(v_cur, first_lane, last_lane, hm_cur);
-  for (int y = rb; y < re; ++y) {
+  // next row of the aggregated map, in order
+#define PC_BU_ROW(ROW, OUT)                                                                 \
+  do {                                                                                      \
+    if constexpr (STAGED)                                                                   \
+      staged_row(a, heat_hi, heat_lo, mask, st, (ROW), lane, active, last_lane, (OUT));     \
+    else                                                                                    \
+      aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, (ROW), x0, active,     \
+                                          last_lane, (OUT));                                \
+  } while (0)
+
+  // Publish this warp's kth-largest lane best (k = ceil(M / warps)) and refresh t_lb, a
+  // lower bound of the plane's M-th best VALUE: at least k elements of every band are >=
+  // its kth, so the minimum over the bands has >= M elements above it.  Stale reads of
+  // other warps' slots are only smaller, i.e. still valid.
+  auto refresh_bound = [&]() {
+    float x = t3.v1, kth = -INFINITY;
+    for (int r = 0; r < kth_rank; ++r) {
+      float mx = x;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const unsigned b = __ballot_sync(0xffffffffu, x == mx);
+      if (lane == __ffs(b) - 1) x = -INFINITY;
+      kth = mx;
+    }
+    if (lane == 0) s_kth[warp_id] = kth;
+    float o8 = lane < kFastWarps ? s_kth[lane] : INFINITY;
+#pragma unroll
+    for (int o = kFastWarps / 2; o > 0; o >>= 1)
+      o8 = fminf(o8, __shfl_xor_sync(0xffffffffu, o8, o));
+    o8 = __shfl_sync(0xffffffffu, o8, 0);
+    t_lb = fmaxf(t_lb, o8);
+  };
+
+  // one row: vc / hc hold row y, vn / hn receive row y + 1
+  auto step = [&](int y, float (&vc)[C], float (&hc)[C], float (&vn)[C], float (&hn)[C]) {
     if (!EXACT && raw_out && active) {
 #pragma unroll
       for (int q = 0; q < C / 4; ++q)
         st_stream_f4(raw_out + (size_t)y * W + x0 + 4 * q,
-                     make_float4(v_cur[4 * q], v_cur[4 * q + 1], v_cur[4 * q + 2],
-                                 v_cur[4 * q + 3]));
+                     make_float4(vc[4 * q], vc[4 * q + 1], vc[4 * q + 2], vc[4 * q + 3]));
     }
     const bool more = y + 1 < re || (nms && y + 1 < H);
     if (more) {
-      aggregate_row<C, TWO_STAGE, MASK2X>(a, heat_hi, heat_lo, mask, y + 1, x0, active,
-                                          last_lane, v_new);
-      if (nms) hmax3<C>(v_new, first_lane, last_lane, hm_new);
+      PC_BU_ROW(y + 1, vn);
+      if (nms) hmax3<C>(vn, first_lane, last_lane, hn);
     } else {
 #pragma unroll
-      for (int c = 0; c < C; ++c) hm_new[c] = -INFINITY;
+      for (int c = 0; c < C; ++c) hn[c] = -INFINITY;
     }
     const int row_base = y * W + x0;
     float m[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      m[c] = v_cur[c];
+      m[c] = vc[c];
       if (nms) {
-        const float pooled = fmaxf(fmaxf(hm_prev[c], hm_cur[c]), hm_new[c]);
+        const float pooled = fmaxf(A[c], hn[c]);
         m[c] = __fmul_rn(m[c], pooled == m[c] ? 1.f : 0.f);
+        A[c] = fmaxf(hc[c], hn[c]);
       }
     }
     if (!EXACT) {
-      // A lane sees its pixels in increasing flat index, so an equal value never
-      // displaces an entry: strict compares.  t_lb is a lower bound of the plane's
-      // M-th best VALUE (see below), so values under it cannot matter; values equal
-      // to it can (ties are resolved by index), hence >=.
+      // Per-lane top 3.  A lane sees its pixels in increasing flat index and takes the
+      // qualifying values of a row largest first (equal values left to right), so an
+      // equal value never displaces an entry: strict compares.  Values under t_lb cannot
+      // matter; values equal to it can (ties are resolved by index), hence >=.
       float rowmax = m[0];
 #pragma unroll
       for (int c = 1; c < C; ++c) rowmax = fmaxf(rowmax, m[c]);
-      const bool want = active && rowmax > t3.v3 && rowmax >= t_lb;
+      bool want = active && rowmax > t3.v3 && rowmax >= t_lb;
       if (__any_sync(0xffffffffu, want)) {
+        while (want) {
+          int cb = 0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float mv = m[c];
-          const int idx = row_base + c;
-          const bool g3 = active && mv > t3.v3 && mv >= t_lb;
-          const bool g2 = g3 && mv > t3.v2;
-          const bool g1 = g3 && mv > t3.v1;
-          t3.v3 = g2 ? t3.v2 : (g3 ? mv : t3.v3);
-          t3.i3 = g2 ? t3.i2 : (g3 ? idx : t3.i3);
-          t3.v2 = g1 ? t3.v1 : (g2 ? mv : t3.v2);
-          t3.i2 = g1 ? t3.i1 : (g2 ? idx : t3.i2);
-          t3.v1 = g1 ? mv : t3.v1;
-          t3.i1 = g1 ? idx : t3.i1;
+          for (int c = C - 1; c >= 0; --c)
+            if (m[c] == rowmax) cb = c;
+          const int idx = row_base + cb;
+          if (rowmax > t3.v1) {
+            t3.v3 = t3.v2, t3.i3 = t3.i2;
+            t3.v2 = t3.v1, t3.i2 = t3.i1;
+            t3.v1 = rowmax, t3.i1 = idx;
+          } else if (rowmax > t3.v2) {
+            t3.v3 = t3.v2, t3.i3 = t3.i2;
+            t3.v2 = rowmax, t3.i2 = idx;
+          } else {
+            t3.v3 = rowmax, t3.i3 = idx;
+          }
+          rowmax = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            if (c == cb) m[c] = -INFINITY;
+            rowmax = fmaxf(rowmax, m[c]);
+          }
+          want = rowmax > t3.v3 && rowmax >= t_lb;
         }
       }
-      // Every 4 rows: each warp publishes the kth largest of its lane bests with
-      // k = ceil(M / warps); at least k elements of every band are >= its value, so the
-      // minimum over the bands is a lower bound of the plane's M-th best value.  Stale
-      // reads are only smaller, i.e. still valid.
-      if (((y - rb) & 3) == 3) {
-        float x = t3.v1, kth = -INFINITY;
-        for (int r = 0; r < kth_rank; ++r) {
-          float mx = x;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          const unsigned b = __ballot_sync(0xffffffffu, x == mx);
-          if (lane == __ffs(b) - 1) x = -INFINITY;
-          kth = mx;
-        }
-        if (lane == 0) s_kth[warp_id] = kth;
-        float o8 = lane < kFastWarps ? s_kth[lane] : INFINITY;
-#pragma unroll
-        for (int o = kFastWarps / 2; o > 0; o >>= 1)
-          o8 = fminf(o8, __shfl_xor_sync(0xffffffffu, o8, o));
-        o8 = __shfl_sync(0xffffffffu, o8, 0);
-        t_lb = fmaxf(t_lb, o8);
-      }
+      if (((y - rb) & 7) == 7) refresh_bound();
     } else {
       bool cand[C];
       bool any = false;
@@ -575,13 +698,25 @@ __device__ __forceinline__ void scan_band(const BuArgs& a, const float* __restri
         }
       }
     }
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      hm_prev[c] = hm_cur[c];
-      hm_cur[c] = hm_new[c];
-      v_cur[c] = v_new[c];
-    }
+  };
+
+  if (nms && rb > 0) {
+    PC_BU_ROW(rb - 1, vA);
+    hmax3<C>(vA, first_lane, last_lane, hB);  // hB = hm[rb - 1]
   }
+  PC_BU_ROW(rb, vA);
+  if (nms) {
+    hmax3<C>(vA, first_lane, last_lane, hA);
+#pragma unroll
+    for (int c = 0; c < C; ++c) A[c] = fmaxf(hB[c], hA[c]);
+  }
+  for (int y = rb; y < re; y += 2) {
+    step(y, vA, hA, vB, hB);
+    if (y + 1 < re) step(y + 1, vB, hB, vA, hA);
+  }
+#undef PC_BU_ROW
+  if (!EXACT) refresh_bound();  // final value of this band for the merge
+  if (STAGED) asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // entries of the sorted list (lv, li)[0..n) that beat (v, i)
@@ -601,7 +736,7 @@ __device__ __forceinline__ int count_beating(const float* lv, const int* li, int
 constexpr int kFastBuf = 3 * kFastThreads;
 
 template <int C, bool TWO_STAGE, bool MASK2X>
-__global__ void __launch_bounds__(kFastThreads)
+__global__ void __launch_bounds__(kFastThreads, (C <= 8) ? 3 : 1)
     bottomup_decode_fast_kernel(const BuArgs a) {
   __shared__ float s_lv[kFastWarps][32];
   __shared__ int s_li[kFastWarps][32];
@@ -614,10 +749,14 @@ __global__ void __launch_bounds__(kFastThreads)
   __shared__ float s_tv;
   __shared__ float s_kth[kFastWarps];
 
+  constexpr bool STAGED = (C == 8) && TWO_STAGE && MASK2X;
+  extern __shared__ __align__(16) unsigned char s_ring[];  // kFastWarps * kStageWarp if STAGED
+
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.x / a.K, k = blockIdx.x - n * a.K;
   const int H = a.h1, W = a.w1, M = a.M;
   const bool nms = a.use_nms && a.nms_k == 3;
+  unsigned char* ring = STAGED ? s_ring + warp * kStageWarp : nullptr;
 
   const float* heat_hi;
   const float* heat_lo = nullptr;
@@ -658,55 +797,20 @@ __global__ void __launch_bounds__(kFastThreads)
   ex.last_v = -INFINITY, ex.last_i = 0x7fffffff;
   ex.pre_v = -INFINITY, ex.pre_i = 0x7fffffff;
   if (rb < re)
-    scan_band<C, TWO_STAGE, MASK2X, false>(a, heat_hi, heat_lo, mask, raw_out, rb, re, lane, nms,
-                                           M, t3, ex, s_kth, warp);
+    scan_band<C, TWO_STAGE, MASK2X, false, STAGED>(a, heat_hi, heat_lo, mask, raw_out, rb, re,
+                                                   lane, nms, M, t3, ex, s_kth, warp, ring);
 
-  // ---- merge (1): sort the lane bests of each warp (bitonic, descending) ----------
-  float sv = t3.v1;
-  int si = t3.i1;
-#pragma unroll
-  for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-    for (int j = kk >> 1; j > 0; j >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, sv, j);
-      const int oi = __shfl_xor_sync(0xffffffffu, si, j);
-      const bool desc = (lane & kk) == 0;       // direction of this lane's block
-      const bool lower = (lane & j) == 0;       // lower index of the pair
-      const bool other_beats = beats(ov, oi, sv, si);
-      // descending block: the lower index keeps the winner
-      const bool take = (desc == lower) ? other_beats : !other_beats && (ov != sv || oi != si);
-      if (take) {
-        sv = ov;
-        si = oi;
-      }
-    }
-  }
-  s_lv[warp][lane] = sv;
-  s_li[warp][lane] = si;
-  __syncthreads();
-  // ---- merge (2): global rank of every lane best; rank M-1 is the threshold -------
+  // ---- merge: entries that reach the plane-wide bound are compacted ... -------------
+  __syncthreads();  // every band has published its final kth
   {
-    const bool valid = si != 0x7fffffff;
-    if (valid) {
-      int rank = lane;
-      for (int w = 0; w < kFastWarps; ++w)
-        if (w != warp) rank += count_beating(s_lv[w], s_li[w], 32, sv, si);
-      if (rank == M - 1) {
-        s_tv = sv;
-        s_ti = si;
-      }
-    }
-  }
-  __syncthreads();
-  // ---- merge (3): compact the entries that T does not beat -------------------------
-  {
-    const float tv = s_tv;
-    const int ti = s_ti;
+    float tl = s_kth[0];
+#pragma unroll
+    for (int w = 1; w < kFastWarps; ++w) tl = fminf(tl, s_kth[w]);
     const float ev[3] = {t3.v1, t3.v2, t3.v3};
     const int ei[3] = {t3.i1, t3.i2, t3.i3};
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-      if (ei[e] != 0x7fffffff && !beats(tv, ti, ev[e], ei[e])) {
+      if (ei[e] != 0x7fffffff && ev[e] >= tl) {
         const int pos = atomicAdd(&s_nbuf, 1);
         s_bv[pos] = ev[e];
         s_bi[pos] = ei[e];
@@ -714,7 +818,7 @@ __global__ void __launch_bounds__(kFastThreads)
     }
   }
   __syncthreads();
-  // ---- merge (4): exact rank among the survivors ------------------------------------
+  // ---- ... and ranked exactly (value desc, flat index asc) ----------------------------
   const int nb = s_nbuf;
   for (int t = tid; t < nb; t += kFastThreads) {
     const float v = s_bv[t];
@@ -756,8 +860,8 @@ __global__ void __launch_bounds__(kFastThreads)
     ex.pre_i = s_oi[M - 1];
   }
   if (rb < re)
-    scan_band<C, TWO_STAGE, MASK2X, true>(a, heat_hi, heat_lo, mask, nullptr, rb, re, lane, nms,
-                                          M, t3, ex, s_kth, warp);
+    scan_band<C, TWO_STAGE, MASK2X, true, STAGED>(a, heat_hi, heat_lo, mask, nullptr, rb, re,
+                                                  lane, nms, M, t3, ex, s_kth, warp, ring);
   __syncthreads();  // everyone has read s_ov / s_oi
   s_lv[warp][lane] = ex.top_v;
   s_li[warp][lane] = ex.top_i;
@@ -886,8 +990,14 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
     const bool mask2x = p->mask_w == 2 * p->w1 && (uintptr_t)d_mask % 16 == 0;
     BuArgs b = a;
     if (p->use_nms && p->nms_kernel == 1) b.use_nms = 0;  // a 1x1 pool keeps every value
-#define PC_BU_LAUNCH(CC, TWO, M2X) \
-  bottomup_decode_fast_kernel<CC, TWO, M2X><<<grid, kFastThreads, 0, st>>>(b)
+#define PC_BU_LAUNCH(CC, TWO, M2X)                                                        \
+  do {                                                                                    \
+    const size_t dyn = ((CC) == 8 && (TWO) && (M2X)) ? (size_t)kFastWarps * kStageWarp : 0; \
+    if (dyn)                                                                              \
+      PC_CUDA(cudaFuncSetAttribute(bottomup_decode_fast_kernel<CC, TWO, M2X>,             \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    bottomup_decode_fast_kernel<CC, TWO, M2X><<<grid, kFastThreads, dyn, st>>>(b);        \
+  } while (0)
 #define PC_BU_PICK(CC)                                 \
   do {                                                 \
     if (two) {                                         \
