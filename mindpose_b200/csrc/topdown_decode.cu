@@ -9,22 +9,26 @@
 // float32 plane (and, for the flip test, the plane flipped[n, flip_index[k]])
 // is contiguous in HBM, so a single elected producer thread moves it into a
 // shared-memory stage with one or two 1-D TMA bulk copies (cp.async.bulk +
-// mbarrier complete_tx).  Seven consumer warps each own one stage at a time:
-// flip-average on the fly, warp-shuffle argmax (value desc, flat index asc),
-// sub-pixel refinement (quarter offset or DARK/UDP Taylor step) out of the
-// staged planes, back-projection, 12-byte result.  Every heatmap byte crosses
-// HBM once; nothing but the results is written.
+// mbarrier complete_tx).  The eight consumer warps form groups of G warps; a
+// group owns one item at a time and its members scan 1/G of the plane each
+// (flip-average on the fly, float4-group argmax, value desc / flat index asc).
+// G = 1 for small planes (many stages fit, every warp works on its own item);
+// when a plane pair is 55 KB and only four stages fit, G = 4 keeps the time a
+// stage is held short, so the other stages can be in flight.  The partial
+// results meet in shared memory and ONE warp of the group (round robin)
+// finishes the item: sub-pixel refinement (quarter offset or DARK/UDP Taylor
+// step) out of the staged planes, back-projection, 12-byte result.  Every
+// heatmap byte crosses HBM once; only the results are written.
 #include <math.h>
 
 #include "common.cuh"
 
 namespace pc {
 
-constexpr int kDecodeThreads = 256;
-constexpr int kConsumerWarps = kDecodeThreads / 32 - 1;
+constexpr int kConsumerWarps = 16;
+constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;  // + the producer warp
 constexpr int kMaxStages = 12;
 constexpr int kDarkSamples = 7;
-constexpr int kDarkWinMax = (PC_MAX_DARK_KERNEL + 2) * (PC_MAX_DARK_KERNEL + 2);
 
 struct DecodeArgs {
   const float* heatmap;
@@ -46,6 +50,8 @@ struct DecodeArgs {
   int32_t ks;    // DARK kernel size
   int32_t shift_heatmap;
   int32_t stages;
+  int32_t group;  // consumer warps per item (1, 2, 4, 8 or 16)
+  int32_t win_floats, row_floats;  // per-warp DARK scratch (0 unless mode == 2)
   uint32_t stage_floats;  // floats per stage (HW or 2*HW)
   int32_t vec_ok;         // W % 4 == 0
 };
@@ -117,6 +123,139 @@ __device__ __forceinline__ float blur_row(const float* __restrict__ wrow,
   return acc;
 }
 
+// DARK / UDP Taylor step (top_down_decoder.py:171-205) around the peak (px, py): returns
+// inv(H + 1e-7 I) * d, valid on lane 0.
+// (1) the (ks+2)^2 window of the averaged map around the peak, zero outside the map (the
+//     blur's "same" padding), goes to a per-warp scratch once;
+// (2) 7 samples x ks kernel rows = 7*ks independent row sums out of the scratch (each a
+//     left-to-right float32 chain -- up to three chains per lane run interleaved);
+// (3) lanes 0..6 add their rows top to bottom, clip, log; out-of-map samples are the zero
+//     padding of the LOG map.
+// samples: 0:i  1:ix1  2:iy1  3:ix1y1  4:ix1_y1_  5:ix1_  6:iy1_
+// KS = 11 is the sigma = 2 recipe with everything unrolled; KS = 0 is any odd size.
+template <bool FLIP, int KS>
+__device__ __forceinline__ float2 dark_offset(const float* hm, const float* fm, int W, int H,
+                                              int px, int py, int shift, const DecodeArgs& a,
+                                              const float* s_kernel, float* my_rows,
+                                              float* my_win, int lane) {
+  const int ks = KS > 0 ? KS : a.ks;
+  const int r = (ks - 1) >> 1, wsz = ks + 2;
+  const int oy = py - r - 1, ox = px - r - 1;
+  const int nwin = wsz * wsz;
+  constexpr int kFillRounds = KS > 0 ? ((KS + 2) * (KS + 2) + 31) / 32 : 1;
+  if constexpr (KS > 0) {
+#pragma unroll
+    for (int i = 0; i < kFillRounds; ++i) {
+      const int e = lane + 32 * i;
+      if (e < nwin) {
+        const int wy = e / (KS + 2), wx = e - wy * (KS + 2);
+        const int yy = oy + wy, xx = ox + wx;
+        float v = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = map_at<FLIP>(hm, fm, W, yy, xx, shift);
+        my_win[e] = v;
+      }
+    }
+  } else {
+    for (int e = lane; e < nwin; e += 32) {
+      const int wy = (int)fdiv((uint32_t)e, a.divWin);
+      const int wx = e - wy * wsz;
+      const int yy = oy + wy, xx = ox + wx;
+      float v = 0.f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = map_at<FLIP>(hm, fm, W, yy, xx, shift);
+      my_win[e] = v;
+    }
+  }
+  __syncwarp();
+  const int ntask = kDarkSamples * ks;
+  if constexpr (KS > 0) {
+    constexpr int kChains = (kDarkSamples * KS + 31) / 32;  // 3 for KS = 11
+    const float* vr[kChains];
+    const float* wr[kChains];
+    float acc[kChains];
+    int slot[kChains];
+#pragma unroll
+    for (int u = 0; u < kChains; ++u) {
+      const int t = lane + 32 * u;
+      const int tt = t < ntask ? t : 0;
+      const int smp = tt / KS, ky = tt - smp * KS;
+      const int dxs = (smp == 1 || smp == 3) ? 1 : ((smp == 4 || smp == 5) ? -1 : 0);
+      const int dys = (smp == 2 || smp == 3) ? 1 : ((smp == 4 || smp == 6) ? -1 : 0);
+      vr[u] = my_win + (1 + dys + ky) * (KS + 2) + (1 + dxs);
+      wr[u] = s_kernel + ky * KS;
+      slot[u] = t < ntask ? smp * PC_MAX_DARK_KERNEL + ky : -1;
+      acc[u] = __fmul_rn(wr[u][0], vr[u][0]);
+    }
+#pragma unroll
+    for (int kx = 1; kx < KS; ++kx)
+#pragma unroll
+      for (int u = 0; u < kChains; ++u)
+        acc[u] = __fadd_rn(acc[u], __fmul_rn(wr[u][kx], vr[u][kx]));
+#pragma unroll
+    for (int u = 0; u < kChains; ++u)
+      if (slot[u] >= 0) my_rows[slot[u]] = acc[u];
+  } else {
+    for (int t = lane; t < ntask; t += 32) {
+      const int smp = (int)fdiv((uint32_t)t, a.divKs), ky = t - smp * ks;
+      const int dxs = (smp == 1 || smp == 3) ? 1 : ((smp == 4 || smp == 5) ? -1 : 0);
+      const int dys = (smp == 2 || smp == 3) ? 1 : ((smp == 4 || smp == 6) ? -1 : 0);
+      my_rows[smp * PC_MAX_DARK_KERNEL + ky] =
+          blur_row<0>(s_kernel + ky * ks, my_win + (1 + dys + ky) * wsz + (1 + dxs), ks);
+    }
+  }
+  __syncwarp();
+  float lg = 0.f;
+  if (lane < kDarkSamples) {
+    const int smp = lane;
+    const int dxs = (smp == 1 || smp == 3) ? 1 : ((smp == 4 || smp == 5) ? -1 : 0);
+    const int dys = (smp == 2 || smp == 3) ? 1 : ((smp == 4 || smp == 6) ? -1 : 0);
+    const int sy = py + dys, sx = px + dxs;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+      const float* rows = my_rows + smp * PC_MAX_DARK_KERNEL;
+      float tot = rows[0];
+      if (KS > 0) {
+#pragma unroll
+        for (int ky = 1; ky < KS; ++ky) tot = __fadd_rn(tot, rows[ky]);
+      } else {
+        for (int ky = 1; ky < ks; ++ky) tot = __fadd_rn(tot, rows[ky]);
+      }
+      tot = fminf(fmaxf(tot, 0.001f), 50.f);
+      // correctly rounded float32 log (fp64 log rounded once): logf's last-ulp differences
+      // become a full float32 ulp (> 1e-4 px) of image coordinates beyond 1024
+      lg = (float)log((double)tot);
+    }  // else: the reference zero-pads the LOG map -> 0.0
+  }
+  __syncwarp();  // my_rows / my_win are reused by this warp's next item
+  const float i_ = __shfl_sync(0xffffffffu, lg, 0);
+  const float ix1 = __shfl_sync(0xffffffffu, lg, 1);
+  const float iy1 = __shfl_sync(0xffffffffu, lg, 2);
+  const float ix1y1 = __shfl_sync(0xffffffffu, lg, 3);
+  const float ix1_y1_ = __shfl_sync(0xffffffffu, lg, 4);
+  const float ix1_ = __shfl_sync(0xffffffffu, lg, 5);
+  const float iy1_ = __shfl_sync(0xffffffffu, lg, 6);
+  const float dx = __fmul_rn(0.5f, __fsub_rn(ix1, ix1_));
+  const float dy = __fmul_rn(0.5f, __fsub_rn(iy1, iy1_));
+  const float two_i = __fmul_rn(2.f, i_);
+  const float dxx = __fadd_rn(__fsub_rn(ix1, two_i), ix1_);
+  const float dyy = __fadd_rn(__fsub_rn(iy1, two_i), iy1_);
+  float t = __fsub_rn(ix1y1, ix1);
+  t = __fsub_rn(t, iy1);
+  t = __fadd_rn(t, i_);
+  t = __fadd_rn(t, i_);
+  t = __fsub_rn(t, ix1_);
+  t = __fsub_rn(t, iy1_);
+  t = __fadd_rn(t, ix1_y1_);
+  const float dxy = __fmul_rn(0.5f, t);
+  const float ha = __fadd_rn(dxx, 1e-7f), hd = __fadd_rn(dyy, 1e-7f), hb = dxy;
+  const float det = __fsub_rn(__fmul_rn(ha, hd), __fmul_rn(hb, hb));
+  const float i00 = __fdiv_rn(hd, det);
+  const float i01 = __fdiv_rn(-hb, det);
+  const float i11 = __fdiv_rn(ha, det);
+  float2 o;
+  o.x = __fadd_rn(__fmul_rn(i00, dx), __fmul_rn(i01, dy));
+  o.y = __fadd_rn(__fmul_rn(i01, dx), __fmul_rn(i11, dy));
+  return o;
+}
+
 template <bool FLIP>
 __global__ void __launch_bounds__(kDecodeThreads, 1)
     topdown_decode_kernel(const DecodeArgs a, const __grid_constant__ DecodeTables tab) {
@@ -125,10 +264,13 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
   const size_t stage_bytes_total = (size_t)a.stages * a.stage_floats * sizeof(float);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + stage_bytes_total);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  volatile uint32_t* s_done = reinterpret_cast<volatile uint32_t*>(empty_bar + kMaxStages);
-  float* s_kernel = reinterpret_cast<float*>(const_cast<uint32_t*>(s_done) + kMaxStages);
-  float* s_rows = s_kernel + PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL;  // [warps][7][17]
-  float* s_win = s_rows + kConsumerWarps * kDarkSamples * PC_MAX_DARK_KERNEL;  // [warps][19*19]
+  uint64_t* part_bar = empty_bar + kMaxStages;
+  volatile uint32_t* s_done = reinterpret_cast<volatile uint32_t*>(part_bar + kMaxStages);
+  float* s_part_v = reinterpret_cast<float*>(const_cast<uint32_t*>(s_done) + kMaxStages);  // [stages][warps]
+  int* s_part_i = reinterpret_cast<int*>(s_part_v + kMaxStages * kConsumerWarps);
+  float* s_kernel = reinterpret_cast<float*>(s_part_i + kMaxStages * kConsumerWarps);
+  float* s_rows = s_kernel + PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL;  // [groups][7][17]
+  float* s_win = s_rows + (kConsumerWarps / a.group) * a.row_floats;  // [groups][(ks+2)^2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,6 +280,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&part_bar[s], a.group);
       s_done[s] = 0;
     }
     fence_mbar_init();
@@ -186,34 +329,28 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
   const int cw = warp - 1;
   const int W = a.W, H = a.H, HW = a.HW;
   const int shift = a.shift_heatmap;
-  float* my_rows = s_rows + cw * (kDarkSamples * PC_MAX_DARK_KERNEL);
-  float* my_win = s_win + cw * kDarkWinMax;
 
-  for (int64_t j = cw; j < count; j += kConsumerWarps) {
+
+  // group g of G warps owns items g, g + NG, ...; member r scans units [q_lo, q_hi)
+  const int G = a.group, NG = kConsumerWarps / G;
+  const int grp = cw / G, mem = cw - grp * G;
+  // DARK scratch of the group (one finisher per group at a time)
+  float* my_rows = s_rows + grp * a.row_floats;
+  float* my_win = s_win + grp * a.win_floats;
+  const int units = a.vec_ok ? (HW >> 2) : HW;
+  const int per_warp = ((units + G * 32 - 1) / (G * 32)) * 32;
+  const int q_lo = min(units, mem * per_warp), q_hi = min(units, q_lo + per_warp);
+
+  for (int64_t j = grp; j < count; j += NG) {
     const int s = (int)(j % S);
     const uint32_t round = (uint32_t)(j / S);
-    const int64_t item = first + j * gridDim.x;
-    const int64_t n = item / a.K;
-    const int k = (int)(item - n * a.K);
-
-    // crop geometry, fetched before the wait so its latency hides behind the TMA
-    float cx = 0.f, cy = 0.f, sw = 0.f, sh = 0.f, sc = 0.f;
-    if (lane == 0) {
-      cx = __ldg(a.center + 2 * n);
-      cy = __ldg(a.center + 2 * n + 1);
-      sw = __ldg(a.scale + 2 * n);
-      sh = __ldg(a.scale + 2 * n + 1);
-      if (k == 0) sc = __ldg(a.score + n);
-    }
-
-    // Consumer warps and stages are decoupled (7 warps, 2..12 stages) and bulk copies
-    // complete out of order, so this warp can get here while an EARLIER round of the
-    // same stage is still being read by another warp -- possibly two or more rounds
-    // back when there are fewer stages than warps.  A parity wait is only meaningful
-    // one phase ahead, so the rounds of a stage are first put in order with a plain
-    // counter (s_done[s] = number of rounds of stage s consumed so far); once round-1
-    // has been consumed, full_bar[s] is in phase `round` or has just completed it, and
-    // the parity wait is exact.
+    // Groups and stages are decoupled and bulk copies complete out of order, so a group
+    // can get here while an EARLIER round of the same stage has not even landed or is
+    // still being read by another group.  A parity wait is only meaningful one phase
+    // ahead, so the rounds of a stage are first put in order with a plain counter
+    // (s_done[s] = rounds of stage s finished so far); once round-1 is finished,
+    // full_bar[s] is in phase `round` or has just completed it and the parity wait is
+    // exact.
     while (s_done[s] != round) __nanosleep(32);
     mbar_wait(&full_bar[s], round & 1);
     const float* hm = stage_base + (size_t)s * a.stage_floats;
@@ -227,12 +364,12 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
       // reached it; the element inside the group is resolved after the loop.  With the
       // flip test the comparison runs on the sums h + fh: halving is exact (and so
       // order preserving) unless the result is subnormal, which is redone below.
-      const int nvec = HW >> 2, wq = W >> 2;
-      int y = (int)fdiv((uint32_t)lane, a.divWq);
-      int xq = lane - y * wq;
+      const int wq = W >> 2;
+      int y = (int)fdiv((uint32_t)(q_lo + lane), a.divWq);
+      int xq = q_lo + lane - y * wq;
       int bq = -1;
 #pragma unroll 4
-      for (int q = lane; q < nvec; q += 32) {
+      for (int q = q_lo + lane; q < q_hi; q += 32) {
         const float4 v = quad_at<FLIP>(hm, fm, W, q, y, xq, wq, shift);
         const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
         if (m > bv) {
@@ -253,7 +390,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
         bi = (bq << 2) + c;
       }
     } else {
-      for (int idx = lane; idx < HW; idx += 32) {
+      for (int idx = q_lo + lane; idx < q_hi; idx += 32) {
         const int y = (int)fdiv((uint32_t)idx, a.divW);
         const int x = idx - y * W;
         float v = hm[idx];
@@ -273,6 +410,41 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
         bi = oi;
       }
     }
+    // this warp is done with the planes (the reduction consumed every lane's loads):
+    // publish the partial result; the item's finisher collects all of them
+    if (lane == 0) {
+      s_part_v[s * kConsumerWarps + mem] = bv;
+      s_part_i[s * kConsumerWarps + mem] = bi;
+      mbar_arrive(&part_bar[s]);
+    }
+    if (mem != (int)((j / NG) % G)) continue;
+
+    // ---------------- finisher of item j ------------------------------------------
+    const int64_t item = first + j * gridDim.x;
+    const int64_t n = item / a.K;
+    const int k = (int)(item - n * a.K);
+    float cx = 0.f, cy = 0.f, sw = 0.f, sh = 0.f, sc = 0.f;
+    if (lane == 0) {
+      cx = __ldg(a.center + 2 * n);
+      cy = __ldg(a.center + 2 * n + 1);
+      sw = __ldg(a.scale + 2 * n);
+      sh = __ldg(a.scale + 2 * n + 1);
+      if (k == 0) sc = __ldg(a.score + n);
+    }
+    mbar_wait(&part_bar[s], round & 1);
+    bv = lane < G ? s_part_v[s * kConsumerWarps + lane] : -INFINITY;
+    bi = lane < G ? s_part_i[s * kConsumerWarps + lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = kConsumerWarps / 2; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    bv = __shfl_sync(0xffffffffu, bv, 0);
+    bi = __shfl_sync(0xffffffffu, bi, 0);
     if (FLIP) {
       if (bi != 0x7fffffff && fabsf(bv) < 4.7019774e-38f /* 2^-124 */) {
         // halves of sums this small can round: redo the scan on the exact averages
@@ -320,82 +492,19 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
       }
     } else if (a.mode == 2) {
       // ---- DARK / UDP Taylor step (top_down_decoder.py:171-205) -------------
-      // (1) the (ks+2)^2 window of the averaged map around the peak, zero outside the
-      //     map (the blur's "same" padding), goes to a per-warp scratch once;
-      // (2) 7 samples x ks kernel rows = 7*ks independent row sums out of the scratch;
-      // (3) lanes 0..6 add their rows top to bottom, clip, log; out-of-map samples are
-      //     the zero padding of the LOG map.
-      // samples: 0:i  1:ix1  2:iy1  3:ix1y1  4:ix1_y1_  5:ix1_  6:iy1_
-      const int ks = a.ks, r = (ks - 1) >> 1, wsz = ks + 2;
-      const int oy = py - r - 1, ox = px - r - 1;
-      for (int e = lane; e < wsz * wsz; e += 32) {
-        const int wy = (int)fdiv((uint32_t)e, a.divWin);
-        const int wx = e - wy * wsz;
-        const int yy = oy + wy, xx = ox + wx;
-        float v = 0.f;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = map_at<FLIP>(hm, fm, W, yy, xx, shift);
-        my_win[e] = v;
-      }
-      __syncwarp();
-      const int ntask = kDarkSamples * ks;
-      for (int t = lane; t < ntask; t += 32) {
-        const int smp = (int)fdiv((uint32_t)t, a.divKs), ky = t - smp * ks;
-        const int dxs = (smp == 1 || smp == 3) ? 1 : ((smp == 4 || smp == 5) ? -1 : 0);
-        const int dys = (smp == 2 || smp == 3) ? 1 : ((smp == 4 || smp == 6) ? -1 : 0);
-        const float* vrow = my_win + (1 + dys + ky) * wsz + (1 + dxs);
-        const float* wrow = s_kernel + ky * ks;
-        my_rows[smp * PC_MAX_DARK_KERNEL + ky] =
-            ks == 11 ? blur_row<11>(wrow, vrow, ks) : blur_row<0>(wrow, vrow, ks);
-      }
-      __syncwarp();
-      float lg = 0.f;
-      if (lane < kDarkSamples) {
-        const int smp = lane;
-        const int dxs = (smp == 1 || smp == 3) ? 1 : ((smp == 4 || smp == 5) ? -1 : 0);
-        const int dys = (smp == 2 || smp == 3) ? 1 : ((smp == 4 || smp == 6) ? -1 : 0);
-        const int sy = py + dys, sx = px + dxs;
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-          float tot = my_rows[smp * PC_MAX_DARK_KERNEL];
-          for (int ky = 1; ky < ks; ++ky)
-            tot = __fadd_rn(tot, my_rows[smp * PC_MAX_DARK_KERNEL + ky]);
-          tot = fminf(fmaxf(tot, 0.001f), 50.f);
-          lg = (float)log((double)tot);  // correctly rounded float32 log
-        }  // else: the reference zero-pads the LOG map -> 0.0
-      }
-      const float i_ = __shfl_sync(0xffffffffu, lg, 0);
-      const float ix1 = __shfl_sync(0xffffffffu, lg, 1);
-      const float iy1 = __shfl_sync(0xffffffffu, lg, 2);
-      const float ix1y1 = __shfl_sync(0xffffffffu, lg, 3);
-      const float ix1_y1_ = __shfl_sync(0xffffffffu, lg, 4);
-      const float ix1_ = __shfl_sync(0xffffffffu, lg, 5);
-      const float iy1_ = __shfl_sync(0xffffffffu, lg, 6);
-      if (lane == 0) {
-        const float dx = __fmul_rn(0.5f, __fsub_rn(ix1, ix1_));
-        const float dy = __fmul_rn(0.5f, __fsub_rn(iy1, iy1_));
-        const float two_i = __fmul_rn(2.f, i_);
-        const float dxx = __fadd_rn(__fsub_rn(ix1, two_i), ix1_);
-        const float dyy = __fadd_rn(__fsub_rn(iy1, two_i), iy1_);
-        float t = __fsub_rn(ix1y1, ix1);
-        t = __fsub_rn(t, iy1);
-        t = __fadd_rn(t, i_);
-        t = __fadd_rn(t, i_);
-        t = __fsub_rn(t, ix1_);
-        t = __fsub_rn(t, iy1_);
-        t = __fadd_rn(t, ix1_y1_);
-        const float dxy = __fmul_rn(0.5f, t);
-        const float ha = __fadd_rn(dxx, 1e-7f), hd = __fadd_rn(dyy, 1e-7f), hb = dxy;
-        const float det = __fsub_rn(__fmul_rn(ha, hd), __fmul_rn(hb, hb));
-        const float i00 = __fdiv_rn(hd, det);
-        const float i01 = __fdiv_rn(-hb, det);
-        const float i11 = __fdiv_rn(ha, det);
-        const float ox_ = __fadd_rn(__fmul_rn(i00, dx), __fmul_rn(i01, dy));
-        const float oy_ = __fadd_rn(__fmul_rn(i01, dx), __fmul_rn(i11, dy));
-        rx = __fsub_rn(rx, ox_);
-        ry = __fsub_rn(ry, oy_);
-      }
+      float2 off;
+      if (a.ks == 11)
+        off = dark_offset<FLIP, 11>(hm, fm, W, H, px, py, shift, a, s_kernel, my_rows, my_win,
+                                    lane);
+      else
+        off = dark_offset<FLIP, 0>(hm, fm, W, H, px, py, shift, a, s_kernel, my_rows, my_win,
+                                   lane);
+      rx = __fsub_rn(rx, off.x);
+      ry = __fsub_rn(ry, off.y);
     }
 
-    // stage no longer needed: let the next round's consumer in, hand it back to the producer
+    // the whole group has scanned the stage and the refinement is done: let the next
+    // round's group in, hand the stage back to the producer
     __syncwarp();
     if (lane == 0) {
       s_done[s] = round + 1;
@@ -526,18 +635,39 @@ extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
   a.divWin = make_fastdiv((uint32_t)(p->dark_udp_refine ? p->kernel_size + 2 : 1));
   a.stage_floats = (uint32_t)(p->flip_test ? 2 * hw : hw);
 
-  const size_t tail_bytes = 2 * kMaxStages * sizeof(uint64_t) + kMaxStages * sizeof(uint32_t) +
-                            sizeof(float) * PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL +
-                            sizeof(float) * kConsumerWarps * kDarkSamples * PC_MAX_DARK_KERNEL +
-                            sizeof(float) * kConsumerWarps * kDarkWinMax;
+  // ---- stages and consumer groups ------------------------------------------------
+  // G warps share an item.  A stage is busy from the moment its copy is issued until
+  // the item's finisher releases it; with items arriving every T_arr = bytes / (HBM
+  // share of one SM) cycles, the stages busy being CONSUMED are (Little's law)
+  //     busy(G) = (T_scan / G + T_refine) / T_arr,
+  // where one warp scans at about 1/4.2 of the arrival rate (T_scan = 4.2 T_arr, measured)
+  // and the DARK step costs about 2000 cycles.  Pick the smallest G that leaves two
+  // stages to be in flight; the DARK scratch is per group (one finisher per group at a
+  // time), so fewer, larger groups also free shared memory for stages.
+  a.row_floats = a.mode == 2 ? kDarkSamples * PC_MAX_DARK_KERNEL : 0;
+  a.win_floats = a.mode == 2 ? (p->kernel_size + 2) * (p->kernel_size + 2) : 0;
   const size_t smem_cap = 227 * 1024;
   const size_t stage_bytes = (size_t)a.stage_floats * sizeof(float);
-  int stages = (int)((smem_cap - tail_bytes) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
+  const double t_arr = (double)stage_bytes / 23.0;  // cycles per item at 6.5 TB/s / 148 SMs
+  const double refine = (a.mode == 2 ? 2000.0 : 250.0) / t_arr;
+  int stages = 0, group = 1;
+  size_t tail_bytes = 0;
+  for (group = 1;; group <<= 1) {
+    const int ng = kConsumerWarps / group;
+    tail_bytes = 3 * kMaxStages * sizeof(uint64_t) + kMaxStages * sizeof(uint32_t) +
+                 2 * kMaxStages * kConsumerWarps * sizeof(float) +
+                 sizeof(float) * PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL +
+                 sizeof(float) * ng * (a.row_floats + a.win_floats);
+    stages = (int)((smem_cap - tail_bytes) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    const double busy = 4.2 / group + refine;
+    if (busy <= stages - 2 || group == kConsumerWarps) break;
+  }
   PC_REQUIRE(stages >= 2, PC_ERR_UNSUPPORTED,
              "pc_topdown_decode: a %dx%d plane%s does not fit two shared-memory stages",
              p->height, p->width, p->flip_test ? " pair" : "");
   a.stages = stages;
+  a.group = group;
   const size_t smem = stages * stage_bytes + tail_bytes;
 
   const int sms = sm_count_cached();
