@@ -325,12 +325,12 @@ constexpr int kWarp3TileRows = 16;
 struct Six {
   uint32_t lo, hi;  // bytes 0..3, bytes 4..7 of the run (6 are used)
 };
-__device__ __forceinline__ Six load_six(const uint8_t* p) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t sh = ((uint32_t)a & 3u) << 3;
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
-  const uint32_t w2 = sh == 24u ? __ldg(w + 2) : 0u;
+// 6-byte run at byte offset `off` from the 4-byte aligned base: three aligned words,
+// realigned with a funnel shift.
+__device__ __forceinline__ Six load_six(const uint8_t* __restrict__ base4, uint32_t off) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(base4 + (off & ~3u));
+  const uint32_t sh = (off & 3u) << 3;
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
   Six r;
   r.lo = __funnelshift_r(w0, w1, sh);
   r.hi = __funnelshift_r(w1, w2, sh);
@@ -339,17 +339,31 @@ __device__ __forceinline__ Six load_six(const uint8_t* p) {
 
 // Source row pair of one output pixel: shared by the four pixels of a thread when the
 // matrix has no rotation (then Y does not depend on x).
+//
+// cv::remap limits sources to SHRT_MAX rows / columns, so saturate_cast<short> of the
+// integer coordinates can only turn an out-of-image tap into another out-of-image tap;
+// it is not reproduced.
+//
+// Fast path range: the aligned words of a run reach up to 3 bytes before and 6 bytes
+// after it, so the run must not start at the first pixel of the image nor end in its
+// last 3 pixels; [sx_lo, sx_lo + sx_span] is the range of sx that is both interior
+// (all four taps inside) and safe for this row pair.
 struct RowCtx {
   int sy, fy;
-  uint32_t off;  // byte offset of row sy inside the image (valid rows only)
-  bool y_interior;
+  uint32_t off;     // byte offset of row sy from the aligned base (valid rows only)
+  int sx_lo;
+  uint32_t sx_span;
 };
-__device__ __forceinline__ RowCtx make_row(int Y, int hs, uint32_t ws3) {
+__device__ __forceinline__ RowCtx make_row(int Y, int hs, int ws, uint32_t ws3, uint32_t delta) {
   RowCtx r;
-  r.sy = max(-32768, min(32767, Y >> 5));  // saturate_cast<short>
+  r.sy = Y >> 5;
   r.fy = Y & 31;
-  r.y_interior = (unsigned)r.sy < (unsigned)(hs - 1);
-  r.off = (uint32_t)r.sy * ws3;
+  r.off = (uint32_t)r.sy * ws3 + delta;
+  const int lo = r.sy >= 1 ? 0 : 1;
+  const int hi = r.sy + 2 < hs ? ws - 2 : ws - 4;
+  const bool ok = (unsigned)r.sy < (unsigned)(hs - 1) && hi >= lo;
+  r.sx_lo = ok ? lo : 0x40000000;
+  r.sx_span = ok ? (uint32_t)(hi - lo) : 0u;
   return r;
 }
 
@@ -358,17 +372,15 @@ __device__ __forceinline__ RowCtx make_row(int Y, int hs, uint32_t ws3) {
 // arithmetic), a horizontal blend with weights (32-fx, fx) followed by a vertical blend
 // with (32-fy, fy); the horizontal blends are byte dot products (dp4a) taken straight
 // from the realigned words, with zero weights on the bytes of the other channels.
-__device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img, int hs, int ws,
-                                                uint32_t ws3, int X, const RowCtx rc) {
-  const int sx = max(-32768, min(32767, X >> 5));
+__device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
+                                                const uint8_t* __restrict__ base4, int hs,
+                                                int ws, uint32_t ws3, int X, const RowCtx rc) {
+  const int sx = X >> 5;
   const int fx = X & 31, fy = rc.fy, sy = rc.sy;
-  const bool interior = (unsigned)sx < (unsigned)(ws - 1) && rc.y_interior;
-  // aligned words may reach 3 bytes before / 2 bytes after the 6-byte run: keep them
-  // inside the image (excludes only its first and last pixel pair)
-  if (interior && (sx | sy) != 0 && (sx + 2 < ws || sy + 2 < hs)) {
-    const uint8_t* r0 = img + (rc.off + (uint32_t)sx * 3u);
-    const Six a = load_six(r0);
-    const Six b = load_six(r0 + ws3);
+  if ((uint32_t)(sx - rc.sx_lo) <= rc.sx_span) {
+    const uint32_t off = rc.off + (uint32_t)sx * 3u;
+    const Six a = load_six(base4, off);
+    const Six b = load_six(base4, off + ws3);
     const uint32_t gx = 32u - (uint32_t)fx, ux = (uint32_t)fx;
     const uint32_t k0 = gx | (ux << 24);  // channel 0: bytes 0 and 3 of lo
     const uint32_t k1l = gx << 8;         // channel 1: byte 1 of lo, byte 0 of hi
@@ -439,6 +451,8 @@ __global__ void __launch_bounds__(kWarpThreads)
 
   const int hs = src_hw[2 * crop], ws = src_hw[2 * crop + 1];
   const uint8_t* img = src + src_off[crop];
+  const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(img) & 3u);
+  const uint8_t* base4 = img - delta;  // 4-byte aligned
   const uint32_t ws3 = (uint32_t)ws * 3u;
   const int wq = dst_w >> 2;
   const int nquads = rows * wq;
@@ -457,17 +471,20 @@ __global__ void __launch_bounds__(kWarpThreads)
       const int4 bd = *reinterpret_cast<const int4*>(&s_bdelta[x]);
       const int Ya = (Y0 + bd.x) >> 5, Yb = (Y0 + bd.y) >> 5;
       const int Yc = (Y0 + bd.z) >> 5, Yd = (Y0 + bd.w) >> 5;
-      const RowCtx ra = make_row(Ya, hs, ws3);
+      const RowCtx ra = make_row(Ya, hs, ws, ws3, delta);
       if (Ya == Yb && Ya == Yc && Ya == Yd) {  // no rotation: one source row pair
-        p0 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
-        p1 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.y) >> 5, ra);
-        p2 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.z) >> 5, ra);
-        p3 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.w) >> 5, ra);
+        p0 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
+        p1 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5, ra);
+        p2 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5, ra);
+        p3 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5, ra);
       } else {
-        p0 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
-        p1 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.y) >> 5, make_row(Yb, hs, ws3));
-        p2 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.z) >> 5, make_row(Yc, hs, ws3));
-        p3 = warp_pixel3(img, hs, ws, ws3, (X0 + ad.w) >> 5, make_row(Yd, hs, ws3));
+        p0 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
+        p1 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5,
+                         make_row(Yb, hs, ws, ws3, delta));
+        p2 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5,
+                         make_row(Yc, hs, ws, ws3, delta));
+        p3 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5,
+                         make_row(Yd, hs, ws, ws3, delta));
       }
     }
     stage[3 * lane] = p0 | (p1 << 24);
