@@ -96,6 +96,25 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read + dram__bytes_write of the decode kernel, per launch, from the latest
+    committed `ncu --set full` summary under profiles/ (same workload as this bench)."""
+    import glob
+    import re
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_decode_ncu_summary.txt")))
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    with open(files[-1]) as f:
+        for line in f:
+            m = re.search(r"dram__bytes_(read|write)\.sum = ([0-9.]+) (\w+)", line)
+            if m:
+                total += float(m.group(2)) * unit.get(m.group(3), 1.0)
+    return (int(total) if total else None), os.path.basename(files[-1])
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -334,6 +353,7 @@ def run_ours(args, wl):
         peak, peak_src = measured_peak_gbs()
         alg_bytes = n * (2 * k * h * w * 4 + (k * 3 + 6) * 4)  # decode: 417,792 + 228 per crop
         achieved = alg_bytes / (dec_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic_bytes() if n == wl["crops"] else (None, None)
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
@@ -350,7 +370,8 @@ def run_ours(args, wl):
                        "kernels_ms": {"warp": warp_ms, "decode": dec_ms}},
             "roofline": {"bound": "hbm", "kernel": "topdown_decode_kernel<flip>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": cpu,
             "e2e": e2e,
