@@ -45,6 +45,7 @@ typedef enum pc_status {
 #define PC_MAX_JOINTS 64
 #define PC_MAX_DARK_KERNEL 17 /* kernel_size <= 17 (sigma = 3 recipe) */
 #define PC_MAX_GROUPS 128     /* people per image the grouping kernel can hold */
+#define PC_MAX_SCALES 4       /* heat-map resolutions of the bottom-up target encoder */
 
 /* ---- library ----------------------------------------------------------- */
 
@@ -147,6 +148,26 @@ int pc_topdown_decode(const float* d_heatmap, const float* d_flipped, const floa
                       const float* d_scale, const float* d_score, float* d_all_preds,
                       float* d_all_boxes, const pc_topdown_decode_params* params, int64_t n,
                       void* stream);
+
+/* ---- N1: BottomUpGenerateTarget._encoding (+ pad_to_same) ----------------
+ * mindpose/data/transform/bottomup_transform.py:504-598 and
+ * mindpose/data/transform/utils.py:213-232.
+ * d_keypoints f32 [N, S, M, K, 3]: for every scale s the M people's joints in
+ * heat-map pixels OF THAT SCALE (x, y, visibility); people are padded to M per
+ * batch with visibility 0.
+ * -> d_target f32 [N, S, K, Hmax, Wmax] (each scale zero-padded at the bottom /
+ *    right to the largest map), d_tag_ind i32 [N, S, max_num, K, 2] with
+ *    (mu_y * W_s + mu_x, 1) per visible joint, or [N, S, max_num, 2] when
+ *    tag_per_joint = 0.  num_people > max_num is an argument error (the reference
+ *    raises ValueError). */
+typedef struct pc_bottomup_encode_params {
+  int32_t num_joints, num_scales, num_people, max_num;
+  int32_t heatmap_w[PC_MAX_SCALES], heatmap_h[PC_MAX_SCALES]; /* heatmap_sizes = [[w, h], ...] */
+  float sigma;                                                /* 3*sigma integer <= 15 */
+  int32_t tag_per_joint;
+} pc_bottomup_encode_params;
+int pc_bottomup_encode(const float* d_keypoints, float* d_target, int32_t* d_tag_ind,
+                       const pc_bottomup_encode_params* params, int64_t n, void* stream);
 
 /* ---- A14-A17: BottomUpHeatMapAEDecoder.construct ------------------------
  * mindpose/models/decoders/bottom_up_decoder.py:67-203.

@@ -25,6 +25,7 @@ from ctypes import (
 PC_MAX_JOINTS = 64
 PC_MAX_DARK_KERNEL = 17
 PC_MAX_GROUPS = 128
+PC_MAX_SCALES = 4
 
 PC_OK = 0
 PC_ERR_INVALID_ARGUMENT = -1
@@ -120,6 +121,19 @@ class GroupParams(Structure):
     ]
 
 
+class BottomUpEncodeParams(Structure):
+    _fields_ = [
+        ("num_joints", c_int32),
+        ("num_scales", c_int32),
+        ("num_people", c_int32),
+        ("max_num", c_int32),
+        ("heatmap_w", c_int32 * PC_MAX_SCALES),
+        ("heatmap_h", c_int32 * PC_MAX_SCALES),
+        ("sigma", c_float),
+        ("tag_per_joint", c_int32),
+    ]
+
+
 class AffineHostParams(Structure):
     _fields_ = [
         ("src_h", c_int32),
@@ -149,6 +163,7 @@ SIGNATURES = {
         c_int,
         [_P, _P, _P, _P, _P, _P, _P, POINTER(TopDownDecodeParams), c_int64, _P],
     ),
+    "pc_bottomup_encode": (c_int, [_P, _P, _P, POINTER(BottomUpEncodeParams), c_int64, _P]),
     "pc_bottomup_decode": (
         c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, POINTER(BottomUpDecodeParams), c_int64, _P],

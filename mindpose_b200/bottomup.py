@@ -135,3 +135,39 @@ def transform_keypoints(ans: torch.Tensor, num_groups: torch.Tensor, center, sca
                   _lib.device_ptr(c), _lib.device_ptr(s), _lib.device_ptr(hw), float(pixel_std),
                   k, n, _lib.current_stream())
     return ans
+
+
+def encode_targets(keypoints: torch.Tensor, heatmap_sizes, sigma: float = 2.0, max_num: int = 30,
+                   tag_per_joint: bool = True):
+    """Batched ``BottomUpGenerateTarget._encoding`` (bottomup_transform.py:504-598).
+
+    keypoints f32 [N, S, M, K, 3]: per scale, the M people's joints in heat-map pixels of that
+    scale (pad people with visibility 0). heatmap_sizes = [[w, h], ...] (S entries).
+    -> (target f32 [N, S, K, Hmax, Wmax], tag_ind i32 [N, S, max_num, K, 2] or [N, S, max_num, 2])."""
+    if not (isinstance(keypoints, torch.Tensor) and keypoints.is_cuda):
+        raise ValueError("`keypoints` must be a CUDA tensor (no CPU fallback)")
+    if keypoints.dim() != 5 or keypoints.shape[-1] != 3:
+        raise ValueError("`keypoints` must have shape [N, S, M, K, 3]")
+    keypoints = keypoints.to(torch.float32).contiguous()
+    n, s, m, k, _ = keypoints.shape
+    sizes = np.asarray(heatmap_sizes).reshape(-1, 2)
+    if sizes.shape[0] != s:
+        raise ValueError("one heatmap size per scale is required")
+    if s > _lib.PC_MAX_SCALES:
+        raise ValueError(f"at most {_lib.PC_MAX_SCALES} scales are supported")
+    p = _lib.BottomUpEncodeParams()
+    p.num_joints, p.num_scales, p.num_people, p.max_num = k, s, m, int(max_num)
+    for i in range(s):
+        p.heatmap_w[i], p.heatmap_h[i] = int(sizes[i, 0]), int(sizes[i, 1])
+    p.sigma = float(sigma)
+    p.tag_per_joint = int(bool(tag_per_joint))
+    hmax, wmax = int(sizes[:, 1].max()), int(sizes[:, 0].max())
+    dev = keypoints.device
+    target = torch.empty((n, s, k, hmax, wmax), dtype=torch.float32, device=dev)
+    tag_shape = (n, s, int(max_num), k, 2) if tag_per_joint else (n, s, int(max_num), 2)
+    tag_ind = torch.empty(tag_shape, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("pc_bottomup_encode", _lib.device_ptr(keypoints) if m else 0,
+                  _lib.device_ptr(target), _lib.device_ptr(tag_ind), ctypes.byref(p), n,
+                  _lib.current_stream())
+    return target, tag_ind

@@ -20,6 +20,7 @@ SOURCES = [
     "topdown_encode.cu",
     "warp_affine.cu",
     "bottomup_decode.cu",
+    "bottomup_encode.cu",
     "grouping.cu",
 ]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "posecodec.h")]

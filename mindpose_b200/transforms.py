@@ -182,3 +182,61 @@ class TopDownGenerateTarget(TopDownTransform):
         return codec.topdown_encode(keypoints, cfg["image_size"], cfg["heatmap_size"],
                                     sigma=self.sigma, use_udp=self.use_udp, joint_weights=jw,
                                     out=out)
+
+
+class BottomUpTransform(Transform):
+    """Shared config parsing of the bottom-up transforms (bottomup_transform.py:24-85)."""
+
+    def setup_required_field(self) -> List[str]:
+        return COLUMN_MAP["bottomup"]["train" if self.is_train else "val"]
+
+    def load_transform_cfg(self) -> Dict[str, Any]:
+        cfg = dict()
+        cfg["image_size"] = np.array(self.config["image_size"])
+        cfg["max_image_size"] = np.array(self.config["max_image_size"])
+        cfg["heatmap_sizes"] = np.array(self.config["heatmap_sizes"])
+        assert len(cfg["image_size"]) == 2
+        for x in cfg["heatmap_sizes"]:
+            assert len(x) == 2
+        pairs = np.array(self.config["flip_pairs"])
+        if pairs.ndim == 2:
+            cfg["flip_index"] = np.insert(pairs[:, ::-1].flatten(), 0, 0)
+        else:
+            cfg["flip_index"] = pairs
+        cfg["flip_pairs"] = pairs
+        cfg["pixel_std"] = float(self.config["pixel_std"])
+        cfg["tag_per_joint"] = self.config["tag_per_joint"]
+        return cfg
+
+
+@register("transform", extra_name="bottomup_generate_target")
+class BottomUpGenerateTarget(BottomUpTransform):
+    """Keypoints -> multi-resolution Gaussian heatmaps + tag indices
+    (bottomup_transform.py:463-598).
+
+    Required keys: keypoints (one [M,K,3] array per scale).  Returned keys: target, tag_ind.
+    """
+
+    def __init__(self, is_train: bool = True, config: Optional[Dict[str, Any]] = None,
+                 sigma: float = 2.0, max_num: int = 30) -> None:
+        super().__init__(is_train=is_train, config=config)
+        self.sigma = sigma
+        self.max_num = max_num
+
+    def transform(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        kps = [np.asarray(k, dtype=np.float32) for k in state["keypoints"]]
+        m = kps[0].shape[0]
+        if m > self.max_num:
+            raise ValueError(
+                f"Number of keypoints in one image `{m}` exeeds the maximum num: `{self.max_num}`")
+        batch = torch.from_numpy(np.ascontiguousarray(np.stack(kps)[None])).to(_dev())
+        target, tag_ind = self.encode_batch(batch)
+        return dict(target=target[0].cpu().numpy(), tag_ind=tag_ind[0].cpu().numpy())
+
+    def encode_batch(self, keypoints: torch.Tensor):
+        """keypoints f32 [N,S,M,K,3] -> (target [N,S,K,Hmax,Wmax], tag_ind [N,S,max_num,K,2])."""
+        from . import bottomup
+
+        cfg = self._transform_cfg
+        return bottomup.encode_targets(keypoints, cfg["heatmap_sizes"], sigma=self.sigma,
+                                       max_num=self.max_num, tag_per_joint=cfg["tag_per_joint"])

@@ -46,7 +46,56 @@ def grouping_inputs(seed, n, k=17, m=30, mode="people"):
     return val, tag, ind
 
 
+BOTTOMUP_ENCODE_CASES = [
+    # (heatmap_sizes [[w, h], ...], people, tag_per_joint, seed)
+    ([[32, 32], [64, 64]], 0, True, 0),
+    ([[32, 32], [64, 64]], 1, True, 1),
+    ([[32, 32], [64, 64]], 8, True, 2),
+    ([[32, 32], [64, 64]], 30, True, 3),
+    ([[48, 40], [96, 80]], 12, True, 4),
+    ([[32, 32], [64, 64]], 8, False, 5),
+    ([[64, 64]], 5, True, 6),
+]
+
+
+def bottomup_people(seed, m, k, sizes):
+    """One keypoint array per scale (float32 [M,K,3], heat-map pixels of that scale): windows
+    that clip, fall outside, overlap (np.maximum merge) and exact .5 coordinates."""
+    rng = np.random.RandomState(seed)
+    w0, h0 = sizes[0]
+    kp = np.zeros((m, k, 3), np.float32)
+    kp[..., 0] = rng.uniform(-10, w0 + 10, (m, k))
+    kp[..., 1] = rng.uniform(-10, h0 + 10, (m, k))
+    kp[..., 2] = rng.choice([0, 1, 2], (m, k), p=[0.2, 0.3, 0.5])
+    if m > 0:
+        kp[0, :, 0] = np.floor(kp[0, :, 0]) + 0.5
+    if m > 2:
+        kp[2, :, :2] = kp[1, :, :2] + rng.uniform(-3, 3, (k, 2))
+    out = []
+    for (w, h) in sizes:
+        s = kp.copy()
+        s[..., 0] *= np.float32(w / w0)
+        s[..., 1] *= np.float32(h / h0)
+        out.append(s)
+    return out
+
+
+def bottomup_encode_golden(ns, golden_dir):
+    out = {}
+    for ci, (sizes, m, tpj, seed) in enumerate(BOTTOMUP_ENCODE_CASES):
+        cfg = dict(image_size=[512, 512], max_image_size=[832, 512], heatmap_sizes=sizes,
+                   flip_pairs=[[1, 2]], pixel_std=200.0, tag_per_joint=tpj)
+        t = ns.bottomup.BottomUpGenerateTarget(is_train=True, config=cfg, sigma=2.0, max_num=30)
+        kps = bottomup_people(seed, m, 17, sizes)
+        res = t.transform(dict(keypoints=[k.copy() for k in kps]))
+        out[f"target_{ci}"] = res["target"]
+        out[f"tag_ind_{ci}"] = res["tag_ind"]
+    np.savez_compressed(os.path.join(golden_dir, "bottomup_encode_ref.npz"), **out)
+
+
 def main(ns, golden_dir):
+    bottomup_encode_golden(ns, golden_dir)
+
     import scipy.optimize
 
     # ---- scipy LSAP on tie-heavy matrices

@@ -42,7 +42,7 @@ def timeit(fn, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--only", default="decode,encode,warp,bottomup,group")
+    ap.add_argument("--only", default="decode,encode,warp,bottomup,group,bu_encode")
     ap.add_argument("--json", default="")
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -146,6 +146,20 @@ def main():
             fn = lambda: bottomup.group_by_tag(val_k, tag_k, ind_k, synth.COCO_JOINT_ORDER)  # noqa: E731
             med, mn = timeit(fn, args.iters)
             report("group_by_tag 64 images (latency bound)", n, "images", 8160, med, mn)
+    if "bu_encode" in only:
+        n, m = 64, 30
+        sizes = [[128, 128], [256, 256]]
+        rng = np.random.RandomState(0)
+        kp = np.zeros((n, 2, m, 17, 3), np.float32)
+        kp[:, 0, :, :, 0] = rng.uniform(-5, 133, (n, m, 17))
+        kp[:, 0, :, :, 1] = rng.uniform(-5, 133, (n, m, 17))
+        kp[:, 0, :, :, 2] = (rng.random_sample((n, m, 17)) < 0.3) * (np.arange(m)[None, :, None] < 8)
+        kp[:, 1] = kp[:, 0] * np.array([2, 2, 1], np.float32)
+        kpt = torch.from_numpy(kp).to(dev)
+        fn = lambda: bottomup.encode_targets(kpt, sizes)  # noqa: E731
+        med, mn = timeit(fn, args.iters)
+        report("bottomup_encode 64 x 2 x 17 x 256^2 (8 people)", n, "images",
+               2 * 17 * 256 * 256 * 4 + 2 * 30 * 17 * 8, med, mn)
     if args.json:
         with open(args.json, "w") as f:
             json.dump(rows, f, indent=1)

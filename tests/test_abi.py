@@ -56,6 +56,7 @@ def test_struct_sizes_match_header(tmp_path):
         "pc_encode_params": _lib.EncodeParams,
         "pc_topdown_decode_params": _lib.TopDownDecodeParams,
         "pc_bottomup_decode_params": _lib.BottomUpDecodeParams,
+        "pc_bottomup_encode_params": _lib.BottomUpEncodeParams,
         "pc_group_params": _lib.GroupParams,
     }
     src = tmp_path / "sizes.c"
@@ -88,6 +89,13 @@ def test_argument_errors_raise_value_error_without_gpu(lib):
     e.sigma = 1.5  # 3 * sigma not an integer
     with pytest.raises(ValueError):
         _lib.call("pc_topdown_encode", 0, 0, 0, ctypes.byref(e), 1, 0)
+    b = _lib.BottomUpEncodeParams()
+    b.num_joints, b.num_scales, b.num_people, b.max_num = 17, 2, 31, 30
+    b.heatmap_w[0] = b.heatmap_h[0] = 128
+    b.heatmap_w[1] = b.heatmap_h[1] = 256
+    b.sigma, b.tag_per_joint = 2.0, 1
+    with pytest.raises(ValueError, match="exeeds the maximum num"):  # the reference's message
+        _lib.call("pc_bottomup_encode", 0, 0, 0, ctypes.byref(b), 1, 0)
 
 
 def test_missing_library_fails_loudly(monkeypatch):

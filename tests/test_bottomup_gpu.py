@@ -210,3 +210,52 @@ def test_bottomup_inferencer_end_to_end(cuda_device):
     for rec, w, p in zip(records, want, people):
         assert np.array_equal(rec["pred"], w)
         assert rec["score"] == [y[:, 2].mean() for y in p]
+
+
+# ------------------------------------------------------------------ N1: bottom-up encode
+def test_bottomup_encode_matches_reference_golden(cuda_device, golden):
+    from oracle import gen_golden_bottomup as ggb
+
+    g = golden("bottomup_encode_ref.npz")
+    for case, (sizes, m, tpj, seed) in enumerate(ggb.BOTTOMUP_ENCODE_CASES):
+        kps = ggb.bottomup_people(seed, m, 17, sizes)
+        cfg = dict(image_size=[512, 512], max_image_size=[832, 512], heatmap_sizes=sizes,
+                   flip_pairs=[[1, 2]], pixel_std=200.0, tag_per_joint=tpj)
+        t = mp.create_transform("bottomup_generate_target", is_train=True, config=cfg, sigma=2.0,
+                                max_num=30)
+        batch = _t(np.stack(kps)[None], cuda_device)
+        target, tag_ind = t.encode_batch(batch)
+        want_t, want_g = g[f"target_{case}"], g[f"tag_ind_{case}"]
+        assert target.shape[1:] == want_t.shape and tag_ind.shape[1:] == want_g.shape
+        assert np.abs(target[0].cpu().numpy() - want_t).max() <= 1e-5, case
+        assert np.array_equal(tag_ind[0].cpu().numpy(), want_g), case
+        # per-sample calling convention (the reference's transform(state))
+        out = t.transform(dict(keypoints=kps))
+        assert np.array_equal(out["tag_ind"], want_g)
+        assert np.abs(out["target"] - want_t).max() <= 1e-5
+
+
+def test_bottomup_encode_full_size_batch(cuda_device):
+    """BASELINE config 4 shapes (128^2 + 256^2, 17 joints), batch of 16 images with different
+    people counts padded to M = 30; every image against the oracle."""
+    from oracle import bottomup_encode as be
+    from oracle import gen_golden_bottomup as ggb
+
+    sizes = [[128, 128], [256, 256]]
+    n, m = 16, 30
+    batch = np.zeros((n, 2, m, 17, 3), np.float32)
+    people = []
+    for i in range(n):
+        cnt = [0, 1, 5, 12, 30][i % 5]
+        kps = ggb.bottomup_people(50 + i, cnt, 17, sizes)
+        people.append(kps)
+        for s in range(2):
+            batch[i, s, :cnt] = kps[s]
+    target, tag_ind = bottomup.encode_targets(_t(batch, cuda_device), sizes)
+    target, tag_ind = target.cpu().numpy(), tag_ind.cpu().numpy()
+    for i in range(n):
+        want_t, want_g = be.encode(people[i], sizes)
+        assert np.abs(target[i] - want_t).max() <= 1e-5, i
+        assert np.array_equal(tag_ind[i], want_g), i
+    with pytest.raises(ValueError, match="exeeds the maximum num"):
+        bottomup.encode_targets(torch.zeros(1, 2, 31, 17, 3, device=cuda_device), sizes)

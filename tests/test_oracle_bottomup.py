@@ -5,6 +5,8 @@ import pytest
 
 from mindpose_b200 import synth
 from oracle import bottomup_decode as bd
+from oracle import bottomup_encode as be
+from oracle import gen_golden_bottomup as ggb
 from oracle import grouping, lsap, ref_loader
 
 
@@ -132,3 +134,35 @@ def test_topk_ties_take_lowest_index_and_nms_keeps_plateaus():
     val, tag, ind, order = bd.top_k(kept, np.zeros((1, 1, 8, 8, 1), np.float32), 5)
     assert order[0, 0].tolist() == [54, 18, 19, 0, 1]
     assert val[0, 0].tolist() == [np.float32(0.9), 0.5, 0.5, 0.0, 0.0]
+
+
+# ------------------------------------------------------------------ N1: bottom-up encode
+@pytest.mark.parametrize("case", range(len(ggb.BOTTOMUP_ENCODE_CASES)))
+def test_bottomup_encode_matches_reference_golden(golden, case):
+    g = golden("bottomup_encode_ref.npz")
+    sizes, m, tpj, seed = ggb.BOTTOMUP_ENCODE_CASES[case]
+    kps = ggb.bottomup_people(seed, m, 17, sizes)
+    target, tag_ind = be.encode(kps, sizes, sigma=2.0, max_num=30, tag_per_joint=tpj)
+    assert target.dtype == np.float32 and tag_ind.dtype == np.int32
+    assert np.array_equal(target, g[f"target_{case}"])
+    assert np.array_equal(tag_ind, g[f"tag_ind_{case}"])
+
+
+def test_bottomup_encode_rejects_too_many_people():
+    kps = np.zeros((31, 17, 3), np.float32)
+    with pytest.raises(ValueError, match="exeeds the maximum num"):
+        be.generate_heatmap_and_tag_ind(kps, (64, 64), max_num=30)
+
+
+@pytest.mark.needs_reference
+def test_bottomup_encode_matches_live_reference():
+    ns = ref_loader.load()
+    sizes = [[40, 24], [80, 48]]
+    cfg = dict(image_size=[512, 512], max_image_size=[832, 512], heatmap_sizes=sizes,
+               flip_pairs=[[1, 2]], pixel_std=200.0, tag_per_joint=True)
+    t = ns.bottomup.BottomUpGenerateTarget(is_train=True, config=cfg, sigma=2.0, max_num=30)
+    for seed in range(5):
+        kps = ggb.bottomup_people(100 + seed, 9, 17, sizes)
+        want = t.transform(dict(keypoints=[k.copy() for k in kps]))
+        target, tag_ind = be.encode(kps, sizes)
+        assert np.array_equal(target, want["target"]) and np.array_equal(tag_ind, want["tag_ind"])

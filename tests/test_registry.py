@@ -11,6 +11,8 @@ from mindpose_b200 import synth
 
 def test_names_registered_like_the_reference():
     assert set(mp.list_modules()) >= {"decoder", "inferencer", "transform"}
+    for name in ("bottomup_generate_target", "BottomUpGenerateTarget"):
+        assert name in mp.list_components("transform")
     for name in ("topdown_box_to_center_scale", "topdown_affine", "topdown_generate_target",
                  "TopDownBoxToCenterScale", "TopDownAffine", "TopDownGenerateTarget"):
         assert name in mp.list_components("transform")
