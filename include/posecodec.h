@@ -98,6 +98,21 @@ int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offset,
                       const int32_t* d_src_hw, const double* d_inv, uint8_t* d_dst,
                       const pc_warp_params* params, int64_t n, void* stream);
 
+/* ---- N2: warp fused with vision.Normalize + HWC2CHW ----------------------
+ * The step after the warp in the reference's pipeline
+ * (mindpose/data/data_factory.py:127-138): Normalize(mean * 255, std * 255), then
+ * HWC -> CHW.  Same sources / matrices as pc_warp_affine_u8; the uint8 crop is not
+ * materialised: d_dst f32 [N, 3, dst_h, dst_w] = (crop - mean[c]) / std[c].
+ * mean / std are the values handed to vision.Normalize (already multiplied by 255).
+ * 3-channel images, dst_w % 4 == 0. */
+typedef struct pc_warp_norm_params {
+  int32_t dst_w, dst_h, channels;
+  float mean[4], std[4];
+} pc_warp_norm_params;
+int pc_warp_affine_u8_norm_chw(const uint8_t* d_src, const int64_t* d_src_offset,
+                               const int32_t* d_src_hw, const double* d_inv, float* d_dst,
+                               const pc_warp_norm_params* params, int64_t n, void* stream);
+
 /* Keypoint half of TopDownAffine (topdown_transform.py:224-231 / :255-259):
  * in place on d_keypoints f32 [N,K,3]; standard path moves joints with
  * visibility > 0 only, UDP moves all joints (matrix taken as float32). */

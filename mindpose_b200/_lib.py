@@ -59,6 +59,16 @@ class WarpParams(Structure):
     _fields_ = [("dst_w", c_int32), ("dst_h", c_int32), ("channels", c_int32)]
 
 
+class WarpNormParams(Structure):
+    _fields_ = [
+        ("dst_w", c_int32),
+        ("dst_h", c_int32),
+        ("channels", c_int32),
+        ("mean", c_float * 4),
+        ("std", c_float * 4),
+    ]
+
+
 class EncodeParams(Structure):
     _fields_ = [
         ("num_joints", c_int32),
@@ -157,6 +167,8 @@ SIGNATURES = {
     "pc_affine_matrices": (c_int, [_P, _P, _P, _P, _P, POINTER(AffineParams), c_int64, _P]),
     "pc_invert_affine": (c_int, [_P, _P, c_int64, _P]),
     "pc_warp_affine_u8": (c_int, [_P, _P, _P, _P, _P, POINTER(WarpParams), c_int64, _P]),
+    "pc_warp_affine_u8_norm_chw": (
+        c_int, [_P, _P, _P, _P, _P, POINTER(WarpNormParams), c_int64, _P]),
     "pc_affine_joints": (c_int, [_P, _P, c_int32, c_int32, c_int64, _P]),
     "pc_topdown_encode": (c_int, [_P, _P, _P, POINTER(EncodeParams), c_int64, _P]),
     "pc_topdown_decode": (

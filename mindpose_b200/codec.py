@@ -99,6 +99,36 @@ def warp_affine(src: torch.Tensor, src_offset: torch.Tensor, src_hw: torch.Tenso
     return out
 
 
+def warp_affine_normalized(src: torch.Tensor, src_offset: torch.Tensor, src_hw: torch.Tensor,
+                           inv: torch.Tensor, dst_size, mean: Sequence[float],
+                           std: Sequence[float], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Warp + ``vision.Normalize(mean, std)`` + ``HWC2CHW`` in one pass
+    (mindpose/data/data_factory.py:127-138): -> f32 [N, 3, h, w].  ``mean`` / ``std`` are the
+    values given to Normalize, i.e. already multiplied by 255."""
+    if not (src.is_cuda and src.dtype == torch.uint8 and src.is_contiguous()):
+        raise ValueError("`src` must be a contiguous uint8 CUDA tensor")
+    n = inv.shape[0]
+    src_offset = src_offset.to(torch.int64).contiguous()
+    src_hw = src_hw.to(torch.int32).contiguous()
+    inv = inv.to(torch.float64).contiguous()
+    w, h = _wh(dst_size)
+    mean = np.asarray(mean, dtype=np.float32).reshape(-1)
+    std = np.asarray(std, dtype=np.float32).reshape(-1)
+    if mean.shape[0] != 3 or std.shape[0] != 3:
+        raise ValueError("`mean` and `std` must have three entries")
+    if out is None:
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=src.device)
+    p = _lib.WarpNormParams()
+    p.dst_w, p.dst_h, p.channels = w, h, 3
+    for c in range(3):
+        p.mean[c], p.std[c] = float(mean[c]), float(std[c])
+    with torch.cuda.device(src.device):
+        _lib.call("pc_warp_affine_u8_norm_chw", _lib.device_ptr(src), _lib.device_ptr(src_offset),
+                  _lib.device_ptr(src_hw), _lib.device_ptr(inv), _lib.device_ptr(out),
+                  ctypes.byref(p), n, _lib.current_stream())
+    return out
+
+
 def warp_affine_uniform(images: torch.Tensor, inv: torch.Tensor, dst_size) -> torch.Tensor:
     """images u8 [N, Hs, Ws, C], one source image per crop."""
     n, hs, ws, c = images.shape

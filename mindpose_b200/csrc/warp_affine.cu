@@ -416,13 +416,24 @@ __device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
   return out;
 }
 
-// dst_w % 16 == 0, dst 16-byte aligned: every warp's 32 quads are 384 contiguous,
-// 16-byte aligned output bytes.
+struct NormArgs {
+  float mean[3], std[3];
+};
+
+// NORM = false: uint8 HWC crops; dst_w % 16 == 0 and dst 16-byte aligned, so every warp's
+//   32 quads are 384 contiguous, 16-byte aligned output bytes.
+// NORM = true: the step that follows the warp in the
+//   reference's pipeline -- vision.Normalize(mean * 255, std * 255) and HWC2CHW
+//   (mindpose/data/data_factory.py:127-138) -- fused into the store: float32 CHW planes,
+//   (pixel - mean[c]) / std[c] in float32, one 16-byte store per channel and thread
+//   (dst_w % 4 == 0).  The uint8 crop is never written.
+template <bool NORM>
 __global__ void __launch_bounds__(kWarpThreads)
     warp_affine_u8x3_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
                             const int32_t* __restrict__ src_hw, const double* __restrict__ inv,
-                            uint8_t* __restrict__ dst, int dst_w, int dst_h, int tiles_per_crop,
-                            FastDiv div_wq) {
+                            void* __restrict__ dst_any, int dst_w, int dst_h, int tiles_per_crop,
+                            FastDiv div_wq, const NormArgs norm) {
+  uint8_t* dst = static_cast<uint8_t*>(dst_any);
   __shared__ __align__(16) int s_adelta[kWarpMaxDstW];
   __shared__ __align__(16) int s_bdelta[kWarpMaxDstW];
   __shared__ int s_x0[kWarp3TileRows];
@@ -486,6 +497,25 @@ __global__ void __launch_bounds__(kWarpThreads)
         p3 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5,
                          make_row(Yd, hs, ws, ws3, delta));
       }
+    }
+    if (NORM) {
+      if (t < nquads) {
+        const int ry = (int)fdiv((uint32_t)t, div_wq);
+        const int x = (t - ry * wq) << 2;
+        float* fdst = static_cast<float*>(dst_any);
+        const uint32_t px[4] = {p0, p1, p2, p3};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            v[e] = __fdiv_rn(__fsub_rn((float)((px[e] >> (8 * c)) & 255u), norm.mean[c]),
+                             norm.std[c]);
+          st_stream_f4(fdst + (((size_t)crop * 3 + c) * dst_h + row0 + ry) * dst_w + x,
+                       make_float4(v[0], v[1], v[2], v[3]));
+        }
+      }
+      continue;
     }
     stage[3 * lane] = p0 | (p1 << 24);
     stage[3 * lane + 1] = (p1 >> 8) | (p2 << 16);
@@ -583,9 +613,9 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
     const int tiles3 = (p->dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
     const int64_t grid3 = n * tiles3;
     PC_REQUIRE(grid3 < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_warp_affine_u8: batch too large");
-    warp_affine_u8x3_kernel<<<(unsigned)grid3, kWarpThreads, 0, st>>>(
+    warp_affine_u8x3_kernel<false><<<(unsigned)grid3, kWarpThreads, 0, st>>>(
         d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3,
-        make_fastdiv((uint32_t)(p->dst_w >> 2)));
+        make_fastdiv((uint32_t)(p->dst_w >> 2)), NormArgs());
     PC_CUDA(cudaGetLastError());
     return PC_OK;
   }
@@ -604,6 +634,42 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
     default: PC_LAUNCH_WARP(4); break;
   }
 #undef PC_LAUNCH_WARP
+  PC_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+extern "C" int pc_warp_affine_u8_norm_chw(const uint8_t* d_src, const int64_t* d_src_offset,
+                                          const int32_t* d_src_hw, const double* d_inv,
+                                          float* d_dst, const pc_warp_norm_params* p, int64_t n,
+                                          void* stream) {
+  PC_REQUIRE(p != nullptr, PC_ERR_INVALID_ARGUMENT, "pc_warp_affine_u8_norm_chw: params is NULL");
+  PC_REQUIRE(n >= 0 && p->dst_w >= 1 && p->dst_h >= 1, PC_ERR_INVALID_ARGUMENT,
+             "pc_warp_affine_u8_norm_chw: bad n / destination size");
+  PC_REQUIRE(p->channels == 3, PC_ERR_UNSUPPORTED,
+             "pc_warp_affine_u8_norm_chw: channels %d (only 3-channel images)", p->channels);
+  PC_REQUIRE(p->dst_w % 4 == 0 && p->dst_w <= kWarpMaxDstW, PC_ERR_UNSUPPORTED,
+             "pc_warp_affine_u8_norm_chw: dst_w %d must be a multiple of 4 and <= %d", p->dst_w,
+             kWarpMaxDstW);
+  for (int c = 0; c < 3; ++c)
+    PC_REQUIRE(p->std[c] != 0.f, PC_ERR_INVALID_ARGUMENT,
+               "pc_warp_affine_u8_norm_chw: std[%d] is zero", c);
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(d_src && d_src_offset && d_src_hw && d_inv && d_dst, PC_ERR_INVALID_ARGUMENT,
+             "pc_warp_affine_u8_norm_chw: NULL tensor pointer");
+  PC_REQUIRE(((uintptr_t)d_dst & 15) == 0, PC_ERR_UNSUPPORTED,
+             "pc_warp_affine_u8_norm_chw: destination must be 16-byte aligned");
+  const int tiles3 = (p->dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
+  const int64_t grid3 = n * tiles3;
+  PC_REQUIRE(grid3 < 0x7fffffffLL, PC_ERR_UNSUPPORTED,
+             "pc_warp_affine_u8_norm_chw: batch too large");
+  NormArgs na;
+  for (int c = 0; c < 3; ++c) {
+    na.mean[c] = p->mean[c];
+    na.std[c] = p->std[c];
+  }
+  warp_affine_u8x3_kernel<true><<<(unsigned)grid3, kWarpThreads, 0, (cudaStream_t)stream>>>(
+      d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3,
+      make_fastdiv((uint32_t)(p->dst_w >> 2)), na);
   PC_CUDA(cudaGetLastError());
   return PC_OK;
 }

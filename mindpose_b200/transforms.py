@@ -139,12 +139,26 @@ class TopDownAffine(TopDownTransform):
             out["keypoints"] = state["keypoints"]
         return out
 
-    def affine_batch(self, images: torch.Tensor, center, scale, rot=None, keypoints=None):
-        """images u8 [N,Hs,Ws,C] (one per crop) -> (crops u8 [N,h,w,C], keypoints)."""
+    def affine_batch(self, images: torch.Tensor, center, scale, rot=None, keypoints=None,
+                     normalize_mean=None, normalize_std=None):
+        """images u8 [N,Hs,Ws,C] (one per crop) -> (crops u8 [N,h,w,C], keypoints).
+
+        With ``normalize_mean`` / ``normalize_std`` (the ``create_pipeline`` arguments, in
+        [0, 1] units: data_factory.py:78-79) the pipeline's Normalize + HWC2CHW step is fused
+        into the warp and the crops come back as float32 [N,3,h,w]."""
         cfg = self._transform_cfg
         fwd, inv = codec.affine_matrices(center, scale, rot, cfg["image_size"],
                                          pixel_std=cfg["pixel_std"], use_udp=self.use_udp)
-        crops = codec.warp_affine_uniform(images, inv, cfg["image_size"])
+        if normalize_mean is not None:
+            n, hs, ws, c = images.shape
+            off = torch.arange(n, device=images.device, dtype=torch.int64) * (hs * ws * c)
+            hw = torch.tensor([hs, ws], device=images.device, dtype=torch.int32).repeat(n, 1)
+            # np.array(mean) * 255.0 in float64, handed to Normalize as float32
+            mean = (np.array(normalize_mean) * 255.0).tolist()
+            std = (np.array(normalize_std) * 255.0).tolist()
+            crops = codec.warp_affine_normalized(images, off, hw, inv, cfg["image_size"], mean, std)
+        else:
+            crops = codec.warp_affine_uniform(images, inv, cfg["image_size"])
         if keypoints is not None:
             keypoints = codec.affine_joints(keypoints.contiguous(), fwd, use_udp=self.use_udp)
         return crops, keypoints

@@ -131,3 +131,16 @@ def warp_affine_u8(image, mat, dsize):
     out = (acc + (1 << (INTER_REMAP_COEF_BITS - 1))) >> INTER_REMAP_COEF_BITS
     out = np.clip(out, 0, 255).astype(np.uint8)
     return out[:, :, 0] if squeeze else out
+
+
+def normalize_chw(crop_u8, mean, std):
+    """``vision.Normalize(mean, std)`` followed by ``vision.HWC2CHW()``
+    (mindpose/data/data_factory.py:127-138; mean / std already multiplied by 255).
+
+    PARITY UNPINNED: MindSpore's dataset ops cannot run here.  The arithmetic of record is
+    ``(float32(pixel) - float32(mean[c])) / float32(std[c])`` in float32; MindSpore's
+    implementation may instead multiply by a precomputed reciprocal (<= 1 ulp apart)."""
+    mean = np.asarray(mean, np.float32)
+    std = np.asarray(std, np.float32)
+    out = (crop_u8.astype(np.float32) - mean[None, None, :]) / std[None, None, :]
+    return np.ascontiguousarray(out.transpose(2, 0, 1))

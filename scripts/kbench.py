@@ -125,6 +125,13 @@ def main():
         roi = float(np.mean((x1 - x0) * (y1 - y0) * 3))
         report("warp_affine_u8 480x640 -> 256x192 (dst+ROI)", n, "crops", 147456 + roi, med, mn)
         report("warp_affine_u8 (dst bytes only)", n, "crops", 147456, med, mn)
+        outf = torch.empty(n, 3, 256, 192, device=dev)
+        m255 = (np.array([0.485, 0.456, 0.406]) * 255.0).tolist()
+        s255 = (np.array([0.229, 0.224, 0.255]) * 255.0).tolist()
+        fn = lambda: codec.warp_affine_normalized(images, off, hw, inv, [192, 256], m255, s255, out=outf)  # noqa: E731
+        med, mn = timeit(fn, args.iters)
+        report("warp + normalize + CHW f32 (dst+ROI)", n, "crops", 589824 + roi, med, mn)
+        del outf
         del images, out
     if "bottomup" in only:
         n = 64

@@ -54,6 +54,7 @@ def test_struct_sizes_match_header(tmp_path):
         "pc_affine_params": _lib.AffineParams,
         "pc_warp_params": _lib.WarpParams,
         "pc_encode_params": _lib.EncodeParams,
+        "pc_warp_norm_params": _lib.WarpNormParams,
         "pc_topdown_decode_params": _lib.TopDownDecodeParams,
         "pc_bottomup_decode_params": _lib.BottomUpDecodeParams,
         "pc_bottomup_encode_params": _lib.BottomUpEncodeParams,

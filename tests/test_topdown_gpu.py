@@ -386,3 +386,30 @@ def test_warp_image_corners_and_unaligned_sources(cuda_device, channels):
     for i in range(n):
         want = warp.warp_affine_u8(imgs[i], mats[i], (dw, dh))
         assert np.array_equal(out[i], want.reshape(dh, dw, channels)), i
+
+
+def test_warp_fused_normalize_chw(cuda_device):
+    """N2: warp + Normalize(mean * 255, std * 255) + HWC2CHW in one kernel equals the uint8
+    warp followed by the oracle's normalisation, bit for bit (same float32 formula)."""
+    n = 12
+    images, boxes = synth.source_images_and_boxes(n, 240, 320, seed=3)
+    cfg = synth.TOPDOWN_CONFIG
+    dev = cuda_device
+    bt = mp.create_transform("topdown_box_to_center_scale", is_train=False, config=cfg)
+    at = mp.create_transform("topdown_affine", is_train=False, config=cfg)
+    c, s = bt.box_to_center_scale_batch(_t(boxes, dev))
+    rot = torch.zeros(n, device=dev)
+    rot[::4] = -25.0
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.255]  # the reference's defaults
+    crops_u8, _ = at.affine_batch(_t(images, dev), c, s, rot)
+    fused, _ = at.affine_batch(_t(images, dev), c, s, rot, normalize_mean=mean, normalize_std=std)
+    assert fused.shape == (n, 3, 256, 192) and fused.dtype == torch.float32
+    m255 = (np.array(mean) * 255.0).tolist()
+    s255 = (np.array(std) * 255.0).tolist()
+    for i in range(n):
+        want = warp.normalize_chw(crops_u8[i].cpu().numpy(), m255, s255)
+        assert np.array_equal(fused[i].cpu().numpy(), want), i
+    with pytest.raises(ValueError):
+        codec.warp_affine_normalized(_t(images, dev), torch.zeros(n, device=dev),
+                                     torch.zeros(n, 2, device=dev), torch.zeros(n, 2, 3, device=dev),
+                                     (190, 256), m255, s255)   # dst_w % 4 != 0
