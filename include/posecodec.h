@@ -231,6 +231,21 @@ int pc_transform_keypoints(float* d_ans, const int32_t* d_num_groups, const doub
                            const double* d_scale, const double* d_heatmap_wh, float pixel_std,
                            int32_t num_joints, int64_t n, void* stream);
 
+/* ---- N3: BottomUpHeatMapAEInferencer._refine_missing --------------------
+ * mindpose/engine/inferencer/bottomup_inferencer.py:189-249, for every person of
+ * every image.  Runs on the grouped people in heat-map coordinates, i.e. after
+ * pc_group_by_tag and before pc_transform_keypoints (bottomup_inferencer.py:158-166).
+ * d_heatmap f32 [N,K,H,W] and d_tagging f32 [N,K,H,W,1] are the heatmap_raw /
+ * tagging_heatmap outputs of pc_bottomup_decode; d_ans f32 [N, PC_MAX_GROUPS, K, 4]
+ * is updated in place (x, y, val of joints with val == 0); d_mean_tag f32
+ * [N, PC_MAX_GROUPS] is caller-provided scratch. */
+typedef struct pc_refine_params {
+  int32_t num_joints, height, width;
+} pc_refine_params;
+int pc_refine_missing(const float* d_heatmap, const float* d_tagging, float* d_ans,
+                      const int32_t* d_num_groups, float* d_mean_tag,
+                      const pc_refine_params* params, int64_t n, void* stream);
+
 /* ---- host-buffer front end (what the e2e number is measured through) ----
  * Same decode as pc_topdown_decode but every pointer is a HOST pointer.  The
  * context owns device scratch and two streams; crops are streamed through in

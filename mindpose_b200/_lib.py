@@ -144,6 +144,10 @@ class BottomUpEncodeParams(Structure):
     ]
 
 
+class RefineParams(Structure):
+    _fields_ = [("num_joints", c_int32), ("height", c_int32), ("width", c_int32)]
+
+
 class AffineHostParams(Structure):
     _fields_ = [
         ("src_h", c_int32),
@@ -185,6 +189,7 @@ SIGNATURES = {
         c_int,
         [_P, _P, _P, _P, _P, c_float, c_int32, c_int64, _P],
     ),
+    "pc_refine_missing": (c_int, [_P, _P, _P, _P, _P, POINTER(RefineParams), c_int64, _P]),
     "pc_ctx_create": (c_int, [c_int, c_int64, POINTER(c_void_p)]),
     "pc_ctx_destroy": (c_int, [c_void_p]),
     "pc_topdown_affine_host": (

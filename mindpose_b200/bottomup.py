@@ -171,3 +171,26 @@ def encode_targets(keypoints: torch.Tensor, heatmap_sizes, sigma: float = 2.0, m
                   _lib.device_ptr(target), _lib.device_ptr(tag_ind), ctypes.byref(p), n,
                   _lib.current_stream())
     return target, tag_ind
+
+
+def refine_missing(heatmap: torch.Tensor, tagging_heatmap: torch.Tensor, ans: torch.Tensor,
+                   num_groups: torch.Tensor) -> torch.Tensor:
+    """Batched ``_refine_missing`` (bottomup_inferencer.py:189-249), in place on ``ans``
+    [N, PC_MAX_GROUPS, K, 4] (heat-map coordinates).  heatmap [N,K,H,W] / tagging_heatmap
+    [N,K,H,W,1] are the decoder's ``heatmap_raw`` / ``tagging_heatmap`` outputs."""
+    for t in (heatmap, tagging_heatmap, ans):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("heatmap / tagging_heatmap / ans must be contiguous float32 CUDA tensors")
+    n, k, h, w = heatmap.shape
+    if tagging_heatmap.shape != (n, k, h, w, 1):
+        raise ValueError("the CUDA refinement supports one tag channel (tagging_heatmap [N,K,H,W,1])")
+    if ans.shape != (n, _lib.PC_MAX_GROUPS, k, 4):
+        raise ValueError("`ans` must be the [N, PC_MAX_GROUPS, K, 4] output of group_by_tag")
+    num_groups = num_groups.to(torch.int32).contiguous()
+    scratch = torch.empty((n, _lib.PC_MAX_GROUPS), dtype=torch.float32, device=ans.device)
+    p = _lib.RefineParams(k, h, w)
+    with torch.cuda.device(ans.device):
+        _lib.call("pc_refine_missing", _lib.device_ptr(heatmap), _lib.device_ptr(tagging_heatmap),
+                  _lib.device_ptr(ans), _lib.device_ptr(num_groups), _lib.device_ptr(scratch),
+                  ctypes.byref(p), n, _lib.current_stream())
+    return ans

@@ -22,6 +22,7 @@ SOURCES = [
     "bottomup_decode.cu",
     "bottomup_encode.cu",
     "grouping.cu",
+    "refine_missing.cu",
 ]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "posecodec.h")]
 

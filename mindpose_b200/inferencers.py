@@ -143,8 +143,6 @@ class BottomUpHeatMapAEInferencer(Inferencer):
             raise ValueError("bottom-up flip TTA is not supported")
         if self.decoder is None:
             raise ValueError("Decoder must be provided")
-        if self._inference_cfg["refine_missing_joint"]:
-            raise ValueError("refine_missing_joint is not supported by the CUDA codec yet")
 
     def load_inference_cfg(self) -> Dict[str, Any]:
         c = self.config
@@ -168,11 +166,16 @@ class BottomUpHeatMapAEInferencer(Inferencer):
         outputs = list()
         cfg = self._inference_cfg
         for data in dataset:
-            val_k, tag_k, ind_k, _, _ = self.decoder(self.net(data["image"]), data["mask"])
+            val_k, tag_k, ind_k, raw, tagging = self.decoder(self.net(data["image"]), data["mask"])
             ans, num, scores = bottomup.group_by_tag(
                 val_k, tag_k, ind_k, joint_order=cfg["joint_order"], vis_thr=cfg["vis_thr"],
                 tag_thr=cfg["tag_thr"], ignore_too_much=cfg["ignore_too_much"],
                 use_rounded_norm=cfg["use_rounded_norm"])
+            if cfg["refine_missing_joint"]:  # after the scores, as the reference (:153-166)
+                if raw is None or tagging is None:
+                    raise ValueError("refine_missing_joint needs the decoder's heatmap outputs "
+                                     "(decoder.return_maps = True)")
+                bottomup.refine_missing(raw, tagging, ans, num)
             image_shape = torch.as_tensor(np.asarray(data["image_shape"]), dtype=torch.float64)
             bottomup.transform_keypoints(
                 ans, num, data["center"], data["scale"],

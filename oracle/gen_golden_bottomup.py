@@ -93,8 +93,45 @@ def bottomup_encode_golden(ns, golden_dir):
     np.savez_compressed(os.path.join(golden_dir, "bottomup_encode_ref.npz"), **out)
 
 
+def refine_inputs(seed, k=17, h=32, w=32, people=5):
+    """heat / tag maps with `people` tagged blobs per joint and grouped keypoints [P,K,4] with
+    some joints missing (val = 0), one plane without positive values, peaks on the border."""
+    rng = np.random.RandomState(seed)
+    heat = (rng.random_sample((k, h, w)) * 0.05).astype(np.float32)
+    tagm = rng.uniform(-1, 1, (k, h, w, 1)).astype(np.float32)
+    kps = np.zeros((people, k, 4), np.float32)
+    bump = np.array([[.5, .8, .5], [.8, 1, .8], [.5, .8, .5]], np.float32)
+    for p in range(people):
+        ptag = 3.0 * p + rng.uniform(0, 0.5)
+        for j in range(k):
+            y, x = rng.randint(0, h), rng.randint(0, w)
+            y0, y1, x0, x1 = max(y - 1, 0), min(y + 2, h), max(x - 1, 0), min(x + 2, w)
+            heat[j, y0:y1, x0:x1] += rng.uniform(0.3, 0.9) * bump[y0 - y + 1:y1 - y + 1, x0 - x + 1:x1 - x + 1]
+            tagm[j, max(y - 2, 0):y + 3, max(x - 2, 0):x + 3, 0] = ptag + rng.normal(0, 0.1)
+            if rng.random_sample() < 0.6:
+                kps[p, j] = (x, y, heat[j, y, x], tagm[j, y, x, 0])
+        if not (kps[p, :, 2] > 0).any():
+            kps[p, 0] = (3, 3, 0.5, ptag)
+    heat[3] = -np.abs(heat[3])          # no positive value: nothing is filled in for joint 3
+    heat[5] = np.round(heat[5] * 4) / 4  # plateaus: ties for the argmax and the +-0.25 shift
+    return heat, tagm, kps
+
+
+def refine_missing_golden(golden_dir):
+    from oracle import refine_missing as rm
+
+    f = rm.reference_function()
+    out = {}
+    for seed in range(4):
+        heat, tagm, kps = refine_inputs(seed, people=[1, 3, 6, 11][seed])
+        out[f"heat_{seed}"], out[f"tag_{seed}"], out[f"kps_{seed}"] = heat, tagm, kps
+        out[f"refined_{seed}"] = np.stack([f(None, heat, tagm, kp.copy()) for kp in kps])
+    np.savez_compressed(os.path.join(golden_dir, "refine_missing_ref.npz"), **out)
+
+
 def main(ns, golden_dir):
     bottomup_encode_golden(ns, golden_dir)
+    refine_missing_golden(golden_dir)
 
     import scipy.optimize
 

@@ -42,7 +42,7 @@ def timeit(fn, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--only", default="decode,encode,warp,bottomup,group,bu_encode")
+    ap.add_argument("--only", default="decode,encode,warp,bottomup,group,bu_encode,refine")
     ap.add_argument("--json", default="")
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -153,6 +153,20 @@ def main():
             fn = lambda: bottomup.group_by_tag(val_k, tag_k, ind_k, synth.COCO_JOINT_ORDER)  # noqa: E731
             med, mn = timeit(fn, args.iters)
             report("group_by_tag 64 images (latency bound)", n, "images", 8160, med, mn)
+    if "refine" in only:
+        n, k, h, w, people = 64, 17, 256, 256, 8
+        g = torch.Generator(device=dev).manual_seed(1)
+        heat = torch.rand(n, k, h, w, device=dev, generator=g)
+        tagm = torch.rand(n, k, h, w, 1, device=dev, generator=g) * 10
+        ans = torch.zeros(n, bottomup._lib.PC_MAX_GROUPS, k, 4, device=dev)
+        ans[:, :people, :, 0] = torch.randint(0, w, (n, people, k), device=dev, generator=g).float()
+        ans[:, :people, :, 1] = torch.randint(0, h, (n, people, k), device=dev, generator=g).float()
+        ans[:, :people, :, 2] = (torch.rand(n, people, k, device=dev, generator=g) > 0.4).float() * 0.5
+        num = torch.full((n,), people, dtype=torch.int32, device=dev)
+        fn = lambda: bottomup.refine_missing(heat, tagm, ans.clone(), num)  # noqa: E731
+        med, mn = timeit(fn, args.iters)
+        report("refine_missing 64 images x 8 people (maps read once)", n, "images",
+               2 * k * h * w * 4, med, mn)
     if "bu_encode" in only:
         n, m = 64, 30
         sizes = [[128, 128], [256, 256]]

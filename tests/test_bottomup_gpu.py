@@ -183,14 +183,18 @@ def test_transform_keypoints_matches_oracle(cuda_device):
         assert np.array_equal(ans[i, :int(num[i])].cpu().numpy(), want[i])
 
 
-def test_bottomup_inferencer_end_to_end(cuda_device):
-    """decode -> group -> score -> back-project through the registry classes."""
+@pytest.mark.parametrize("refine", [False, True])
+def test_bottomup_inferencer_end_to_end(cuda_device, refine):
+    """decode -> group -> score -> [refine missing joints] -> back-project through the
+    registry classes."""
+    from oracle import refine_missing as rm
+
     d = synth.bottomup_outputs(2, 17, 32, 32, mask_hw=(128, 128), seed=11, max_people=4)
     dev = cuda_device
     out = [_t(d["out0"], dev), _t(d["out1"], dev)]
     cfg = dict(has_heatmap_output=True, hflip_tta=False, joint_order=synth.COCO_JOINT_ORDER,
                vis_thr=0.1, ignore_too_much=False, use_rounded_norm=True, tag_thr=1.0,
-               pixel_std=200.0, downsample_scale=2, refine_missing_joint=False,
+               pixel_std=200.0, downsample_scale=2, refine_missing_joint=refine,
                flip_pairs=synth.COCO_FLIP_PAIRS)
     dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3)
     inf = mp.create_inferencer(lambda image: out, "bottomup_heatmap_ae", config=cfg, decoder=dec)
@@ -200,16 +204,20 @@ def test_bottomup_inferencer_end_to_end(cuda_device):
     data = dict(image=None, mask=_t(d["mask"], dev), center=center, scale=scale,
                 image_shape=shape, image_file=["a.jpg", "b.jpg"])
     records = inf([data])
-    val_k, tag_k, ind_k, _, _ = bd.decode([d["out0"], d["out1"]], d["mask"], use_nms=True,
-                                          nms_kernel=3, max_num=30)
+    val_k, tag_k, ind_k, raw, tagging = bd.decode([d["out0"], d["out1"]], d["mask"], use_nms=True,
+                                                  nms_kernel=3, max_num=30)
     people = [grouping.match_by_tag(val_k[i], tag_k[i], ind_k[i], synth.COCO_JOINT_ORDER)
               for i in range(2)]
     people = [p if p.ndim == 3 else np.zeros((0, 17, 4), np.float32) for p in people]
+    scores = [[y[:, 2].mean() for y in p] for p in people]  # before the refinement (:153-156)
+    if refine:
+        people = [np.stack([rm.refine_missing(raw[i], tagging[i], kp) for kp in p])
+                  if len(p) else p for i, p in enumerate(people)]
     want = grouping.transform_keypoints(people, center, scale, shape / 2, pixel_std=200.0)
     assert len(records) == 2
-    for rec, w, p in zip(records, want, people):
+    for rec, w, sc in zip(records, want, scores):
         assert np.array_equal(rec["pred"], w)
-        assert rec["score"] == [y[:, 2].mean() for y in p]
+        assert rec["score"] == sc
 
 
 # ------------------------------------------------------------------ N1: bottom-up encode
@@ -259,3 +267,40 @@ def test_bottomup_encode_full_size_batch(cuda_device):
         assert np.array_equal(tag_ind[i], want_g), i
     with pytest.raises(ValueError, match="exeeds the maximum num"):
         bottomup.encode_targets(torch.zeros(1, 2, 31, 17, 3, device=cuda_device), sizes)
+
+
+# ------------------------------------------------------------------ N3: refine_missing
+def _refine_batch(dev, cases):
+    """cases: list of (heat [K,H,W], tag [K,H,W,1], kps [P,K,4]) of one map size."""
+    n = len(cases)
+    k, h, w = cases[0][0].shape
+    g = bottomup._lib.PC_MAX_GROUPS
+    heat = np.stack([c[0] for c in cases])
+    tagm = np.stack([c[1] for c in cases])
+    ans = np.zeros((n, g, k, 4), np.float32)
+    num = np.zeros(n, np.int32)
+    for i, c in enumerate(cases):
+        num[i] = c[2].shape[0]
+        ans[i, :num[i]] = c[2]
+    out = bottomup.refine_missing(_t(heat, dev), _t(tagm, dev), _t(ans, dev), _t(num, dev))
+    return out.cpu().numpy(), num
+
+
+def test_refine_missing_matches_reference_golden(cuda_device, golden):
+    g = golden("refine_missing_ref.npz")
+    cases = [(g[f"heat_{s}"], g[f"tag_{s}"], g[f"kps_{s}"]) for s in range(4)]
+    got, num = _refine_batch(cuda_device, cases)
+    for s in range(4):
+        assert np.array_equal(got[s, :num[s]], g[f"refined_{s}"]), s
+
+
+def test_refine_missing_full_size_and_inferencer(cuda_device):
+    """256 x 256 maps, 20 people (three chunks of 8), and the inferencer flag end to end."""
+    from oracle import gen_golden_bottomup as ggb
+    from oracle import refine_missing as rm
+
+    cases = [ggb.refine_inputs(40 + i, h=256, w=256, people=p) for i, p in enumerate((20, 0, 9))]
+    got, num = _refine_batch(cuda_device, cases)
+    for i, (heat, tagm, kps) in enumerate(cases):
+        for p in range(num[i]):
+            assert np.array_equal(got[i, p], rm.refine_missing(heat, tagm, kps[p])), (i, p)

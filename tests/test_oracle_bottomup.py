@@ -8,6 +8,7 @@ from oracle import bottomup_decode as bd
 from oracle import bottomup_encode as be
 from oracle import gen_golden_bottomup as ggb
 from oracle import grouping, lsap, ref_loader
+from oracle import refine_missing as rm
 
 
 def _split_counts(flat, counts, k=17, width=4):
@@ -166,3 +167,22 @@ def test_bottomup_encode_matches_live_reference():
         want = t.transform(dict(keypoints=[k.copy() for k in kps]))
         target, tag_ind = be.encode(kps, sizes)
         assert np.array_equal(target, want["target"]) and np.array_equal(tag_ind, want["tag_ind"])
+
+
+# ------------------------------------------------------------------ N3: refine_missing
+@pytest.mark.parametrize("seed", range(4))
+def test_refine_missing_matches_reference_golden(golden, seed):
+    g = golden("refine_missing_ref.npz")
+    heat, tagm, kps = g[f"heat_{seed}"], g[f"tag_{seed}"], g[f"kps_{seed}"]
+    got = np.stack([rm.refine_missing(heat, tagm, kp) for kp in kps])
+    assert np.array_equal(got, g[f"refined_{seed}"])
+    assert not np.array_equal(got, kps)  # something was filled in
+
+
+@pytest.mark.needs_reference
+def test_refine_missing_matches_live_reference_body():
+    f = rm.reference_function()
+    for seed in range(10, 14):
+        heat, tagm, kps = ggb.refine_inputs(seed, h=24, w=40, people=4)
+        for kp in kps:
+            assert np.array_equal(rm.refine_missing(heat, tagm, kp), f(None, heat, tagm, kp.copy()))
