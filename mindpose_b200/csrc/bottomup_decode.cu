@@ -883,6 +883,424 @@ __global__ void __launch_bounds__(kFastThreads, (C <= 8) ? 3 : 1)
   }
 }
 
+// ---------------------------------------------------------------------------
+// Pair scan (C = 8, two stages at exactly half size, 2x mask, 3x3 pool or none).
+//
+// Same decomposition as the fast kernel (one CTA per plane, one band of rows per warp,
+// lane = 8 columns, per-lane top 3 + CTA merge), but pass 1 walks the band two output
+// rows at a time, which is the natural unit of the 1/2-scale upsampling:
+//   * the horizontally interpolated low-resolution row L[p] (8 values per lane) is
+//     computed ONCE and used by output rows 2p-1, 2p and 2p+1 (the row-at-a-time scan
+//     interpolated both source rows again for every output row);
+//   * per pair a lane stages 5 x 16 B (rows 2p and 2p+1 of the high-resolution plane,
+//     low-resolution row p+1) instead of 2 x 5 x 16 B;
+//   * the mask is not read in the loop at all: mask_zero_rows_kernel reduces it to one
+//     word per (image, output row) -- bit l set when lane l's 8 pixels contain a masked
+//     one -- and only flagged rows fetch their mask bytes;
+//   * the vertical pool is one 3-input max per pixel.
+// A fourth register per lane (the largest value that was NOT kept in the lane's top 3)
+// makes the "could a lane have dropped a member of the top M" check exact up to ties.
+constexpr int kPairSeg = 512;                // 32 lanes x 16 B
+constexpr int kPairSlot = 5 * kPairSeg;      // hi(2p) x2 | hi(2p+1) x2 | low(p+1)
+static_assert(2 * kPairSlot <= kStageWarp, "pair ring must fit the row ring");
+
+// bit l of zrow[n * H + y]: some pixel x in [8l, 8l+8) of output row y is masked out
+__global__ void __launch_bounds__(256)
+    mask_zero_rows_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ zrow, int H,
+                          int W, int mh, int mw, float msy, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t n = r / H;
+  const int y = (int)(r - n * H);
+  const int my = min((int)floorf(__fmul_rn((float)y, msy)), mh - 1);
+  bool z = false;
+  if (lane * 8 < W) {
+    const uint4 mb = __ldg(reinterpret_cast<const uint4*>(mask + ((size_t)n * mh + my) * mw) + lane);
+    const uint32_t w[4] = {mb.x, mb.y, mb.z, mb.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) z |= (w[t] & 0xffu) == 0 || (w[t] & 0xff0000u) == 0;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, z);
+  if (lane == 0) zrow[r] = b;
+}
+
+__device__ __forceinline__ void pair_issue(const float* __restrict__ heat_hi,
+                                           const float* __restrict__ heat_lo, int W, int w0,
+                                           int h0, int p, int pe, int p_end,
+                                           unsigned char* slot, int x0, bool active) {
+  if (active && p <= p_end) {
+    const float* h = heat_hi + (size_t)(2 * p) * W + x0;
+    cp_async16(slot, h);
+    cp_async16(slot + kPairSeg, h + 4);
+    if (p < pe) {
+      cp_async16(slot + 2 * kPairSeg, h + W);
+      cp_async16(slot + 3 * kPairSeg, h + W + 4);
+      cp_async16(slot + 4 * kPairSeg, heat_lo + (size_t)min(p + 1, h0 - 1) * w0 + (x0 >> 1));
+    }
+  }
+  cp_async_commit();  // one group per pair, empty past the end: wait_group 1 stays exact
+}
+
+// horizontally interpolated low-resolution row: even columns are the samples, odd
+// columns a + (b - a) * 0.5 (legacy asymmetric bilinear at scale 1/2)
+__device__ __forceinline__ void lo_interp(const float4 q, bool last_lane, float (&L)[8]) {
+  const float nx = __shfl_down_sync(0xffffffffu, q.x, 1);
+  const float q4 = last_lane ? q.w : nx;
+  L[0] = q.x;
+  L[1] = __fadd_rn(q.x, __fmul_rn(__fsub_rn(q.y, q.x), 0.5f));
+  L[2] = q.y;
+  L[3] = __fadd_rn(q.y, __fmul_rn(__fsub_rn(q.z, q.y), 0.5f));
+  L[4] = q.z;
+  L[5] = __fadd_rn(q.z, __fmul_rn(__fsub_rn(q.w, q.z), 0.5f));
+  L[6] = q.w;
+  L[7] = __fadd_rn(q.w, __fmul_rn(__fsub_rn(q4, q.w), 0.5f));
+}
+
+__device__ __forceinline__ void mask_row_slow(const BuArgs& a, const uint8_t* __restrict__ mask,
+                                              int y, int x0, bool flagged, float (&v)[8]) {
+  if (flagged) {
+    const int my = min((int)floorf(__fmul_rn((float)y, a.msy)), a.mh - 1);
+    const uint4 mb = __ldg(reinterpret_cast<const uint4*>(mask + (size_t)my * a.mw + 2 * x0));
+    const uint32_t w[4] = {mb.x, mb.y, mb.z, mb.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if ((w[t] & 0xffu) == 0) v[2 * t] = 0.f;
+      if ((w[t] & 0xff0000u) == 0) v[2 * t + 1] = 0.f;
+    }
+  }
+}
+
+struct Top3x {
+  Top3 t;
+  float v4;  // upper bound of everything this lane saw and did not keep
+};
+
+template <bool NMS>
+__device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restrict__ heat_hi,
+                                           const float* __restrict__ heat_lo,
+                                           const uint8_t* __restrict__ mask,
+                                           const uint32_t* __restrict__ zrow, float* raw_out,
+                                           int rb, int re, int lane, int M, Top3x& tx,
+                                           volatile float* s_kth, int warp_id,
+                                           unsigned char* ring) {
+  const int H = a.h1, W = a.w1, h0 = a.h0, w0 = a.w0;
+  const int x0 = lane * 8;
+  const bool active = x0 < W;
+  const bool first_lane = lane == 0;
+  const bool last_lane = x0 + 8 >= W;
+  const int pb = rb >> 1, pe = re >> 1;
+  const int p_end = re < H ? pe : pe - 1;
+  const int kth_rank = (M + kFastWarps - 1) / kFastWarps;
+  unsigned char* slot0 = ring + lane * 16;
+  Top3& t3 = tx.t;
+
+  pair_issue(heat_hi, heat_lo, W, w0, h0, pb, pe, p_end, slot0, x0, active);
+  pair_issue(heat_hi, heat_lo, W, w0, h0, pb + 1, pe, p_end, slot0 + kPairSlot, x0, active);
+
+  // rows rb-1 .. re that contain masked pixels: bit j <-> row rb - 1 + j
+  const int zr0 = rb - 1, zlast = min(re, H - 1);
+  uint32_t za = 0, zb = 0;
+  {
+    const int r = zr0 + lane;
+    if (r >= 0 && r <= zlast) za = __ldg(zrow + r);
+    if (r + 32 <= zlast) zb = __ldg(zrow + r + 32);
+  }
+  const uint64_t nz = (uint64_t)__ballot_sync(0xffffffffu, za != 0) |
+                      ((uint64_t)__ballot_sync(0xffffffffu, zb != 0) << 32);
+  auto masked = [&](int y, float (&v)[8]) {  // only called when row y is flagged (uniform)
+    const int j = y - zr0;
+    const uint32_t bits = __shfl_sync(0xffffffffu, j < 32 ? za : zb, j & 31);
+    mask_row_slow(a, mask, y, x0, active && ((bits >> lane) & 1u), v);
+  };
+
+  float L0[8], vP[8], hPP[8], hP[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) vP[c] = hPP[c] = hP[c] = -INFINITY;
+  if (NMS && rb > 0) {
+    float t[8];
+    aggregate_row<8, true, true>(a, heat_hi, heat_lo, mask, rb - 1, x0, active, last_lane, t);
+    hmax3<8>(t, first_lane, last_lane, hP);
+  }
+  {
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) q = __ldg(reinterpret_cast<const float4*>(heat_lo + (size_t)pb * w0 + (x0 >> 1)));
+    lo_interp(q, last_lane, L0);
+  }
+
+  float t_lb = -INFINITY;
+  auto refresh_bound = [&]() {
+    // kth largest lane best of this warp (positive values only: integer order == float order)
+    int key = t3.v1 > 0.f ? __float_as_int(t3.v1) : 0;
+    int mx = 0;
+    for (int r = 0; r < kth_rank; ++r) {
+      mx = __reduce_max_sync(0xffffffffu, key);
+      const unsigned b = __ballot_sync(0xffffffffu, key == mx);
+      if (lane == __ffs(b) - 1) key = 0;
+    }
+    if (lane == 0) s_kth[warp_id] = mx > 0 ? __int_as_float(mx) : -INFINITY;
+    __syncwarp();
+    // min over the bands (slots hold -inf or a positive float: signed integer order)
+    int o = lane < kFastWarps ? __float_as_int(s_kth[lane]) : 0x7f800000;
+    o = __reduce_min_sync(0xffffffffu, o);
+    t_lb = fmaxf(t_lb, __int_as_float(o));
+  };
+
+  // NMS decision + per-lane top 3 for one finished row
+  auto evaluate = [&](int y, const float (&v)[8], const float (&pl)[8]) {
+    float m[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      m[c] = NMS ? __fmul_rn(v[c], pl[c] == v[c] ? 1.f : 0.f) : v[c];
+    float cm = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])),
+                     fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+    bool want = active && cm > t3.v3 && cm >= t_lb;
+    if (__any_sync(0xffffffffu, want)) {
+      const int row_base = y * W + x0;
+      while (want) {
+        int cb = 0;
+#pragma unroll
+        for (int c = 7; c >= 0; --c)
+          if (m[c] == cm) cb = c;
+        const int idx = row_base + cb;
+        tx.v4 = fmaxf(tx.v4, t3.v3);
+        if (cm > t3.v1) {
+          t3.v3 = t3.v2, t3.i3 = t3.i2;
+          t3.v2 = t3.v1, t3.i2 = t3.i1;
+          t3.v1 = cm, t3.i1 = idx;
+        } else if (cm > t3.v2) {
+          t3.v3 = t3.v2, t3.i3 = t3.i2;
+          t3.v2 = cm, t3.i2 = idx;
+        } else {
+          t3.v3 = cm, t3.i3 = idx;
+        }
+        cm = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c == cb) m[c] = -INFINITY;
+          cm = fmaxf(cm, m[c]);
+        }
+        want = cm > t3.v3 && cm >= t_lb;
+      }
+    }
+    if (active) tx.v4 = fmaxf(tx.v4, cm);  // the best value of this row that was not kept
+  };
+
+  for (int p = pb; p < pe; ++p) {
+    cp_async_wait_1();
+    const unsigned char* slot = slot0 + ((p - pb) & 1) * kPairSlot;
+    float4 a0, a1, b0, b1, q;
+    a0 = a1 = b0 = b1 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+      a0 = *reinterpret_cast<const float4*>(slot);
+      a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);
+      b0 = *reinterpret_cast<const float4*>(slot + 2 * kPairSeg);
+      b1 = *reinterpret_cast<const float4*>(slot + 3 * kPairSeg);
+      q = *reinterpret_cast<const float4*>(slot + 4 * kPairSeg);
+    }
+    pair_issue(heat_hi, heat_lo, W, w0, h0, p + 2, pe, p_end,
+               slot0 + ((p - pb) & 1) * kPairSlot, x0, active);
+    float L1[8];
+    lo_interp(q, last_lane, L1);
+    float v0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float v1[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      v0[c] = __fmul_rn(__fadd_rn(v0[c], L0[c]), 0.5f);
+      const float mid = __fadd_rn(L0[c], __fmul_rn(__fsub_rn(L1[c], L0[c]), 0.5f));
+      v1[c] = __fmul_rn(__fadd_rn(v1[c], mid), 0.5f);
+    }
+    const int y = 2 * p;
+    if ((nz >> (y - zr0)) & 3ull) {
+      if ((nz >> (y - zr0)) & 1ull) masked(y, v0);
+      if ((nz >> (y - zr0)) & 2ull) masked(y + 1, v1);
+    }
+    if (raw_out && active) {
+      float* o = raw_out + (size_t)y * W + x0;
+      st_stream_f4(o, make_float4(v0[0], v0[1], v0[2], v0[3]));
+      st_stream_f4(o + 4, make_float4(v0[4], v0[5], v0[6], v0[7]));
+      st_stream_f4(o + W, make_float4(v1[0], v1[1], v1[2], v1[3]));
+      st_stream_f4(o + W + 4, make_float4(v1[4], v1[5], v1[6], v1[7]));
+    }
+    if (NMS) {
+      float hA[8], hB[8], pl[8];
+      hmax3<8>(v0, first_lane, last_lane, hA);
+      if (p > pb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pl[c] = fmaxf(fmaxf(hPP[c], hP[c]), hA[c]);
+        evaluate(y - 1, vP, pl);
+      }
+      hmax3<8>(v1, first_lane, last_lane, hB);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) pl[c] = fmaxf(fmaxf(hP[c], hA[c]), hB[c]);
+      evaluate(y, v0, pl);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) vP[c] = v1[c], hPP[c] = hA[c], hP[c] = hB[c];
+    } else {
+      evaluate(y, v0, v0);
+      evaluate(y + 1, v1, v1);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) L0[c] = L1[c];
+    const int cnt = p - pb + 1;
+    if ((cnt & (cnt - 1)) == 0 || (cnt & 3) == 0) refresh_bound();
+  }
+  if (NMS) {  // the band's last row is still waiting for the row below it
+    float hN[8], pl[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) hN[c] = -INFINITY;
+    if (re < H) {
+      cp_async_wait_1();
+      const unsigned char* slot = slot0 + ((pe - pb) & 1) * kPairSlot;
+      float4 a0, a1;
+      a0 = a1 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (active) {
+        a0 = *reinterpret_cast<const float4*>(slot);
+        a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);
+      }
+      float v0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v0[c] = __fmul_rn(__fadd_rn(v0[c], L0[c]), 0.5f);
+      if ((nz >> (re - zr0)) & 1ull) masked(re, v0);
+      hmax3<8>(v0, first_lane, last_lane, hN);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) pl[c] = fmaxf(fmaxf(hPP[c], hP[c]), hN[c]);
+    evaluate(re - 1, vP, pl);
+  }
+  refresh_bound();  // final value of this band for the merge
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+template <bool NMS>
+__global__ void __launch_bounds__(kFastThreads, 3)
+    bottomup_decode_pairs_kernel(const BuArgs a, const uint32_t* __restrict__ zrow_all) {
+  __shared__ float s_lv[kFastWarps][32];
+  __shared__ int s_li[kFastWarps][32];
+  __shared__ int s_cnt[kFastWarps];
+  __shared__ float s_bv[kFastBuf];
+  __shared__ int s_bi[kFastBuf];
+  __shared__ float s_ov[32];
+  __shared__ int s_oi[32];
+  __shared__ int s_nbuf, s_nout;
+  __shared__ float s_kth[kFastWarps];
+  extern __shared__ __align__(16) unsigned char s_ring[];  // kFastWarps * kStageWarp
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.x / a.K, k = blockIdx.x - n * a.K;
+  const int H = a.h1, W = a.w1, M = a.M;
+  unsigned char* ring = s_ring + warp * kStageWarp;
+
+  const float* heat_lo = a.out0 + ((size_t)n * 2 * a.K + k) * a.h0 * a.w0;
+  const float* tag_src = a.out0 + ((size_t)n * 2 * a.K + a.K + k) * a.h0 * a.w0;
+  const float* heat_hi = a.out1 + ((size_t)n * a.K + k) * H * W;
+  const uint8_t* mask = a.mask + (size_t)n * a.mh * a.mw;
+  const uint32_t* zrow = zrow_all + (size_t)n * H;
+  float* raw_out = a.heatmap_raw ? a.heatmap_raw + ((size_t)n * a.K + k) * H * W : nullptr;
+
+  // even number of rows per band
+  const int R = (((H + kFastWarps - 1) / kFastWarps) + 1) & ~1;
+  const int rb = min(H, warp * R), re = min(H, rb + R);
+
+  if (tid == 0) s_nbuf = 0, s_nout = 0;
+  if (tid < kFastWarps) s_kth[tid] = -INFINITY;
+  __syncthreads();
+
+  Top3x tx;
+  tx.t.v1 = tx.t.v2 = tx.t.v3 = -INFINITY;
+  tx.t.i1 = tx.t.i2 = tx.t.i3 = 0x7fffffff;
+  tx.v4 = -INFINITY;
+  if (rb < re)
+    scan_pairs<NMS>(a, heat_hi, heat_lo, mask, zrow, raw_out, rb, re, lane, M, tx, s_kth, warp,
+                    ring);
+  const Top3& t3 = tx.t;
+
+  __syncthreads();  // every band has published its final kth
+  {
+    float tl = s_kth[0];
+#pragma unroll
+    for (int w = 1; w < kFastWarps; ++w) tl = fminf(tl, s_kth[w]);
+    const float ev[3] = {t3.v1, t3.v2, t3.v3};
+    const int ei[3] = {t3.i1, t3.i2, t3.i3};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      if (ei[e] != 0x7fffffff && ev[e] >= tl) {
+        const int pos = atomicAdd(&s_nbuf, 1);
+        s_bv[pos] = ev[e];
+        s_bi[pos] = ei[e];
+      }
+    }
+  }
+  __syncthreads();
+  const int nb = s_nbuf;
+  for (int t = tid; t < nb; t += kFastThreads) {
+    const float v = s_bv[t];
+    const int i = s_bi[t];
+    int rank = 0;
+    for (int j = 0; j < nb; ++j) rank += beats(s_bv[j], s_bi[j], v, i) ? 1 : 0;
+    if (rank < M) {
+      s_ov[rank] = v;
+      s_oi[rank] = i;
+    }
+  }
+  if (tid == 0) s_nout = min(nb, M);
+  __syncthreads();
+  // A lane dropped a member of the top M only if something it did not keep reaches the
+  // M-th result (ties go to the exact pass); a short union (e.g. -inf pixels, which the
+  // strict compares never keep) also does.
+  const int nout = s_nout;
+  const bool risk = nout < M || tx.v4 >= s_ov[M - 1];
+  const bool fallback = __syncthreads_or(risk ? 1 : 0) != 0;
+
+  if (!fallback) {
+    if (tid < nout) {
+      const size_t o = ((size_t)n * a.K + k) * M + tid;
+      const int ti = s_oi[tid];
+      const int y = (int)fdiv((uint32_t)ti, a.div_w1);
+      const int x = ti - y * W;
+      a.val_k[o] = s_ov[tid];
+      a.ind_k[2 * o] = (float)x;
+      a.ind_k[2 * o + 1] = (float)y;
+      a.tag_k[o] = bilinear_legacy(tag_src, a.h0, a.w0, a.sy, a.sx, y, x);
+    }
+    return;
+  }
+
+  // ---- pass 2 (rare): exact per-warp lists with the row-at-a-time scan ---------------
+  ExactList ex;
+  ex.top_v = -INFINITY, ex.top_i = 0x7fffffff, ex.count = 0;
+  ex.last_v = -INFINITY, ex.last_i = 0x7fffffff;
+  ex.pre_v = -INFINITY, ex.pre_i = 0x7fffffff;
+  if (nout == M) {
+    ex.pre_v = s_ov[M - 1];
+    ex.pre_i = s_oi[M - 1];
+  }
+  Top3 dummy = t3;
+  if (rb < re)
+    scan_band<8, true, true, true, true>(a, heat_hi, heat_lo, mask, nullptr, rb, re, lane, NMS, M,
+                                         dummy, ex, s_kth, warp, ring);
+  __syncthreads();  // everyone has read s_ov / s_oi
+  s_lv[warp][lane] = ex.top_v;
+  s_li[warp][lane] = ex.top_i;
+  if (lane == 0) s_cnt[warp] = ex.count;
+  __syncthreads();
+  if (lane < ex.count) {
+    int rank = lane;
+    for (int w = 0; w < kFastWarps; ++w)
+      if (w != warp) rank += count_beating(s_lv[w], s_li[w], s_cnt[w], ex.top_v, ex.top_i);
+    if (rank < M) {
+      const size_t o = ((size_t)n * a.K + k) * M + rank;
+      const int y = (int)fdiv((uint32_t)ex.top_i, a.div_w1);
+      const int x = ex.top_i - y * W;
+      a.val_k[o] = ex.top_v;
+      a.ind_k[2 * o] = (float)x;
+      a.ind_k[2 * o + 1] = (float)y;
+      a.tag_k[o] = bilinear_legacy(tag_src, a.h0, a.w0, a.sy, a.sx, y, x);
+    }
+  }
+}
+
 // tagging_heatmap output (bottom_up_decoder.py:118-120): the tag planes resized to the
 // output resolution; only _refine_missing and the visualiser read it.
 __global__ void __launch_bounds__(256)
@@ -1008,7 +1426,28 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
       else PC_BU_LAUNCH(CC, false, false);             \
     }                                                  \
   } while (0)
-    if (C == 4) PC_BU_PICK(4);
+    const bool pairs = C == 8 && two && mask2x && p->h1 % 2 == 0 && p->h1 <= 496;
+    if (pairs) {
+      // one word per (image, output row): which lanes see a masked pixel (stream-ordered scratch)
+      uint32_t* zrow = nullptr;
+      const int64_t rows = n * p->h1;
+      PC_CUDA(cudaMallocAsync((void**)&zrow, sizeof(uint32_t) * (size_t)rows, st));
+      mask_zero_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+          d_mask, zrow, p->h1, p->w1, p->mask_h, p->mask_w, a.msy, rows);
+      const size_t dyn = (size_t)kFastWarps * kStageWarp;
+      if (b.use_nms) {
+        PC_CUDA(cudaFuncSetAttribute(bottomup_decode_pairs_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        bottomup_decode_pairs_kernel<true><<<grid, kFastThreads, dyn, st>>>(b, zrow);
+      } else {
+        PC_CUDA(cudaFuncSetAttribute(bottomup_decode_pairs_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        bottomup_decode_pairs_kernel<false><<<grid, kFastThreads, dyn, st>>>(b, zrow);
+      }
+      const cudaError_t le = cudaGetLastError();
+      PC_CUDA(cudaFreeAsync(zrow, st));
+      PC_CUDA(le);
+    } else if (C == 4) PC_BU_PICK(4);
     else if (C == 8) PC_BU_PICK(8);
     else PC_BU_PICK(16);
 #undef PC_BU_PICK

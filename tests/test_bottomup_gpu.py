@@ -83,6 +83,65 @@ def test_decode_ties_and_flat_maps(cuda_device):
         assert np.array_equal(g.cpu().numpy(), w)
 
 
+@pytest.mark.parametrize("h0,w0,mask_hw,use_nms,nms_kernel", [
+    (96, 96, (384, 384), True, 3),      # W = 192: 24 active lanes
+    (72, 72, (288, 288), True, 3),      # W = 144, bands of 18 rows
+    (100, 100, (400, 400), True, 3),    # H = 200: ragged last band
+    (30, 80, (120, 320), True, 3),      # non-square, bands of 8 rows
+    (30, 80, (90, 320), True, 3),       # mask rows at 1.5x
+    (30, 80, (120, 320), False, 3),
+    (128, 128, (512, 512), True, 3)])
+def test_decode_pair_scan_matches_oracle(cuda_device, h0, w0, mask_hw, use_nms, nms_kernel):
+    """Shapes that take bottomup_decode_pairs_kernel (two stages at half size, 2x mask width,
+    128 < W <= 256): all five outputs bit-exact, masks with several zero rectangles."""
+    n = 3
+    d = synth.bottomup_outputs(n, 17, h0, w0, mask_hw=mask_hw, seed=h0 + w0, max_people=6)
+    rng = np.random.RandomState(h0)
+    for i in range(n):
+        for _ in range(4):
+            y0, x0 = rng.randint(0, mask_hw[0] - 8), rng.randint(0, mask_hw[1] - 8)
+            d["mask"][i, y0:y0 + rng.randint(1, 40), x0:x0 + rng.randint(1, 90)] = 0
+    d["mask"][1, :, :5] = 0
+    d["mask"][2, -3:, :] = 0
+    want = bd.decode([d["out0"], d["out1"]], d["mask"], use_nms=use_nms, nms_kernel=nms_kernel,
+                     max_num=30)
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=use_nms, nms_kernel=nms_kernel,
+                            max_num=30)
+    got = dec([_t(d["out0"], cuda_device), _t(d["out1"], cuda_device)], _t(d["mask"], cuda_device))
+    for name, g, w in zip(["val_k", "tag_k", "ind_k", "heatmap_raw", "tagging_heatmap"], got, want):
+        assert np.array_equal(g.cpu().numpy(), w), name
+
+
+@pytest.mark.parametrize("max_num", [30, 7])
+def test_decode_pair_scan_sparse_and_tied_planes(cuda_device, max_num):
+    """Planes with fewer than M positive survivors, plateaus, exact ties and one lane region
+    holding many of the top M: the exact second pass must take over."""
+    n, k, h0, w0 = 2, 17, 40, 80
+    rng = np.random.RandomState(5)
+    out0 = np.zeros((n, 2 * k, h0, w0), np.float32)
+    out1 = np.zeros((n, k, 2 * h0, 2 * w0), np.float32)
+    out0[:, k:] = rng.uniform(-1, 1, (n, k, h0, w0))
+    out1[0, 1] = 0.5                                   # plateau: every pixel survives
+    out1[0, 2, 5, 7] = out1[0, 2, 60, 130] = 0.9       # two spikes, zeros fill the rest
+    out1[0, 3] = -0.3                                  # negative plateau
+    out1[0, 4] = rng.uniform(-0.5, -0.1, (2 * h0, 2 * w0))   # all negative: zeros outrank survivors
+    for j in range(12):                                # 12 of the top M in one 8 x 10 lane region
+        out1[0, 5, 20 + 2 * (j // 4), 40 + 2 * (j % 4)] = 0.5 + 0.01 * j
+    out1[0, 5] += rng.uniform(0, 0.01, (2 * h0, 2 * w0)).astype(np.float32)
+    out1[0, 6] = np.round(rng.uniform(0, 4, (2 * h0, 2 * w0))) / 4   # heavy ties
+    out0[0, 6] = np.round(rng.uniform(0, 4, (h0, w0))) / 4
+    out1[1] = rng.uniform(-0.02, 0.02, (k, 2 * h0, 2 * w0))
+    out0[1, :k] = rng.uniform(-0.02, 0.02, (k, h0, w0))
+    mask = np.ones((n, 4 * h0, 4 * w0), np.uint8)
+    mask[0, :9, :] = 0
+    mask[1, 50:70, 100:300] = 0
+    want = bd.decode([out0, out1], mask, use_nms=True, nms_kernel=3, max_num=max_num)
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3, max_num=max_num)
+    got = dec([_t(out0, cuda_device), _t(out1, cuda_device)], _t(mask, cuda_device))
+    for name, g, w in zip(["val_k", "tag_k", "ind_k", "heatmap_raw"], got, want):
+        assert np.array_equal(g.cpu().numpy(), w), name
+
+
 def test_decode_full_size_properties(cuda_device):
     """BASELINE config 4 shapes (64 x [34,128,128] + [17,256,256], 512^2 mask): values sorted,
     indices in range and consistent with heatmap_raw; spot-check 2 images against the oracle."""
