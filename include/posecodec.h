@@ -208,6 +208,11 @@ int pc_bottomup_decode(const float* d_out0, const float* d_out1, const uint8_t* 
                        float* d_val_k, float* d_tag_k, float* d_ind_k, float* d_heatmap_raw,
                        float* d_tagging, const pc_bottomup_decode_params* params, int64_t n,
                        void* stream);
+/* Diagnostics: number of (image, joint) planes whose per-lane top-3 pass could not prove
+ * the top M and that were re-scanned by the exact pass, on the current device, since the
+ * last reset.  Synchronises the device.  Results are exact either way; a high count only
+ * costs time (planes with fewer than M positive local maxima always take the exact pass). */
+int pc_bottomup_decode_stats(int64_t* exact_pass_planes, int reset);
 
 /* ---- A18/A19: match_by_tag + instance score + transform_keypoints -------
  * mindpose/utils/match.py:14-116, engine/inferencer/bottomup_inferencer.py:

@@ -184,6 +184,7 @@ SIGNATURES = {
         c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, POINTER(BottomUpDecodeParams), c_int64, _P],
     ),
+    "pc_bottomup_decode_stats": (c_int, [POINTER(c_int64), c_int]),
     "pc_group_by_tag": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(GroupParams), c_int64, _P]),
     "pc_transform_keypoints": (
         c_int,

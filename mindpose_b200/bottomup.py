@@ -82,6 +82,14 @@ def decode(decoder, heatmap: List[torch.Tensor], tagging_heatmap: List[torch.Ten
     return val_k, tag_k, ind_k, raw_map, tag_map
 
 
+def decode_stats(reset: bool = False) -> int:
+    """Planes (image x joint) that needed the exact second pass since the last reset
+    (``pc_bottomup_decode_stats``; synchronises the device)."""
+    v = ctypes.c_int64(0)
+    _lib.call("pc_bottomup_decode_stats", ctypes.byref(v), int(reset))
+    return int(v.value)
+
+
 def group_by_tag(val_k: torch.Tensor, tag_k: torch.Tensor, ind_k: torch.Tensor,
                  joint_order: Sequence[int], vis_thr: float = 0.1, tag_thr: float = 1.0,
                  ignore_too_much: bool = False, use_rounded_norm: bool = True):

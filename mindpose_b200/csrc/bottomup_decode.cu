@@ -16,6 +16,7 @@
 // still produces many candidates is first cut down with the M-th largest
 // per-thread maximum, which is a valid lower bound for the M-th largest element.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -287,6 +288,9 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
 // low-resolution map is exactly half the size; anything else uses the generic kernel.
 constexpr int kFastWarps = 8;
 constexpr int kFastThreads = kFastWarps * 32;
+
+// planes that needed the exact second pass since the last reset (pc_bottomup_decode_stats)
+__device__ unsigned long long g_bu_exact_planes = 0ull;
 
 template <int C>
 struct RowRegs {
@@ -854,6 +858,7 @@ __global__ void __launch_bounds__(kFastThreads, (C <= 8) ? 3 : 1)
     return;
   }
 
+  if (tid == 0) atomicAdd(&g_bu_exact_planes, 1ull);
   // ---- pass 2 (rare): exact per-warp lists, pre-filtered by the M-th result ---------
   if (nout == M) {
     ex.pre_v = s_ov[M - 1];
@@ -904,57 +909,84 @@ constexpr int kPairSeg = 512;                // 32 lanes x 16 B
 constexpr int kPairSlot = 5 * kPairSeg;      // hi(2p) x2 | hi(2p+1) x2 | low(p+1)
 static_assert(2 * kPairSlot <= kStageWarp, "pair ring must fit the row ring");
 
-// bit l of zrow[n * H + y]: some pixel x in [8l, 8l+8) of output row y is masked out
+// bit l of zrow[n * H + y]: some pixel x in [8l, 8l+8) of output row y is masked out.
+// One warp per 4 rows (4 independent 16-byte loads in flight per lane).
 __global__ void __launch_bounds__(256)
     mask_zero_rows_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ zrow, int H,
                           int W, int mh, int mw, float msy, int64_t rows) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows) return;
-  const int64_t n = r / H;
-  const int y = (int)(r - n * H);
-  const int my = min((int)floorf(__fmul_rn((float)y, msy)), mh - 1);
-  bool z = false;
-  if (lane * 8 < W) {
-    const uint4 mb = __ldg(reinterpret_cast<const uint4*>(mask + ((size_t)n * mh + my) * mw) + lane);
-    const uint32_t w[4] = {mb.x, mb.y, mb.z, mb.w};
+  const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4;
+  uint4 mb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mb[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    const int64_t r = r0 + i;
+    if (r < rows && lane * 8 < W) {
+      const int64_t n = r / H;
+      const int y = (int)(r - n * H);
+      const int my = min((int)floorf(__fmul_rn((float)y, msy)), mh - 1);
+      mb[i] = __ldg(reinterpret_cast<const uint4*>(mask + ((size_t)n * mh + my) * mw) + lane);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t w[4] = {mb[i].x, mb[i].y, mb[i].z, mb[i].w};
+    bool z = false;
 #pragma unroll
     for (int t = 0; t < 4; ++t) z |= (w[t] & 0xffu) == 0 || (w[t] & 0xff0000u) == 0;
+    const unsigned b = __ballot_sync(0xffffffffu, z);
+    if (lane == 0 && r0 + i < rows) zrow[r0 + i] = b;
   }
-  const unsigned b = __ballot_sync(0xffffffffu, z);
-  if (lane == 0) zrow[r] = b;
 }
 
-__device__ __forceinline__ void pair_issue(const float* __restrict__ heat_hi,
-                                           const float* __restrict__ heat_lo, int W, int w0,
-                                           int h0, int p, int pe, int p_end,
-                                           unsigned char* slot, int x0, bool active) {
-  if (active && p <= p_end) {
-    const float* h = heat_hi + (size_t)(2 * p) * W + x0;
-    cp_async16(slot, h);
-    cp_async16(slot + kPairSeg, h + 4);
-    if (p < pe) {
-      cp_async16(slot + 2 * kPairSeg, h + W);
-      cp_async16(slot + 3 * kPairSeg, h + W + 4);
-      cp_async16(slot + 4 * kPairSeg, heat_lo + (size_t)min(p + 1, h0 - 1) * w0 + (x0 >> 1));
+__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem) : "memory");
+}
+
+// this lane's source pointers for the next pair to stage
+struct PairSrc {
+  const float* hi;  // row 2p, columns x0 .. x0+7
+  const float* lo;  // low-resolution row min(p + 1, h0 - 1), columns x0/2 .. x0/2+3
+  int p;
+};
+
+template <bool ALL>
+__device__ __forceinline__ void pair_issue(PairSrc& s, int W, int w0, int h0, int pe, int p_end,
+                                           uint32_t slot, bool active) {
+  if ((ALL || active) && s.p <= p_end) {
+    cp_async16_s(slot, s.hi);
+    cp_async16_s(slot + kPairSeg, s.hi + 4);
+    if (s.p < pe) {
+      cp_async16_s(slot + 2 * kPairSeg, s.hi + W);
+      cp_async16_s(slot + 3 * kPairSeg, s.hi + W + 4);
+      cp_async16_s(slot + 4 * kPairSeg, s.lo);
     }
   }
   cp_async_commit();  // one group per pair, empty past the end: wait_group 1 stays exact
+  s.hi += 2 * W;
+  if (s.p + 2 < h0) s.lo += w0;
+  ++s.p;
 }
 
-// horizontally interpolated low-resolution row: even columns are the samples, odd
-// columns a + (b - a) * 0.5 (legacy asymmetric bilinear at scale 1/2)
-__device__ __forceinline__ void lo_interp(const float4 q, bool last_lane, float (&L)[8]) {
-  const float nx = __shfl_down_sync(0xffffffffu, q.x, 1);
-  const float q4 = last_lane ? q.w : nx;
-  L[0] = q.x;
-  L[1] = __fadd_rn(q.x, __fmul_rn(__fsub_rn(q.y, q.x), 0.5f));
-  L[2] = q.y;
-  L[3] = __fadd_rn(q.y, __fmul_rn(__fsub_rn(q.z, q.y), 0.5f));
-  L[4] = q.z;
-  L[5] = __fadd_rn(q.z, __fmul_rn(__fsub_rn(q.w, q.z), 0.5f));
-  L[6] = q.w;
-  L[7] = __fadd_rn(q.w, __fmul_rn(__fsub_rn(q4, q.w), 0.5f));
+// HALF of the horizontally interpolated low-resolution row.  The reference computes
+// L = a + (b - a) * 0.5 on odd columns and the aggregate (hi + up) * 0.5; scaling by 0.5
+// commutes with every rounding step (binary floating point, no underflow), so the loop
+// works on hL = 0.5 * L and one fused multiply-add per term gives the same bits:
+//   0.5 * (a + (b - a) * 0.5) == fma(0.5 b - 0.5 a, 0.5, 0.5 a),  (hi + L) * 0.5 == fma(hi, 0.5, hL).
+// (Values within a factor 4 of the float32 underflow threshold are the only exception.)
+__device__ __forceinline__ void lo_interp_half(const float4 q, bool last_lane, float (&L)[8]) {
+  const float hx = __fmul_rn(q.x, 0.5f), hy = __fmul_rn(q.y, 0.5f);
+  const float hz = __fmul_rn(q.z, 0.5f), hw = __fmul_rn(q.w, 0.5f);
+  const float nx = __shfl_down_sync(0xffffffffu, hx, 1);
+  const float h4 = last_lane ? hw : nx;
+  L[0] = hx;
+  L[1] = __fmaf_rn(__fsub_rn(hy, hx), 0.5f, hx);
+  L[2] = hy;
+  L[3] = __fmaf_rn(__fsub_rn(hz, hy), 0.5f, hy);
+  L[4] = hz;
+  L[5] = __fmaf_rn(__fsub_rn(hw, hz), 0.5f, hz);
+  L[6] = hw;
+  L[7] = __fmaf_rn(__fsub_rn(h4, hw), 0.5f, hw);
 }
 
 __device__ __forceinline__ void mask_row_slow(const BuArgs& a, const uint8_t* __restrict__ mask,
@@ -971,32 +1003,89 @@ __device__ __forceinline__ void mask_row_slow(const BuArgs& a, const uint8_t* __
   }
 }
 
-struct Top3x {
-  Top3 t;
-  float v4;  // upper bound of everything this lane saw and did not keep
+// Per-band candidate buffer in shared memory (one per warp, count in a register).
+constexpr int kCandCap = 256;
+struct CandBuf {
+  float* v;
+  int* i;
+  int cnt;  // warp-uniform
 };
 
-template <bool NMS>
+// Keep the best M entries of a band's buffer (sorted: slot r = rank r).  With M entries
+// kept, the M-th is a lower bound of the plane's M-th best value.  Cold path: not inlined.
+struct CompressOut {
+  int cnt;
+  float bound;
+};
+__device__ __noinline__ CompressOut cand_compress(float* cv, int* ci, int cnt, int M, int lane) {
+  constexpr int S = kCandCap / 32;
+  float ev[S];
+  int ei[S], rk[S];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    const int e = lane + 32 * k;
+    ev[k] = -INFINITY, ei[k] = 0x7fffffff, rk[k] = 0;
+    if (e < cnt) ev[k] = cv[e], ei[k] = ci[e];
+  }
+  for (int j = 0; j < cnt; ++j) {
+    const float jv = cv[j];
+    const int ji = ci[j];
+#pragma unroll
+    for (int k = 0; k < S; ++k) rk[k] += beats(jv, ji, ev[k], ei[k]) ? 1 : 0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < S; ++k)
+    if (lane + 32 * k < cnt && rk[k] < M) cv[rk[k]] = ev[k], ci[rk[k]] = ei[k];
+  __syncwarp();
+  CompressOut o;
+  o.bound = cnt >= M ? cv[M - 1] : -INFINITY;
+  o.cnt = min(cnt, M);
+  return o;
+}
+
+// Pass 1 of the pair kernel over rows [rb, re) (both even).
+//
+// Only pixels that reach t_lb -- a lower bound of the plane's M-th best value, shared by
+// the CTA's bands -- can be in the result, and a pixel that reaches it is almost always a
+// local maximum.  So the pool is evaluated lazily: per output row a lane only takes the
+// maximum of its 8 aggregated values; the 3x3 max (vertical 3-max of the three rows, then
+// the horizontal 3-max with the neighbour columns by shuffle) and the survivor test run
+// only for rows in which some lane reaches t_lb (warp-uniform branch).  Survivors that
+// reach t_lb are appended to the band's buffer by ballot compaction (no per-lane
+// divergence); survivors below t_lb are never looked at, which is exact: they are strictly
+// below the M-th value.  Suppressed pixels (value * 0) are not collected either; they can
+// only belong to the top M when the M-th value is <= 0, and the merge sends exactly those
+// planes to the exact pass.
+//
+// ALL: W == 256, every lane owns 8 columns (no per-lane activity predicates)
+template <bool NMS, bool ALL>
 __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restrict__ heat_hi,
                                            const float* __restrict__ heat_lo,
                                            const uint8_t* __restrict__ mask,
                                            const uint32_t* __restrict__ zrow, float* raw_out,
-                                           int rb, int re, int lane, int M, Top3x& tx,
+                                           int rb, int re, int lane, int M, CandBuf& cb,
                                            volatile float* s_kth, int warp_id,
                                            unsigned char* ring) {
-  const int H = a.h1, W = a.w1, h0 = a.h0, w0 = a.w0;
+  const int H = a.h1, W = ALL ? 256 : a.w1, h0 = a.h0, w0 = ALL ? 128 : a.w0;
   const int x0 = lane * 8;
-  const bool active = x0 < W;
+  const bool active = ALL || x0 < W;
   const bool first_lane = lane == 0;
-  const bool last_lane = x0 + 8 >= W;
+  const bool last_lane = ALL ? lane == 31 : x0 + 8 >= W;
   const int pb = rb >> 1, pe = re >> 1;
   const int p_end = re < H ? pe : pe - 1;
   const int kth_rank = (M + kFastWarps - 1) / kFastWarps;
+  const unsigned lt_mask = (1u << lane) - 1u;
   unsigned char* slot0 = ring + lane * 16;
-  Top3& t3 = tx.t;
+  const uint32_t sa0 = smem_u32(slot0);
 
-  pair_issue(heat_hi, heat_lo, W, w0, h0, pb, pe, p_end, slot0, x0, active);
-  pair_issue(heat_hi, heat_lo, W, w0, h0, pb + 1, pe, p_end, slot0 + kPairSlot, x0, active);
+  PairSrc src;
+  src.hi = heat_hi + (size_t)rb * W + x0;
+  src.lo = heat_lo + (size_t)min(pb + 1, h0 - 1) * w0 + (x0 >> 1);
+  src.p = pb;
+  pair_issue<ALL>(src, W, w0, h0, pe, p_end, sa0, active);
+  pair_issue<ALL>(src, W, w0, h0, pe, p_end, sa0 + kPairSlot, active);
 
   // rows rb-1 .. re that contain masked pixels: bit j <-> row rb - 1 + j
   const int zr0 = rb - 1, zlast = min(re, H - 1);
@@ -1014,24 +1103,27 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
     mask_row_slow(a, mask, y, x0, active && ((bits >> lane) & 1u), v);
   };
 
-  float L0[8], vP[8], hPP[8], hP[8];
+  // state carried from pair to pair: hL = half of the interpolated low-resolution row p,
+  // vPP / vP = aggregated rows 2p-2 / 2p-1
+  float hL[8], vPP[8], vP[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) vP[c] = hPP[c] = hP[c] = -INFINITY;
-  if (NMS && rb > 0) {
-    float t[8];
-    aggregate_row<8, true, true>(a, heat_hi, heat_lo, mask, rb - 1, x0, active, last_lane, t);
-    hmax3<8>(t, first_lane, last_lane, hP);
-  }
+  for (int c = 0; c < 8; ++c) vPP[c] = vP[c] = -INFINITY;
+  if (NMS && rb > 0)
+    aggregate_row<8, true, true>(a, heat_hi, heat_lo, mask, rb - 1, x0, active, last_lane, vP);
   {
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) q = __ldg(reinterpret_cast<const float4*>(heat_lo + (size_t)pb * w0 + (x0 >> 1)));
-    lo_interp(q, last_lane, L0);
+    lo_interp_half(q, last_lane, hL);
   }
 
+  // t_lb: each band publishes the kth largest of its lanes' best candidates (k = ceil(M/8),
+  // distinct pixels); the minimum over the bands has >= M elements at or above it.  Stale
+  // reads of other bands' slots are only smaller, i.e. still valid.
   float t_lb = -INFINITY;
+  float best = -INFINITY;  // this lane's best candidate so far
   auto refresh_bound = [&]() {
-    // kth largest lane best of this warp (positive values only: integer order == float order)
-    int key = t3.v1 > 0.f ? __float_as_int(t3.v1) : 0;
+    // positive values only: integer order == float order
+    int key = best > 0.f ? __float_as_int(best) : 0;
     int mx = 0;
     for (int r = 0; r < kth_rank; ++r) {
       mx = __reduce_max_sync(0xffffffffu, key);
@@ -1040,76 +1132,68 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
     }
     if (lane == 0) s_kth[warp_id] = mx > 0 ? __int_as_float(mx) : -INFINITY;
     __syncwarp();
-    // min over the bands (slots hold -inf or a positive float: signed integer order)
+    // slots hold -inf or a positive float: signed integer order == float order
     int o = lane < kFastWarps ? __float_as_int(s_kth[lane]) : 0x7f800000;
     o = __reduce_min_sync(0xffffffffu, o);
     t_lb = fmaxf(t_lb, __int_as_float(o));
   };
 
-  // NMS decision + per-lane top 3 for one finished row
-  auto evaluate = [&](int y, const float (&v)[8], const float (&pl)[8]) {
-    float m[8];
+  // row y = vb, with the rows above (va) and below (vc) it
+  auto evaluate = [&](int y, const float (&va)[8], const float (&vb)[8], const float (&vc)[8]) {
+    const float vm = fmaxf(fmaxf(fmaxf(vb[0], vb[1]), fmaxf(vb[2], vb[3])),
+                           fmaxf(fmaxf(vb[4], vb[5]), fmaxf(vb[6], vb[7])));
+    if (!__any_sync(0xffffffffu, active && vm >= t_lb)) return;
+    float pl[8];
+    if (NMS) {
+      float cmx[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      m[c] = NMS ? __fmul_rn(v[c], pl[c] == v[c] ? 1.f : 0.f) : v[c];
-    float cm = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])),
-                     fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-    bool want = active && cm > t3.v3 && cm >= t_lb;
-    if (__any_sync(0xffffffffu, want)) {
-      const int row_base = y * W + x0;
-      while (want) {
-        int cb = 0;
+      for (int c = 0; c < 8; ++c) cmx[c] = fmaxf(fmaxf(va[c], vb[c]), vc[c]);
+      hmax3<8>(cmx, first_lane, last_lane, pl);
+    }
+    const int row_base = y * W + x0;
 #pragma unroll
-        for (int c = 7; c >= 0; --c)
-          if (m[c] == cm) cb = c;
-        const int idx = row_base + cb;
-        tx.v4 = fmaxf(tx.v4, t3.v3);
-        if (cm > t3.v1) {
-          t3.v3 = t3.v2, t3.i3 = t3.i2;
-          t3.v2 = t3.v1, t3.i2 = t3.i1;
-          t3.v1 = cm, t3.i1 = idx;
-        } else if (cm > t3.v2) {
-          t3.v3 = t3.v2, t3.i3 = t3.i2;
-          t3.v2 = cm, t3.i2 = idx;
-        } else {
-          t3.v3 = cm, t3.i3 = idx;
+    for (int c = 0; c < 8; ++c) {
+      const float bar = NMS ? fmaxf(pl[c], t_lb) : t_lb;
+      const bool pr = active && vb[c] >= bar;
+      const unsigned bal = __ballot_sync(0xffffffffu, pr);
+      if (bal) {
+        if (cb.cnt > kCandCap - 32) {
+          const CompressOut co = cand_compress(cb.v, cb.i, cb.cnt, M, lane);
+          cb.cnt = co.cnt;
+          t_lb = fmaxf(t_lb, co.bound);
         }
-        cm = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (c == cb) m[c] = -INFINITY;
-          cm = fmaxf(cm, m[c]);
+        if (pr) {
+          const int pos = cb.cnt + __popc(bal & lt_mask);
+          cb.v[pos] = vb[c];
+          cb.i[pos] = row_base + c;
+          best = fmaxf(best, vb[c]);
         }
-        want = cm > t3.v3 && cm >= t_lb;
+        cb.cnt += __popc(bal);
       }
     }
-    if (active) tx.v4 = fmaxf(tx.v4, cm);  // the best value of this row that was not kept
   };
 
+#pragma unroll 2
   for (int p = pb; p < pe; ++p) {
     cp_async_wait_1();
-    const unsigned char* slot = slot0 + ((p - pb) & 1) * kPairSlot;
-    float4 a0, a1, b0, b1, q;
-    a0 = a1 = b0 = b1 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-      a0 = *reinterpret_cast<const float4*>(slot);
-      a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);
-      b0 = *reinterpret_cast<const float4*>(slot + 2 * kPairSeg);
-      b1 = *reinterpret_cast<const float4*>(slot + 3 * kPairSeg);
-      q = *reinterpret_cast<const float4*>(slot + 4 * kPairSeg);
-    }
-    pair_issue(heat_hi, heat_lo, W, w0, h0, p + 2, pe, p_end,
-               slot0 + ((p - pb) & 1) * kPairSlot, x0, active);
-    float L1[8];
-    lo_interp(q, last_lane, L1);
+    const int tog = ((p - pb) & 1) * kPairSlot;
+    const unsigned char* slot = slot0 + tog;
+    const float4 a0 = *reinterpret_cast<const float4*>(slot);
+    const float4 a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);
+    const float4 b0 = *reinterpret_cast<const float4*>(slot + 2 * kPairSeg);
+    const float4 b1 = *reinterpret_cast<const float4*>(slot + 3 * kPairSeg);
+    const float4 q = *reinterpret_cast<const float4*>(slot + 4 * kPairSeg);
+    // (inactive lanes read stale bytes: nothing they compute reaches an active lane)
+    pair_issue<ALL>(src, W, w0, h0, pe, p_end, sa0 + tog, active);
+    float hN[8];
+    lo_interp_half(q, last_lane, hN);
     float v0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     float v1[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      v0[c] = __fmul_rn(__fadd_rn(v0[c], L0[c]), 0.5f);
-      const float mid = __fadd_rn(L0[c], __fmul_rn(__fsub_rn(L1[c], L0[c]), 0.5f));
-      v1[c] = __fmul_rn(__fadd_rn(v1[c], mid), 0.5f);
+      v0[c] = __fmaf_rn(v0[c], 0.5f, hL[c]);
+      const float hmid = __fmaf_rn(__fsub_rn(hN[c], hL[c]), 0.5f, hL[c]);
+      v1[c] = __fmaf_rn(v1[c], 0.5f, hmid);
     }
     const int y = 2 * p;
     if ((nz >> (y - zr0)) & 3ull) {
@@ -1124,68 +1208,56 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
       st_stream_f4(o + W + 4, make_float4(v1[4], v1[5], v1[6], v1[7]));
     }
     if (NMS) {
-      float hA[8], hB[8], pl[8];
-      hmax3<8>(v0, first_lane, last_lane, hA);
-      if (p > pb) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) pl[c] = fmaxf(fmaxf(hPP[c], hP[c]), hA[c]);
-        evaluate(y - 1, vP, pl);
-      }
-      hmax3<8>(v1, first_lane, last_lane, hB);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) pl[c] = fmaxf(fmaxf(hP[c], hA[c]), hB[c]);
-      evaluate(y, v0, pl);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) vP[c] = v1[c], hPP[c] = hA[c], hP[c] = hB[c];
+      if (p > pb) evaluate(y - 1, vPP, vP, v0);
+      evaluate(y, vP, v0, v1);
     } else {
-      evaluate(y, v0, v0);
-      evaluate(y + 1, v1, v1);
+      evaluate(y, v0, v0, v0);
+      evaluate(y + 1, v1, v1, v1);
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) L0[c] = L1[c];
+    for (int c = 0; c < 8; ++c) vPP[c] = v0[c], vP[c] = v1[c], hL[c] = hN[c];
     const int cnt = p - pb + 1;
-    if ((cnt & (cnt - 1)) == 0 || (cnt & 3) == 0) refresh_bound();
+    if (cnt <= 4 || (cnt <= 8 && (cnt & 1) == 0) || (cnt & 3) == 0) refresh_bound();
   }
   if (NMS) {  // the band's last row is still waiting for the row below it
-    float hN[8], pl[8];
+    float vN[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) hN[c] = -INFINITY;
+    for (int c = 0; c < 8; ++c) vN[c] = -INFINITY;
     if (re < H) {
       cp_async_wait_1();
       const unsigned char* slot = slot0 + ((pe - pb) & 1) * kPairSlot;
-      float4 a0, a1;
-      a0 = a1 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      if (active) {
-        a0 = *reinterpret_cast<const float4*>(slot);
-        a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);
-      }
+      const float4 a0 = *reinterpret_cast<const float4*>(slot);
+      const float4 a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);
       float v0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-      for (int c = 0; c < 8; ++c) v0[c] = __fmul_rn(__fadd_rn(v0[c], L0[c]), 0.5f);
-      if ((nz >> (re - zr0)) & 1ull) masked(re, v0);
-      hmax3<8>(v0, first_lane, last_lane, hN);
+      for (int c = 0; c < 8; ++c) vN[c] = __fmaf_rn(v0[c], 0.5f, hL[c]);
+      if ((nz >> (re - zr0)) & 1ull) masked(re, vN);
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) pl[c] = fmaxf(fmaxf(hPP[c], hP[c]), hN[c]);
-    evaluate(re - 1, vP, pl);
+    evaluate(re - 1, vPP, vP, vN);
   }
   refresh_bound();  // final value of this band for the merge
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-template <bool NMS>
-__global__ void __launch_bounds__(kFastThreads, 3)
+constexpr int kPairBuf = kFastWarps * kCandCap;
+
+template <bool NMS, bool ALL, int MINB>
+__global__ void __launch_bounds__(kFastThreads, MINB)
     bottomup_decode_pairs_kernel(const BuArgs a, const uint32_t* __restrict__ zrow_all) {
   __shared__ float s_lv[kFastWarps][32];
   __shared__ int s_li[kFastWarps][32];
   __shared__ int s_cnt[kFastWarps];
-  __shared__ float s_bv[kFastBuf];
-  __shared__ int s_bi[kFastBuf];
+  __shared__ float s_cv[kFastWarps][kCandCap];
+  __shared__ int s_ci[kFastWarps][kCandCap];
   __shared__ float s_ov[32];
   __shared__ int s_oi[32];
   __shared__ int s_nbuf, s_nout;
   __shared__ float s_kth[kFastWarps];
   extern __shared__ __align__(16) unsigned char s_ring[];  // kFastWarps * kStageWarp
+  static_assert(kPairBuf * 8 <= kFastWarps * kStageWarp, "merge buffer must fit the ring");
+  // merge buffer: reuses the staging ring once every band is done with it
+  float* s_bv = reinterpret_cast<float*>(s_ring);
+  int* s_bi = reinterpret_cast<int*>(s_ring) + kPairBuf;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.x / a.K, k = blockIdx.x - n * a.K;
@@ -1207,28 +1279,25 @@ __global__ void __launch_bounds__(kFastThreads, 3)
   if (tid < kFastWarps) s_kth[tid] = -INFINITY;
   __syncthreads();
 
-  Top3x tx;
-  tx.t.v1 = tx.t.v2 = tx.t.v3 = -INFINITY;
-  tx.t.i1 = tx.t.i2 = tx.t.i3 = 0x7fffffff;
-  tx.v4 = -INFINITY;
+  CandBuf cb;
+  cb.v = s_cv[warp];
+  cb.i = s_ci[warp];
+  cb.cnt = 0;
   if (rb < re)
-    scan_pairs<NMS>(a, heat_hi, heat_lo, mask, zrow, raw_out, rb, re, lane, M, tx, s_kth, warp,
-                    ring);
-  const Top3& t3 = tx.t;
+    scan_pairs<NMS, ALL>(a, heat_hi, heat_lo, mask, zrow, raw_out, rb, re, lane, M, cb, s_kth,
+                         warp, ring);
 
   __syncthreads();  // every band has published its final kth
   {
     float tl = s_kth[0];
 #pragma unroll
     for (int w = 1; w < kFastWarps; ++w) tl = fminf(tl, s_kth[w]);
-    const float ev[3] = {t3.v1, t3.v2, t3.v3};
-    const int ei[3] = {t3.i1, t3.i2, t3.i3};
-#pragma unroll
-    for (int e = 0; e < 3; ++e) {
-      if (ei[e] != 0x7fffffff && ev[e] >= tl) {
+    for (int e = lane; e < cb.cnt; e += 32) {
+      const float v = cb.v[e];
+      if (v >= tl) {
         const int pos = atomicAdd(&s_nbuf, 1);
-        s_bv[pos] = ev[e];
-        s_bi[pos] = ei[e];
+        s_bv[pos] = v;
+        s_bi[pos] = cb.i[e];
       }
     }
   }
@@ -1246,12 +1315,11 @@ __global__ void __launch_bounds__(kFastThreads, 3)
   }
   if (tid == 0) s_nout = min(nb, M);
   __syncthreads();
-  // A lane dropped a member of the top M only if something it did not keep reaches the
-  // M-th result (ties go to the exact pass); a short union (e.g. -inf pixels, which the
-  // strict compares never keep) also does.
+  // The buffers hold every survivor that reached the bound, so the result is exact unless
+  // fewer than M were collected or the M-th value is <= 0: then suppressed pixels
+  // (value * 0), which pass 1 never collects, could belong to the top M.
   const int nout = s_nout;
-  const bool risk = nout < M || tx.v4 >= s_ov[M - 1];
-  const bool fallback = __syncthreads_or(risk ? 1 : 0) != 0;
+  const bool fallback = nout < M || !(s_ov[M - 1] > 0.f);  // CTA-uniform
 
   if (!fallback) {
     if (tid < nout) {
@@ -1267,16 +1335,20 @@ __global__ void __launch_bounds__(kFastThreads, 3)
     return;
   }
 
+  if (tid == 0) atomicAdd(&g_bu_exact_planes, 1ull);
   // ---- pass 2 (rare): exact per-warp lists with the row-at-a-time scan ---------------
   ExactList ex;
   ex.top_v = -INFINITY, ex.top_i = 0x7fffffff, ex.count = 0;
   ex.last_v = -INFINITY, ex.last_i = 0x7fffffff;
   ex.pre_v = -INFINITY, ex.pre_i = 0x7fffffff;
-  if (nout == M) {
+  if (nout == M && s_ov[M - 1] > 0.f) {
+    // every pass-1 candidate is a real survivor, so the M-th of them bounds the result
     ex.pre_v = s_ov[M - 1];
     ex.pre_i = s_oi[M - 1];
   }
-  Top3 dummy = t3;
+  Top3 dummy;
+  dummy.v1 = dummy.v2 = dummy.v3 = -INFINITY;
+  dummy.i1 = dummy.i2 = dummy.i3 = 0x7fffffff;
   if (rb < re)
     scan_band<8, true, true, true, true>(a, heat_hi, heat_lo, mask, nullptr, rb, re, lane, NMS, M,
                                          dummy, ex, s_kth, warp, ring);
@@ -1300,6 +1372,7 @@ __global__ void __launch_bounds__(kFastThreads, 3)
     }
   }
 }
+
 
 // tagging_heatmap output (bottom_up_decoder.py:118-120): the tag planes resized to the
 // output resolution; only _refine_missing and the visualiser read it.
@@ -1328,6 +1401,17 @@ __global__ void __launch_bounds__(256)
 }  // namespace pc
 
 using namespace pc;
+
+extern "C" int pc_bottomup_decode_stats(int64_t* exact_pass_planes, int reset) {
+  unsigned long long v = 0ull;
+  PC_CUDA(cudaMemcpyFromSymbol(&v, g_bu_exact_planes, sizeof(v)));
+  if (exact_pass_planes) *exact_pass_planes = (int64_t)v;
+  if (reset) {
+    v = 0ull;
+    PC_CUDA(cudaMemcpyToSymbol(g_bu_exact_planes, &v, sizeof(v)));
+  }
+  return PC_OK;
+}
 
 extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
                                   const uint8_t* d_mask, float* d_val_k, float* d_tag_k,
@@ -1432,18 +1516,32 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
       uint32_t* zrow = nullptr;
       const int64_t rows = n * p->h1;
       PC_CUDA(cudaMallocAsync((void**)&zrow, sizeof(uint32_t) * (size_t)rows, st));
-      mask_zero_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+      mask_zero_rows_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(
           d_mask, zrow, p->h1, p->w1, p->mask_h, p->mask_w, a.msy, rows);
       const size_t dyn = (size_t)kFastWarps * kStageWarp;
+      const bool all = p->w1 == 256 && p->w0 == 128;
+      const char* env_minb = getenv("PC_BU_MINB");  // experiment switch
+      const bool minb2 = !(env_minb && env_minb[0] == '3');
+#define PC_BU_PAIRS(NMS_, ALL_)                                                              \
+  do {                                                                                       \
+    if (minb2) {                                                                             \
+      PC_CUDA(cudaFuncSetAttribute(bottomup_decode_pairs_kernel<NMS_, ALL_, 2>,              \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));  \
+      bottomup_decode_pairs_kernel<NMS_, ALL_, 2><<<grid, kFastThreads, dyn, st>>>(b, zrow); \
+    } else {                                                                                 \
+      PC_CUDA(cudaFuncSetAttribute(bottomup_decode_pairs_kernel<NMS_, ALL_, 3>,              \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));  \
+      bottomup_decode_pairs_kernel<NMS_, ALL_, 3><<<grid, kFastThreads, dyn, st>>>(b, zrow); \
+    }                                                                                        \
+  } while (0)
       if (b.use_nms) {
-        PC_CUDA(cudaFuncSetAttribute(bottomup_decode_pairs_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        bottomup_decode_pairs_kernel<true><<<grid, kFastThreads, dyn, st>>>(b, zrow);
+        if (all) PC_BU_PAIRS(true, true);
+        else PC_BU_PAIRS(true, false);
       } else {
-        PC_CUDA(cudaFuncSetAttribute(bottomup_decode_pairs_kernel<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        bottomup_decode_pairs_kernel<false><<<grid, kFastThreads, dyn, st>>>(b, zrow);
+        if (all) PC_BU_PAIRS(false, true);
+        else PC_BU_PAIRS(false, false);
       }
+#undef PC_BU_PAIRS
       const cudaError_t le = cudaGetLastError();
       PC_CUDA(cudaFreeAsync(zrow, st));
       PC_CUDA(le);

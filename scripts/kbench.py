@@ -147,6 +147,9 @@ def main():
         dec.return_maps = False
         fn = lambda: dec([out0, out1], mask)  # noqa: E731
         med, mn = timeit(fn, args.iters)
+        bottomup.decode_stats(reset=True)
+        fn()
+        print(f"  exact-pass planes in one call: {bottomup.decode_stats()} of {n * 17}")
         report("bottomup_decode 64 x (34x128^2 + 17x256^2)", n, "images", 6946816 + 8160, med, mn)
         if "group" in only:
             val_k, tag_k, ind_k, _, _ = dec([out0, out1], mask)
