@@ -433,6 +433,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_pending() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_1() {
   asm volatile("cp.async.wait_group 1;" ::: "memory");
 }
@@ -907,13 +911,16 @@ __global__ void __launch_bounds__(kFastThreads, (C <= 8) ? 3 : 1)
 // makes the "could a lane have dropped a member of the top M" check exact up to ties.
 constexpr int kPairSeg = 512;                // 32 lanes x 16 B
 constexpr int kPairSlot = 5 * kPairSeg;      // hi(2p) x2 | hi(2p+1) x2 | low(p+1)
-static_assert(2 * kPairSlot <= kStageWarp, "pair ring must fit the row ring");
+static_assert(2 * kPairSlot >= kStageWarp, "the exact pass reuses the ring for its row staging");
 
 // bit l of zrow[n * H + y]: some pixel x in [8l, 8l+8) of output row y is masked out.
 // One warp per 4 rows (4 independent 16-byte loads in flight per lane).
 __global__ void __launch_bounds__(256)
     mask_zero_rows_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ zrow, int H,
                           int W, int mh, int mw, float msy, int64_t rows) {
+  // programmatic dependent launch: the decode kernel may start its prologue now; it waits
+  // (griddepcontrol.wait) for this whole grid before it reads zrow
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4;
   uint4 mb[4];
@@ -1008,42 +1015,9 @@ constexpr int kCandCap = 256;
 struct CandBuf {
   float* v;
   int* i;
-  int cnt;  // warp-uniform
+  int cnt;        // warp-uniform
+  bool overflow;  // a row did not fit: the buffer is no longer complete
 };
-
-// Keep the best M entries of a band's buffer (sorted: slot r = rank r).  With M entries
-// kept, the M-th is a lower bound of the plane's M-th best value.  Cold path: not inlined.
-struct CompressOut {
-  int cnt;
-  float bound;
-};
-__device__ __noinline__ CompressOut cand_compress(float* cv, int* ci, int cnt, int M, int lane) {
-  constexpr int S = kCandCap / 32;
-  float ev[S];
-  int ei[S], rk[S];
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < S; ++k) {
-    const int e = lane + 32 * k;
-    ev[k] = -INFINITY, ei[k] = 0x7fffffff, rk[k] = 0;
-    if (e < cnt) ev[k] = cv[e], ei[k] = ci[e];
-  }
-  for (int j = 0; j < cnt; ++j) {
-    const float jv = cv[j];
-    const int ji = ci[j];
-#pragma unroll
-    for (int k = 0; k < S; ++k) rk[k] += beats(jv, ji, ev[k], ei[k]) ? 1 : 0;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < S; ++k)
-    if (lane + 32 * k < cnt && rk[k] < M) cv[rk[k]] = ev[k], ci[rk[k]] = ei[k];
-  __syncwarp();
-  CompressOut o;
-  o.bound = cnt >= M ? cv[M - 1] : -INFINITY;
-  o.cnt = min(cnt, M);
-  return o;
-}
 
 // Pass 1 of the pair kernel over rows [rb, re) (both even).
 //
@@ -1057,10 +1031,11 @@ __device__ __noinline__ CompressOut cand_compress(float* cv, int* ci, int cnt, i
 // divergence); survivors below t_lb are never looked at, which is exact: they are strictly
 // below the M-th value.  Suppressed pixels (value * 0) are not collected either; they can
 // only belong to the top M when the M-th value is <= 0, and the merge sends exactly those
-// planes to the exact pass.
+// planes to the exact pass -- as it does planes in which a band's buffer overflowed
+// (plateaus: hundreds of survivors at or above the bound in one band).
 //
 // ALL: W == 256, every lane owns 8 columns (no per-lane activity predicates)
-template <bool NMS, bool ALL>
+template <bool NMS, bool ALL, int kPairDepth>
 __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restrict__ heat_hi,
                                            const float* __restrict__ heat_lo,
                                            const uint8_t* __restrict__ mask,
@@ -1077,23 +1052,47 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
   const int p_end = re < H ? pe : pe - 1;
   const int kth_rank = (M + kFastWarps - 1) / kFastWarps;
   const unsigned lt_mask = (1u << lane) - 1u;
+  constexpr int kPairWarp = kPairDepth * kPairSlot;
   unsigned char* slot0 = ring + lane * 16;
   const uint32_t sa0 = smem_u32(slot0);
+
+  // Prologue loads first, all independent, so that their round trips overlap each other and
+  // the first two staged pairs: mask flags of rows rb-1 .. re (bit j <-> row rb - 1 + j),
+  // low-resolution rows pb-1 and pb, row rb-1 of the high-resolution plane (the band's
+  // upper halo).
+  const int zr0 = rb - 1, zlast = min(re, H - 1);
+  const bool halo = NMS && rb > 0;
+  uint32_t za = 0, zb = 0;
+  float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+  float4 g0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), g1 = g0;
+  {
+    if (active) {
+      const float* lrow = heat_lo + (size_t)pb * w0 + (x0 >> 1);
+      qb = __ldg(reinterpret_cast<const float4*>(lrow));
+      if (halo) {
+        qa = __ldg(reinterpret_cast<const float4*>(lrow - w0));
+        const float* hrow = heat_hi + (size_t)(rb - 1) * W + x0;
+        g0 = ld_stream_f4(hrow);
+        g1 = ld_stream_f4(hrow + 4);
+      }
+    }
+  }
 
   PairSrc src;
   src.hi = heat_hi + (size_t)rb * W + x0;
   src.lo = heat_lo + (size_t)min(pb + 1, h0 - 1) * w0 + (x0 >> 1);
   src.p = pb;
-  pair_issue<ALL>(src, W, w0, h0, pe, p_end, sa0, active);
-  pair_issue<ALL>(src, W, w0, h0, pe, p_end, sa0 + kPairSlot, active);
+#pragma unroll
+  for (int d = 0; d < kPairDepth; ++d)
+    pair_issue<ALL>(src, W, w0, h0, pe, p_end, sa0 + d * kPairSlot, active);
 
-  // rows rb-1 .. re that contain masked pixels: bit j <-> row rb - 1 + j
-  const int zr0 = rb - 1, zlast = min(re, H - 1);
-  uint32_t za = 0, zb = 0;
+  // zrow is written by mask_zero_rows_kernel, which this kernel may overlap (programmatic
+  // dependent launch): wait for that grid, then read with plain (coherent) loads
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   {
     const int r = zr0 + lane;
-    if (r >= 0 && r <= zlast) za = __ldg(zrow + r);
-    if (r + 32 <= zlast) zb = __ldg(zrow + r + 32);
+    if (r >= 0 && r <= zlast) za = *(const volatile uint32_t*)(zrow + r);
+    if (r + 32 <= zlast) zb = *(const volatile uint32_t*)(zrow + r + 32);
   }
   const uint64_t nz = (uint64_t)__ballot_sync(0xffffffffu, za != 0) |
                       ((uint64_t)__ballot_sync(0xffffffffu, zb != 0) << 32);
@@ -1108,12 +1107,15 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
   float hL[8], vPP[8], vP[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) vPP[c] = vP[c] = -INFINITY;
-  if (NMS && rb > 0)
-    aggregate_row<8, true, true>(a, heat_hi, heat_lo, mask, rb - 1, x0, active, last_lane, vP);
-  {
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) q = __ldg(reinterpret_cast<const float4*>(heat_lo + (size_t)pb * w0 + (x0 >> 1)));
-    lo_interp_half(q, last_lane, hL);
+  lo_interp_half(qb, last_lane, hL);
+  if (halo) {  // row rb-1 = 2(pb-1)+1: between low-resolution rows pb-1 and pb
+    float hA[8];
+    lo_interp_half(qa, last_lane, hA);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      vP[c] = __fmaf_rn(g[c], 0.5f, __fmaf_rn(__fsub_rn(hL[c], hA[c]), 0.5f, hA[c]));
+    if (nz & 1ull) masked(rb - 1, vP);
   }
 
   // t_lb: each band publishes the kth largest of its lanes' best candidates (k = ceil(M/8),
@@ -1150,33 +1152,45 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
       for (int c = 0; c < 8; ++c) cmx[c] = fmaxf(fmaxf(va[c], vb[c]), vc[c]);
       hmax3<8>(cmx, first_lane, last_lane, pl);
     }
-    const int row_base = y * W + x0;
+    // all eight ballots first (independent), then one branch for the common "no survivor" case
+    bool pr[8];
+    unsigned bal[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float bar = NMS ? fmaxf(pl[c], t_lb) : t_lb;
-      const bool pr = active && vb[c] >= bar;
-      const unsigned bal = __ballot_sync(0xffffffffu, pr);
-      if (bal) {
-        if (cb.cnt > kCandCap - 32) {
-          const CompressOut co = cand_compress(cb.v, cb.i, cb.cnt, M, lane);
-          cb.cnt = co.cnt;
-          t_lb = fmaxf(t_lb, co.bound);
-        }
-        if (pr) {
-          const int pos = cb.cnt + __popc(bal & lt_mask);
+      pr[c] = active && vb[c] >= bar;
+      bal[c] = __ballot_sync(0xffffffffu, pr[c]);
+    }
+    const unsigned any = (bal[0] | bal[1] | bal[2] | bal[3]) | (bal[4] | bal[5] | bal[6] | bal[7]);
+    if (any == 0) return;
+    int total = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) total += __popc(bal[c]);
+    if (cb.cnt + total > kCandCap) {  // does not happen on heat maps (a band collects ~150)
+      cb.overflow = true;             // -> the plane goes to the exact pass
+      return;
+    }
+    const int row_base = y * W + x0;
+    int base = cb.cnt;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (bal[c]) {  // warp-uniform
+        if (pr[c]) {
+          const int pos = base + __popc(bal[c] & lt_mask);
           cb.v[pos] = vb[c];
           cb.i[pos] = row_base + c;
           best = fmaxf(best, vb[c]);
         }
-        cb.cnt += __popc(bal);
+        base += __popc(bal[c]);
       }
     }
+    cb.cnt = base;
   };
 
-#pragma unroll 2
+#pragma unroll 1
+  int tog = 0;  // byte offset of pair p's slot in the ring
   for (int p = pb; p < pe; ++p) {
-    cp_async_wait_1();
-    const int tog = ((p - pb) & 1) * kPairSlot;
+    cp_async_wait_pending<kPairDepth - 1>();
     const unsigned char* slot = slot0 + tog;
     const float4 a0 = *reinterpret_cast<const float4*>(slot);
     const float4 a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);
@@ -1185,6 +1199,7 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
     const float4 q = *reinterpret_cast<const float4*>(slot + 4 * kPairSeg);
     // (inactive lanes read stale bytes: nothing they compute reaches an active lane)
     pair_issue<ALL>(src, W, w0, h0, pe, p_end, sa0 + tog, active);
+    tog = tog + kPairSlot == kPairWarp ? 0 : tog + kPairSlot;
     float hN[8];
     lo_interp_half(q, last_lane, hN);
     float v0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -1224,8 +1239,8 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
 #pragma unroll
     for (int c = 0; c < 8; ++c) vN[c] = -INFINITY;
     if (re < H) {
-      cp_async_wait_1();
-      const unsigned char* slot = slot0 + ((pe - pb) & 1) * kPairSlot;
+      cp_async_wait_pending<kPairDepth - 1>();
+      const unsigned char* slot = slot0 + tog;
       const float4 a0 = *reinterpret_cast<const float4*>(slot);
       const float4 a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);
       float v0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -1253,8 +1268,11 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   __shared__ int s_oi[32];
   __shared__ int s_nbuf, s_nout;
   __shared__ float s_kth[kFastWarps];
-  extern __shared__ __align__(16) unsigned char s_ring[];  // kFastWarps * kStageWarp
-  static_assert(kPairBuf * 8 <= kFastWarps * kStageWarp, "merge buffer must fit the ring");
+  // pairs in flight per warp: 3 CTAs per SM only fit with a two-deep ring
+  constexpr int kPairDepth = MINB >= 3 ? 2 : 3;
+  constexpr int kPairWarp = kPairDepth * kPairSlot;
+  extern __shared__ __align__(16) unsigned char s_ring[];  // kFastWarps * kPairWarp
+  static_assert(kPairBuf * 8 <= kFastWarps * kPairWarp, "merge buffer must fit the ring");
   // merge buffer: reuses the staging ring once every band is done with it
   float* s_bv = reinterpret_cast<float*>(s_ring);
   int* s_bi = reinterpret_cast<int*>(s_ring) + kPairBuf;
@@ -1262,7 +1280,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.x / a.K, k = blockIdx.x - n * a.K;
   const int H = a.h1, W = a.w1, M = a.M;
-  unsigned char* ring = s_ring + warp * kStageWarp;
+  unsigned char* ring = s_ring + warp * kPairWarp;
 
   const float* heat_lo = a.out0 + ((size_t)n * 2 * a.K + k) * a.h0 * a.w0;
   const float* tag_src = a.out0 + ((size_t)n * 2 * a.K + a.K + k) * a.h0 * a.w0;
@@ -1283,9 +1301,10 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   cb.v = s_cv[warp];
   cb.i = s_ci[warp];
   cb.cnt = 0;
+  cb.overflow = false;
   if (rb < re)
-    scan_pairs<NMS, ALL>(a, heat_hi, heat_lo, mask, zrow, raw_out, rb, re, lane, M, cb, s_kth,
-                         warp, ring);
+    scan_pairs<NMS, ALL, kPairDepth>(a, heat_hi, heat_lo, mask, zrow, raw_out, rb, re, lane, M, cb,
+                                     s_kth, warp, ring);
 
   __syncthreads();  // every band has published its final kth
   {
@@ -1307,6 +1326,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
     const float v = s_bv[t];
     const int i = s_bi[t];
     int rank = 0;
+#pragma unroll 4
     for (int j = 0; j < nb; ++j) rank += beats(s_bv[j], s_bi[j], v, i) ? 1 : 0;
     if (rank < M) {
       s_ov[rank] = v;
@@ -1319,7 +1339,8 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   // fewer than M were collected or the M-th value is <= 0: then suppressed pixels
   // (value * 0), which pass 1 never collects, could belong to the top M.
   const int nout = s_nout;
-  const bool fallback = nout < M || !(s_ov[M - 1] > 0.f);  // CTA-uniform
+  const bool fallback =
+      __syncthreads_or(cb.overflow ? 1 : 0) != 0 || nout < M || !(s_ov[M - 1] > 0.f);
 
   if (!fallback) {
     if (tid < nout) {
@@ -1343,6 +1364,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   ex.pre_v = -INFINITY, ex.pre_i = 0x7fffffff;
   if (nout == M && s_ov[M - 1] > 0.f) {
     // every pass-1 candidate is a real survivor, so the M-th of them bounds the result
+    // (also when a band overflowed: what it did collect is still real)
     ex.pre_v = s_ov[M - 1];
     ex.pre_i = s_oi[M - 1];
   }
@@ -1401,6 +1423,28 @@ __global__ void __launch_bounds__(256)
 }  // namespace pc
 
 using namespace pc;
+
+// Launch of the pair kernel as a programmatic dependent of mask_zero_rows_kernel (the
+// previous launch on the stream): its CTAs may become resident and run their prologue
+// while that grid drains; griddepcontrol.wait in the kernel orders the zrow reads.
+template <typename Kernel>
+static cudaError_t launch_pairs(Kernel kernel, unsigned grid, size_t dyn, cudaStream_t st,
+                                const BuArgs& args, const uint32_t* zrow) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)dyn);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kFastThreads);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args, zrow);
+}
 
 extern "C" int pc_bottomup_decode_stats(int64_t* exact_pass_planes, int reset) {
   unsigned long long v = 0ull;
@@ -1518,20 +1562,19 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
       PC_CUDA(cudaMallocAsync((void**)&zrow, sizeof(uint32_t) * (size_t)rows, st));
       mask_zero_rows_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(
           d_mask, zrow, p->h1, p->w1, p->mask_h, p->mask_w, a.msy, rows);
-      const size_t dyn = (size_t)kFastWarps * kStageWarp;
       const bool all = p->w1 == 256 && p->w0 == 128;
       const char* env_minb = getenv("PC_BU_MINB");  // experiment switch
-      const bool minb2 = !(env_minb && env_minb[0] == '3');
+      const bool minb2 = env_minb && env_minb[0] == '2';
 #define PC_BU_PAIRS(NMS_, ALL_)                                                              \
   do {                                                                                       \
     if (minb2) {                                                                             \
-      PC_CUDA(cudaFuncSetAttribute(bottomup_decode_pairs_kernel<NMS_, ALL_, 2>,              \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));  \
-      bottomup_decode_pairs_kernel<NMS_, ALL_, 2><<<grid, kFastThreads, dyn, st>>>(b, zrow); \
+      const size_t dyn = (size_t)kFastWarps * 3 * kPairSlot;                                 \
+      PC_CUDA(launch_pairs(bottomup_decode_pairs_kernel<NMS_, ALL_, 2>, grid, dyn, st, b,    \
+                           zrow));                                                           \
     } else {                                                                                 \
-      PC_CUDA(cudaFuncSetAttribute(bottomup_decode_pairs_kernel<NMS_, ALL_, 3>,              \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));  \
-      bottomup_decode_pairs_kernel<NMS_, ALL_, 3><<<grid, kFastThreads, dyn, st>>>(b, zrow); \
+      const size_t dyn = (size_t)kFastWarps * 2 * kPairSlot;                                 \
+      PC_CUDA(launch_pairs(bottomup_decode_pairs_kernel<NMS_, ALL_, 3>, grid, dyn, st, b,    \
+                           zrow));                                                           \
     }                                                                                        \
   } while (0)
       if (b.use_nms) {
