@@ -46,6 +46,7 @@ typedef enum pc_status {
 #define PC_MAX_DARK_KERNEL 17 /* kernel_size <= 17 (sigma = 3 recipe) */
 #define PC_MAX_GROUPS 128     /* people per image the grouping kernel can hold */
 #define PC_MAX_SCALES 4       /* heat-map resolutions of the bottom-up target encoder */
+#define PC_NMS_MAX_PEOPLE 1024 /* people per image pc_oks_nms can hold */
 
 /* ---- library ----------------------------------------------------------- */
 
@@ -250,6 +251,37 @@ typedef struct pc_refine_params {
 int pc_refine_missing(const float* d_heatmap, const float* d_tagging, float* d_ans,
                       const int32_t* d_num_groups, float* d_mean_tag,
                       const pc_refine_params* params, int64_t n, void* stream);
+
+/* ---- N4: OKS rescoring + oks_nms / soft_oks_nms -------------------------
+ * mindpose/engine/evaluator/topdown_evaluator.py:93-121 (rescoring loop, NMS call) and
+ * mindpose/utils/nms.py:7-190 (oks_iou, oks_nms, _rescore, soft_oks_nms), for every image
+ * of an evaluation in one launch.
+ * People are grouped by image: image i owns rows [d_image_offset[i], d_image_offset[i+1])
+ * of d_kpts f32 [P,K,3] (x, y, score), d_area f32 [P] and d_score f32 [P], already sorted
+ * and de-duplicated by bbox_id (_sort_and_unique_bboxes, host list handling).
+ * rescore != 0: d_score holds the box scores on entry and the rescored scores on return
+ * (mean of the joint scores > rescore_vis_thr, times the box score).
+ * -> d_keep i32 [P]: entries [offset[i], offset[i] + d_num_keep[i]) are the kept people of
+ * image i as indices LOCAL to the image, in keep order; the rest is -1.  d_num_keep i32 [I];
+ * -1 flags an image with more than max_people_per_image people.
+ * Equal scores: the reference's argsort is unstable; here (score desc, position desc),
+ * i.e. a stable ascending sort reversed. */
+typedef struct pc_oks_nms_params {
+  int32_t num_joints;
+  int32_t rescore;         /* apply the evaluator's rescoring first */
+  int32_t use_nms;         /* 0: keep everybody (evaluation config use_nms: False) */
+  int32_t soft;            /* 0: oks_nms, 1: soft_oks_nms (gaussian) */
+  int32_t max_dets;        /* soft_oks_nms max_dets (reference default 20) */
+  int32_t use_iou_vis_thr; /* oks_iou's vis_thr is not None */
+  float rescore_vis_thr;   /* evaluation config vis_thr */
+  float oks_thr;           /* evaluation config oks_thr */
+  float iou_vis_thr;       /* oks_iou vis_thr: joints of the DETECTION above it (nms.py:64) */
+  int32_t max_people_per_image; /* >= max_i(offset[i+1] - offset[i]); <= PC_NMS_MAX_PEOPLE */
+  double sigmas[PC_MAX_JOINTS];
+} pc_oks_nms_params;
+int pc_oks_nms(const float* d_kpts, const float* d_area, float* d_score,
+               const int32_t* d_image_offset, int32_t* d_keep, int32_t* d_num_keep,
+               const pc_oks_nms_params* params, int64_t num_images, void* stream);
 
 /* ---- host-buffer front end (what the e2e number is measured through) ----
  * Same decode as pc_topdown_decode but every pointer is a HOST pointer.  The

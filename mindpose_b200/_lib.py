@@ -23,6 +23,7 @@ from ctypes import (
 )
 
 PC_MAX_JOINTS = 64
+PC_NMS_MAX_PEOPLE = 1024
 PC_MAX_DARK_KERNEL = 17
 PC_MAX_GROUPS = 128
 PC_MAX_SCALES = 4
@@ -148,6 +149,22 @@ class RefineParams(Structure):
     _fields_ = [("num_joints", c_int32), ("height", c_int32), ("width", c_int32)]
 
 
+class OksNmsParams(Structure):
+    _fields_ = [
+        ("num_joints", c_int32),
+        ("rescore", c_int32),
+        ("use_nms", c_int32),
+        ("soft", c_int32),
+        ("max_dets", c_int32),
+        ("use_iou_vis_thr", c_int32),
+        ("rescore_vis_thr", c_float),
+        ("oks_thr", c_float),
+        ("iou_vis_thr", c_float),
+        ("max_people_per_image", c_int32),
+        ("sigmas", ctypes.c_double * PC_MAX_JOINTS),
+    ]
+
+
 class AffineHostParams(Structure):
     _fields_ = [
         ("src_h", c_int32),
@@ -191,6 +208,7 @@ SIGNATURES = {
         [_P, _P, _P, _P, _P, c_float, c_int32, c_int64, _P],
     ),
     "pc_refine_missing": (c_int, [_P, _P, _P, _P, _P, POINTER(RefineParams), c_int64, _P]),
+    "pc_oks_nms": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(OksNmsParams), c_int64, _P]),
     "pc_ctx_create": (c_int, [c_int, c_int64, POINTER(c_void_p)]),
     "pc_ctx_destroy": (c_int, [c_void_p]),
     "pc_topdown_affine_host": (

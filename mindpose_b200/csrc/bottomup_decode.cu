@@ -16,7 +16,6 @@
 // still produces many candidates is first cut down with the M-th largest
 // per-thread maximum, which is a valid lower bound for the M-th largest element.
 #include <math.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -1011,7 +1010,7 @@ __device__ __forceinline__ void mask_row_slow(const BuArgs& a, const uint8_t* __
 }
 
 // Per-band candidate buffer in shared memory (one per warp, count in a register).
-constexpr int kCandCap = 256;
+constexpr int kCandCap = 512;
 struct CandBuf {
   float* v;
   int* i;
@@ -1163,12 +1162,14 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
     }
     const unsigned any = (bal[0] | bal[1] | bal[2] | bal[3]) | (bal[4] | bal[5] | bal[6] | bal[7]);
     if (any == 0) return;
-    int total = 0;
+    if (cb.cnt > kCandCap - 256) {  // a row adds at most 256; heat maps collect ~150 per band
+      int total = 0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) total += __popc(bal[c]);
-    if (cb.cnt + total > kCandCap) {  // does not happen on heat maps (a band collects ~150)
-      cb.overflow = true;             // -> the plane goes to the exact pass
-      return;
+      for (int c = 0; c < 8; ++c) total += __popc(bal[c]);
+      if (cb.cnt + total > kCandCap) {
+        cb.overflow = true;  // -> the plane goes to the exact pass
+        return;
+      }
     }
     const int row_base = y * W + x0;
     int base = cb.cnt;
@@ -1563,20 +1564,9 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
       mask_zero_rows_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(
           d_mask, zrow, p->h1, p->w1, p->mask_h, p->mask_w, a.msy, rows);
       const bool all = p->w1 == 256 && p->w0 == 128;
-      const char* env_minb = getenv("PC_BU_MINB");  // experiment switch
-      const bool minb2 = env_minb && env_minb[0] == '2';
 #define PC_BU_PAIRS(NMS_, ALL_)                                                              \
-  do {                                                                                       \
-    if (minb2) {                                                                             \
-      const size_t dyn = (size_t)kFastWarps * 3 * kPairSlot;                                 \
-      PC_CUDA(launch_pairs(bottomup_decode_pairs_kernel<NMS_, ALL_, 2>, grid, dyn, st, b,    \
-                           zrow));                                                           \
-    } else {                                                                                 \
-      const size_t dyn = (size_t)kFastWarps * 2 * kPairSlot;                                 \
-      PC_CUDA(launch_pairs(bottomup_decode_pairs_kernel<NMS_, ALL_, 3>, grid, dyn, st, b,    \
-                           zrow));                                                           \
-    }                                                                                        \
-  } while (0)
+  PC_CUDA(launch_pairs(bottomup_decode_pairs_kernel<NMS_, ALL_, 3>, grid,                    \
+                       (size_t)kFastWarps * 2 * kPairSlot, st, b, zrow))
       if (b.use_nms) {
         if (all) PC_BU_PAIRS(true, true);
         else PC_BU_PAIRS(true, false);

@@ -23,6 +23,7 @@ SOURCES = [
     "bottomup_encode.cu",
     "grouping.cu",
     "refine_missing.cu",
+    "oks_nms.cu",
 ]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "posecodec.h")]
 
