@@ -203,7 +203,9 @@ typedef struct pc_bottomup_decode_params {
   int32_t mask_h, mask_w;
   int32_t use_nms, nms_kernel;
   int32_t max_num;          /* M <= 32 */
-  int32_t shift_coordinate; /* only 0 is supported (reference quirk A17) */
+  int32_t shift_coordinate; /* A17, reproduced with the reference's pairing: entry t of the
+                             * top M gets the +-0.25 offset of the t-th position in
+                             * row-major order (bottom_up_decoder.py:195-201) */
 } pc_bottomup_decode_params;
 int pc_bottomup_decode(const float* d_out0, const float* d_out1, const uint8_t* d_mask,
                        float* d_val_k, float* d_tag_k, float* d_ind_k, float* d_heatmap_raw,

@@ -1421,6 +1421,76 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- A17: _shift_coordinate (bottom_up_decoder.py:180-203), quirk included -----------
+// The reference takes sign(raw[y, x+1] - raw[y, x-1]) * 0.25 (and the same in y; zero on
+// the border rows / columns) at the top-M positions with masked_select, i.e. in ROW-MAJOR
+// order of the positions, and adds the resulting vector to the coordinates, which are in
+// RANK order: entry t of the top M receives the offset of the t-th position in spatial
+// order.  That pairing is what the reference computes, so it is what is reproduced.
+// raw is the aggregated, masked, pre-NMS map; its values are recomputed here for the four
+// neighbours of each position (same arithmetic as every decode kernel).
+__device__ __forceinline__ float bu_raw_at(const BuArgs& a, const float* __restrict__ heat_hi,
+                                           const float* __restrict__ heat_lo,
+                                           const uint8_t* __restrict__ mask, int y, int x) {
+  float v = __ldg(heat_hi + (size_t)y * a.w1 + x);
+  if (a.stages == 2) {
+    v = __fadd_rn(v, bilinear_legacy(heat_lo, a.h0, a.w0, a.sy, a.sx, y, x));
+    v = __fmul_rn(v, 0.5f);
+  }
+  const int my = min((int)floorf(__fmul_rn((float)y, a.msy)), a.mh - 1);
+  const int mx = min((int)floorf(__fmul_rn((float)x, a.msx)), a.mw - 1);
+  if (mask[(size_t)my * a.mw + mx] == 0) v = 0.f;
+  return v;
+}
+
+__device__ __forceinline__ float sign_of_diff(float hi, float lo) {
+  const float d = __fsub_rn(hi, lo);
+  return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+}
+
+__global__ void __launch_bounds__(128) bottomup_shift_kernel(const BuArgs a, int planes) {
+  __shared__ float s_ox[4][32], s_oy[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int plane = blockIdx.x * 4 + warp;
+  if (plane >= planes) return;
+  const int n = plane / a.K, k = plane - n * a.K;
+  const int H = a.h1, W = a.w1, M = a.M;
+  const float* heat_hi;
+  const float* heat_lo = nullptr;
+  if (a.stages == 2) {
+    heat_lo = a.out0 + ((size_t)n * 2 * a.K + k) * a.h0 * a.w0;
+    heat_hi = a.out1 + ((size_t)n * a.K + k) * H * W;
+  } else {
+    heat_hi = a.out0 + ((size_t)n * 2 * a.K + k) * H * W;
+  }
+  const uint8_t* mask = a.mask + (size_t)n * a.mh * a.mw;
+  float* ind = a.ind_k + (size_t)plane * M * 2;
+  int flat = 0x7fffffff;
+  float ox = 0.f, oy = 0.f;
+  if (lane < M) {
+    const int x = (int)ind[2 * lane], y = (int)ind[2 * lane + 1];
+    flat = y * W + x;
+    if (x >= 1 && x <= W - 2)
+      ox = sign_of_diff(bu_raw_at(a, heat_hi, heat_lo, mask, y, x + 1),
+                        bu_raw_at(a, heat_hi, heat_lo, mask, y, x - 1));
+    if (y >= 1 && y <= H - 2)
+      oy = sign_of_diff(bu_raw_at(a, heat_hi, heat_lo, mask, y + 1, x),
+                        bu_raw_at(a, heat_hi, heat_lo, mask, y - 1, x));
+  }
+  // spatial rank of this entry among the M positions (they are distinct)
+  int rank = 0;
+  for (int j = 0; j < M; ++j) rank += __shfl_sync(0xffffffffu, flat, j) < flat ? 1 : 0;
+  if (lane < M) {
+    s_ox[warp][rank] = ox;
+    s_oy[warp][rank] = oy;
+  }
+  __syncwarp();
+  if (lane < M) {
+    ind[2 * lane] = __fadd_rn(ind[2 * lane], __fmul_rn(s_ox[warp][lane], 0.25f));
+    ind[2 * lane + 1] = __fadd_rn(ind[2 * lane + 1], __fmul_rn(s_oy[warp][lane], 0.25f));
+  }
+}
+
 }  // namespace pc
 
 using namespace pc;
@@ -1481,9 +1551,6 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
   PC_REQUIRE(!p->use_nms || (p->nms_kernel >= 1 && p->nms_kernel <= kBuMaxNms),
              PC_ERR_UNSUPPORTED, "pc_bottomup_decode: nms_kernel %d outside [1, %d]",
              p->nms_kernel, kBuMaxNms);
-  PC_REQUIRE(!p->shift_coordinate, PC_ERR_UNSUPPORTED,
-             "pc_bottomup_decode: shift_coordinate=True is not supported (the reference pairs "
-             "its offsets with the wrong candidates, bottom_up_decoder.py:195-201)");
   PC_REQUIRE((uint64_t)p->h1 * p->w1 * p->w1 < 0xffffffffull, PC_ERR_UNSUPPORTED,
              "pc_bottomup_decode: map too large");
   if (n == 0) return PC_OK;
@@ -1595,6 +1662,10 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
           p->w1, two ? a.sy : 1.f, two ? a.sx : 1.f, a.div_w1, quads);
       PC_CUDA(cudaGetLastError());
     }
+    if (p->shift_coordinate) {
+      bottomup_shift_kernel<<<(grid + 3) / 4, 128, 0, st>>>(a, (int)grid);
+      PC_CUDA(cudaGetLastError());
+    }
     return PC_OK;
   }
 
@@ -1604,5 +1675,9 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   bottomup_decode_kernel<<<grid, kBuThreads, smem, st>>>(a);
   PC_CUDA(cudaGetLastError());
+  if (p->shift_coordinate) {
+    bottomup_shift_kernel<<<(grid + 3) / 4, 128, 0, st>>>(a, (int)grid);
+    PC_CUDA(cudaGetLastError());
+  }
   return PC_OK;
 }

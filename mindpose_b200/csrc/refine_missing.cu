@@ -64,8 +64,10 @@ __device__ __forceinline__ void score_px(float heat, float tag, int idx, const f
                                          float (&bv)[kRefChunk], int (&bi)[kRefChunk]) {
 #pragma unroll
   for (int c = 0; c < kRefChunk; ++c) {
-    const float d = __fsub_rn(tag, mt[c]);
-    const float nd = __fsqrt_rn(__fmul_rn(d, d));  // np.linalg.norm over one tag channel
+    // np.linalg.norm over one tag channel is sqrt(d * d), which in binary floating point
+    // equals |d| exactly unless d * d over- or underflows (|d| > 1.8e19: the reference gets
+    // inf there; |d| < 1e-19 rounds to 0 either way)
+    const float nd = fabsf(__fsub_rn(tag, mt[c]));
     const float s = __fsub_rn(heat, rintf(nd));    // np.round: half to even
     if (s > bv[c]) {
       bv[c] = s;

@@ -171,12 +171,36 @@ def test_decode_full_size_properties(cuda_device):
         assert np.array_equal(gt[sel].cpu().numpy(), w)
 
 
-def test_decode_rejects_unsupported(cuda_device):
-    dec = mp.create_decoder("bottomup_heatmap_ae", shift_coordinate=True)
-    z0 = torch.zeros(1, 34, 16, 16, device=cuda_device)
-    z1 = torch.zeros(1, 17, 32, 32, device=cuda_device)
-    with pytest.raises(ValueError, match="shift_coordinate"):
-        dec([z0, z1], torch.ones(1, 64, 64, dtype=torch.uint8, device=cuda_device))
+@pytest.mark.parametrize("h0,w0,mask_hw,stages", [
+    (32, 32, (128, 128), 2),       # C = 4 fast kernel
+    (128, 128, (512, 512), 2),     # pair kernel
+    (20, 21, (80, 84), 2),         # generic kernel (W = 42)
+    (64, 64, (128, 128), 1)])
+def test_decode_shift_coordinate_matches_oracle(cuda_device, h0, w0, mask_hw, stages):
+    """A17 with the reference's own pairing of offsets and candidates (oracle:
+    shift_coordinate_quirk)."""
+    n = 2
+    if stages == 2:
+        d = synth.bottomup_outputs(n, 17, h0, w0, mask_hw=mask_hw, seed=7 + h0, max_people=5)
+        outs = [d["out0"], d["out1"]]
+        mask = d["mask"]
+        kw = {}
+        okw = {}
+    else:
+        rng = np.random.RandomState(1)
+        outs = [rng.uniform(-0.2, 1, (n, 34, h0, w0)).astype(np.float32)]
+        mask = (rng.random_sample((n,) + mask_hw) > 0.1).astype(np.uint8)
+        kw = dict(num_stages=1, with_ae_loss=[True])
+        okw = dict(num_stages=1, with_ae_loss=(True,))
+    want = bd.decode(outs, mask, use_nms=True, nms_kernel=3, max_num=30, shift_coordinate=True,
+                     **okw)
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3, max_num=30,
+                            shift_coordinate=True, **kw)
+    got = dec([_t(o, cuda_device) for o in outs], _t(mask, cuda_device))
+    for name, g, w in zip(["val_k", "tag_k", "ind_k"], got, want):
+        assert np.array_equal(g.cpu().numpy(), w), name
+    plain = bd.decode(outs, mask, use_nms=True, nms_kernel=3, max_num=30, **okw)
+    assert not np.array_equal(plain[2], want[2])      # the shift did something
 
 
 # ------------------------------------------------------------------- grouping
