@@ -31,6 +31,7 @@ struct BueArgs {
   float two_sigma2;
   int32_t tag_per_joint;
   int32_t vec_ok;
+  int32_t bands;      // CTAs per plane: each fills and pastes hmax / bands rows
 };
 
 struct Window {
@@ -85,10 +86,16 @@ __global__ void __launch_bounds__(kBueThreads) bottomup_encode_kernel(const BueA
   __shared__ int s_valid[kBueMaxPeople];  // people with something to paste, any order
   __shared__ int s_nvalid;
 
+  // A plane is cut into `bands` row bands, one CTA each: many short CTAs whose load / fill /
+  // paste phases interleave across the SM instead of a few long ones in lockstep.
   const int tid = threadIdx.x;
-  const int k = blockIdx.x % a.K;
-  const int s = (blockIdx.x / a.K) % a.S;
-  const int64_t n = blockIdx.x / (a.K * a.S);
+  const int band = blockIdx.x % a.bands;
+  const int plane_id = blockIdx.x / a.bands;
+  const int k = plane_id % a.K;
+  const int s = (plane_id / a.K) % a.S;
+  const int64_t n = plane_id / (a.K * a.S);
+  const int band_rows = a.hmax / a.bands;
+  const int y_band0 = band * band_rows, y_band1 = y_band0 + band_rows;
   const int W = a.w[s], H = a.h[s];
 
   if (tid == 0) s_nvalid = 0;
@@ -102,12 +109,13 @@ __global__ void __launch_bounds__(kBueThreads) bottomup_encode_kernel(const BueA
 
   // ---- the write pass: zeros over the whole padded plane ------------------------------
   float* plane = a.target + (((size_t)n * a.S + s) * a.K + k) * a.hmax * a.wmax;
-  const int total = a.hmax * a.wmax;
+  float* band_base = plane + (size_t)y_band0 * a.wmax;
+  const int total = band_rows * a.wmax;
   if (a.vec_ok) {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < (total >> 2); i += kBueThreads) st_stream_f4(plane + 4 * i, z);
+    for (int i = tid; i < (total >> 2); i += kBueThreads) st_stream_f4(band_base + 4 * i, z);
   } else {
-    for (int i = tid; i < total; i += kBueThreads) plane[i] = 0.f;
+    for (int i = tid; i < total; i += kBueThreads) band_base[i] = 0.f;
   }
   __syncthreads();  // windows are visible; the zero stores are ordered before the paste
 
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(kBueThreads) bottomup_encode_kernel(const BueA
     const Window wd = s_win[s_valid[vi]];
     const int y = wd.ul_y + e / a.size, x = wd.ul_x + e % a.size;
     if (x < wd.x_lo || x >= wd.x_hi || y < wd.y_lo || y >= wd.y_hi) continue;
+    if (y < y_band0 || y >= y_band1) continue;  // another band's rows
     float v = window_value(wd, x, y, a.two_sigma2);
     for (int o = 0; o < nv; ++o) {
       if (o == vi) continue;
@@ -129,7 +138,8 @@ __global__ void __launch_bounds__(kBueThreads) bottomup_encode_kernel(const BueA
     plane[y * a.wmax + x] = v;
   }
 
-  // ---- tag_ind ------------------------------------------------------------------------
+  // ---- tag_ind (first band only) ---------------------------------------------------------
+  if (band != 0) return;
   if (a.tag_per_joint) {
     if (tid < a.max_num) {
       int2 r = make_int2(0, 0);
@@ -216,8 +226,11 @@ extern "C" int pc_bottomup_encode(const float* d_keypoints, float* d_target, int
   a.c0 = (float)(a.size / 2);
   a.two_sigma2 = (float)(2.0 * (double)p->sigma * (double)p->sigma);
   a.tag_per_joint = p->tag_per_joint;
-  a.vec_ok = ((int64_t)hmax * wmax) % 4 == 0 && ((uintptr_t)d_target % 16 == 0);
-  bottomup_encode_kernel<<<(unsigned)grid, kBueThreads, 0, (cudaStream_t)stream>>>(a);
+  a.bands = (hmax % 4 == 0 && hmax >= 64) ? 4 : 1;
+  a.vec_ok = ((int64_t)(hmax / a.bands) * wmax) % 4 == 0 && ((uintptr_t)d_target % 16 == 0);
+  PC_REQUIRE(grid * a.bands < 0x7fffffffLL, PC_ERR_UNSUPPORTED,
+             "pc_bottomup_encode: batch too large");
+  bottomup_encode_kernel<<<(unsigned)(grid * a.bands), kBueThreads, 0, (cudaStream_t)stream>>>(a);
   PC_CUDA(cudaGetLastError());
   return PC_OK;
 }

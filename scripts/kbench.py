@@ -42,7 +42,7 @@ def timeit(fn, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--only", default="decode,encode,warp,bottomup,group,bu_encode,refine")
+    ap.add_argument("--only", default="decode,encode,warp,bottomup,group,bu_encode,refine,nms")
     ap.add_argument("--json", default="")
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -170,6 +170,34 @@ def main():
         med, mn = timeit(fn, args.iters)
         report("refine_missing 64 images x 8 people (maps read once)", n, "images",
                2 * k * h * w * 4, med, mn)
+    if "nms" in only:
+        from mindpose_b200 import nms as dnms
+        images, people = 512, 40
+        ks, ars, scs = [], [], []
+        for i in range(8):                      # 8 distinct images, tiled
+            rng = np.random.RandomState(900 + i)
+            base = rng.randint(0, 10, people)   # 10 poses, each with jittered near-duplicates
+            centers, sizes = rng.uniform(50, 400, (10, 2)), rng.uniform(40, 160, 10)
+            shapes = rng.uniform(-0.5, 0.5, (10, 17, 2))
+            kk = np.zeros((people, 17, 3), np.float32)
+            jit = rng.choice([0.01, 0.03, 0.08, 0.2], people)[:, None, None] * sizes[base][:, None, None]
+            kk[..., :2] = centers[base][:, None] + shapes[base] * sizes[base][:, None, None] + \
+                rng.normal(0, 1, (people, 17, 2)) * jit
+            kk[..., 2] = rng.uniform(0, 1, (people, 17))
+            ks.append(kk)
+            ars.append((sizes[base] ** 2 * rng.uniform(0.8, 1.2, people)).astype(np.float32))
+            scs.append(rng.uniform(0.05, 1.0, people).astype(np.float32))
+        reps = images // 8
+        kp = torch.from_numpy(np.concatenate(ks * reps)).to(dev)
+        ar = torch.from_numpy(np.concatenate(ars * reps)).to(dev)
+        sc0 = torch.from_numpy(np.concatenate(scs * reps)).to(dev)
+        off = torch.arange(images + 1, dtype=torch.int32, device=dev) * people
+        for soft in (False, True):
+            fn = lambda: dnms.rescore_and_nms(kp, ar, sc0.clone(), off, people, oks_thr=0.9,  # noqa: E731
+                                              rescore_vis_thr=0.2, soft=soft)
+            med, mn = timeit(fn, args.iters)
+            report(f"oks {'soft ' if soft else ''}nms {images} images x {people} people (latency bound)",
+                   images, "images", people * (17 * 12 + 8), med, mn)
     if "bu_encode" in only:
         n, m = 64, 30
         sizes = [[128, 128], [256, 256]]
