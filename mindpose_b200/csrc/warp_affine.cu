@@ -370,8 +370,8 @@ __device__ __forceinline__ RowCtx make_row(int Y, int hs, int ws, uint32_t ws3, 
 // One output pixel (3 channels packed r | g << 8 | b << 16) at fixed-point source X in
 // the row pair rc.  OpenCV's sum of four 15-bit weighted taps equals, exactly (integer
 // arithmetic), a horizontal blend with weights (32-fx, fx) followed by a vertical blend
-// with (32-fy, fy); the horizontal blends are byte dot products (dp4a) taken straight
-// from the realigned words, with zero weights on the bytes of the other channels.
+// with (32-fy, fy); the horizontal blends are two-way dot products (dp2a) of the weight
+// pair with the channel's two bytes, paired up by a byte permute of the realigned words.
 __device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
                                                 const uint8_t* __restrict__ base4, int hs,
                                                 int ws, uint32_t ws3, int X, const RowCtx rc) {
@@ -381,22 +381,20 @@ __device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
     const uint32_t off = rc.off + (uint32_t)sx * 3u;
     const Six a = load_six(base4, off);
     const Six b = load_six(base4, off + ws3);
-    const uint32_t gx = 32u - (uint32_t)fx, ux = (uint32_t)fx;
-    const uint32_t k0 = gx | (ux << 24);  // channel 0: bytes 0 and 3 of lo
-    const uint32_t k1l = gx << 8;         // channel 1: byte 1 of lo, byte 0 of hi
-    const uint32_t k2l = gx << 16;        // channel 2: byte 2 of lo, byte 1 of hi
-    const uint32_t k2h = ux << 8;
-    const uint32_t a0 = __dp4a(a.lo, k0, 0u);
-    const uint32_t a1 = __dp4a(a.hi, ux, __dp4a(a.lo, k1l, 0u));
-    const uint32_t a2 = __dp4a(a.hi, k2h, __dp4a(a.lo, k2l, 0u));
-    const uint32_t b0 = __dp4a(b.lo, k0, 0u);
-    const uint32_t b1 = __dp4a(b.hi, ux, __dp4a(b.lo, k1l, 0u));
-    const uint32_t b2 = __dp4a(b.hi, k2h, __dp4a(b.lo, k2l, 0u));
+    // lo = r0 g0 b0 r1, hi = g1 b1 . . : pair the bytes of each channel (byte permute) and
+    // take the 16-bit x 8-bit dot products with the weight pair (32 - fx, fx)
+    const uint32_t wg = (32u - (uint32_t)fx) | ((uint32_t)fx << 16);
+    const uint32_t arg = __byte_perm(a.lo, a.hi, 0x4130), abb = __byte_perm(a.lo, a.hi, 0x0052);
+    const uint32_t brg = __byte_perm(b.lo, b.hi, 0x4130), bbb = __byte_perm(b.lo, b.hi, 0x0052);
+    const uint32_t a0 = __dp2a_lo(wg, arg, 0u), a1 = __dp2a_hi(wg, arg, 0u);
+    const uint32_t a2 = __dp2a_lo(wg, abb, 0u);
+    const uint32_t b0 = __dp2a_lo(wg, brg, 0u), b1 = __dp2a_hi(wg, brg, 0u);
+    const uint32_t b2 = __dp2a_lo(wg, bbb, 0u);
     const uint32_t gy = 32u - (uint32_t)fy, uy = (uint32_t)fy;
     const uint32_t c0 = (gy * a0 + uy * b0 + 512u) >> 10;
     const uint32_t c1 = (gy * a1 + uy * b1 + 512u) >> 10;
     const uint32_t c2 = (gy * a2 + uy * b2 + 512u) >> 10;
-    return c0 | (c1 << 8) | (c2 << 16);
+    return __byte_perm(__byte_perm(c0, c1, 0x0040), c2, 0x5410);  // byte 3 = high byte of c2 = 0
   }
   if (sx >= ws || sx + 1 < 0 || sy >= hs || sy + 1 < 0) return 0u;
   const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy);
