@@ -269,6 +269,9 @@ def run_ours(args, wl):
     stream = torch.cuda.current_stream()
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     marks = []
+    gatherer = None
+    if world > 1 and not args.nccl_gather:
+        gatherer = pdist.make_gatherer(n, k, dev)
 
     def step(record):
         if record:
@@ -284,7 +287,10 @@ def run_ours(args, wl):
             e2.record(stream)
             marks.append((e0, e1, e2))
         if world > 1:
-            pdist.all_gather_keypoints(preds, bxs, world * n)
+            if gatherer is not None:     # one kernel of peer stores + a barrier
+                gatherer.gather(preds, bxs)
+            else:                        # NCCL all-gather
+                pdist.all_gather_keypoints(preds, bxs, world * n)
         return preds, bxs
 
     def fence():
@@ -400,7 +406,10 @@ def run_ours(args, wl):
             "roofline_other": other,
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "gpu_launches": 4 * args.steps,
+            "gpu_launches": (4 + (1 if gatherer is not None else 0)) * args.steps,
+            "gather": (None if world == 1 else
+                       ("peer stores, multicast" if gatherer is not None and gatherer.multicast
+                        else "peer stores" if gatherer is not None else "nccl all_gather")),
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
@@ -419,6 +428,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="N > 1: use the NCCL all-gather instead of the peer-memory stores")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -285,6 +285,20 @@ int pc_oks_nms(const float* d_kpts, const float* d_area, float* d_score,
                const int32_t* d_image_offset, int32_t* d_keep, int32_t* d_num_keep,
                const pc_oks_nms_params* params, int64_t num_images, void* stream);
 
+/* ---- E: all-gather of the decoded keypoints over peer memory --------------
+ * Not in the reference (it evaluates on rank 0, mindpose/callbacks/eval_callback.py:
+ * 142-145); SURVEY.md section 8(e).  Packs this rank's d_preds f32 [n,K,3] + d_boxes f32
+ * [n,6] into rows [row_offset, row_offset + n) of the gathered table f32 [total, K*3+6] OF
+ * EVERY RANK in one kernel: through d_multicast_table, the NVSwitch multicast mapping of
+ * the table (one multimem.st reaches all replicas), or, when that is NULL, through
+ * h_peer_tables, a HOST array of num_peers device pointers -- the peer-mapped address of
+ * the table on each rank, this rank's own included.  The tables are symmetric-memory
+ * allocations owned by the caller, who orders the ranks with a barrier afterwards
+ * (mindpose_b200/dist.py::PeerGather). */
+int pc_scatter_results(const float* d_preds, const float* d_boxes, void* const* h_peer_tables,
+                       int32_t num_peers, void* d_multicast_table, int64_t row_offset,
+                       int32_t num_joints, int64_t n, void* stream);
+
 /* ---- host-buffer front end (what the e2e number is measured through) ----
  * Same decode as pc_topdown_decode but every pointer is a HOST pointer.  The
  * context owns device scratch and two streams; crops are streamed through in

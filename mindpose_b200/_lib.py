@@ -209,6 +209,8 @@ SIGNATURES = {
     ),
     "pc_refine_missing": (c_int, [_P, _P, _P, _P, _P, POINTER(RefineParams), c_int64, _P]),
     "pc_oks_nms": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(OksNmsParams), c_int64, _P]),
+    "pc_scatter_results": (
+        c_int, [_P, _P, POINTER(c_void_p), c_int32, _P, c_int64, c_int32, c_int64, _P]),
     "pc_ctx_create": (c_int, [c_int, c_int64, POINTER(c_void_p)]),
     "pc_ctx_destroy": (c_int, [c_void_p]),
     "pc_topdown_affine_host": (

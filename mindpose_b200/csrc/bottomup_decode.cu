@@ -1495,6 +1495,23 @@ __global__ void __launch_bounds__(128) bottomup_shift_kernel(const BuArgs a, int
 
 using namespace pc;
 
+// The row-flag scratch comes from the device's default stream-ordered pool.  By default the
+// pool hands freed memory back to the driver at every synchronisation, which would turn
+// each call into a driver allocation; keep it (once per device).
+static cudaError_t keep_pool_memory() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return e;
+  cudaMemPool_t pool;
+  e = cudaDeviceGetDefaultMemPool(&pool, dev);
+  if (e != cudaSuccess) return e;
+  uint64_t keep = UINT64_MAX;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  done[dev] = e == cudaSuccess;
+  return e;
+}
+
 // Launch of the pair kernel as a programmatic dependent of mask_zero_rows_kernel (the
 // previous launch on the stream): its CTAs may become resident and run their prologue
 // while that grid drains; griddepcontrol.wait in the kernel orders the zrow reads.
@@ -1627,6 +1644,7 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
       // one word per (image, output row): which lanes see a masked pixel (stream-ordered scratch)
       uint32_t* zrow = nullptr;
       const int64_t rows = n * p->h1;
+      PC_CUDA(keep_pool_memory());
       PC_CUDA(cudaMallocAsync((void**)&zrow, sizeof(uint32_t) * (size_t)rows, st));
       mask_zero_rows_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(
           d_mask, zrow, p->h1, p->w1, p->mask_h, p->mask_w, a.msy, rows);

@@ -24,6 +24,7 @@ SOURCES = [
     "grouping.cu",
     "refine_missing.cu",
     "oks_nms.cu",
+    "peer_gather.cu",
 ]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "posecodec.h")]
 

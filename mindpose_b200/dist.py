@@ -40,11 +40,37 @@ def unpack_results(packed: torch.Tensor, num_joints: int):
             packed[:, num_joints * 3:].reshape(n, 6))
 
 
+class PendingGather:
+    """Handle of an all-gather in flight (``all_gather_keypoints(..., async_op=True)``): the
+    collective runs on the backend's own stream while the caller's stream goes on with the
+    next batch; ``wait()`` orders the caller's stream after it and returns the results."""
+
+    def __init__(self, work, out, sizes, longest, num_joints):
+        self._work, self._out, self._sizes = work, out, sizes
+        self._longest, self._k = longest, num_joints
+
+    def wait(self):
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        sizes, longest, out = self._sizes, self._longest, self._out
+        if all(s == longest for s in sizes):
+            packed = out
+        else:
+            packed = torch.cat([out[r * longest: r * longest + sizes[r]]
+                                for r in range(len(sizes))], dim=0)
+        return unpack_results(packed, self._k)
+
+
 def all_gather_keypoints(preds: torch.Tensor, boxes: torch.Tensor, total: int,
-                         group: Optional[dist.ProcessGroup] = None):
+                         group: Optional[dist.ProcessGroup] = None, async_op: bool = False):
     """Every rank passes the results of its `shard_range` block; every rank gets
-    (all_preds [total,K,3], all_boxes [total,6]) in global crop order."""
+    (all_preds [total,K,3], all_boxes [total,6]) in global crop order -- or, with
+    ``async_op=True``, a `PendingGather` whose ``wait()`` returns them."""
     if not dist.is_available() or not dist.is_initialized():
+        if async_op:
+            n = preds.shape[0]
+            return PendingGather(None, pack_results(preds, boxes), [n], n, preds.shape[1])
         return preds, boxes
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -59,14 +85,85 @@ def all_gather_keypoints(preds: torch.Tensor, boxes: torch.Tensor, total: int,
         pad = torch.zeros((longest - local.shape[0], width), dtype=local.dtype, device=local.device)
         local = torch.cat([local, pad], dim=0)
     out = torch.empty((world * longest, width), dtype=local.dtype, device=local.device)
+    work = None
     try:
-        dist.all_gather_into_tensor(out, local, group=group)
+        work = dist.all_gather_into_tensor(out, local, group=group, async_op=async_op)
     except (RuntimeError, NotImplementedError):  # backend without the flat variant
         parts = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(parts, local, group=group)
         out = torch.cat(parts, dim=0)
-    if all(s == longest for s in sizes):
-        packed = out
-    else:
-        packed = torch.cat([out[r * longest: r * longest + sizes[r]] for r in range(world)], dim=0)
-    return unpack_results(packed, k)
+        work = None
+    pending = PendingGather(work if async_op else None, out, sizes, longest, k)
+    return pending if async_op else pending.wait()
+
+
+class PeerGather:
+    """The keypoint all-gather as ONE kernel of direct stores into peer memory
+    (``pc_scatter_results``) plus a barrier, instead of an NCCL collective: every rank's
+    gathered table is a symmetric-memory allocation, and each rank writes its block of rows
+    into all of them -- through the NVSwitch multicast mapping when the allocation has one,
+    else through the peer-mapped addresses over NVLink.
+
+    Two tables alternate, so a rank that is one step ahead never overwrites rows a peer may
+    still be reading (the barrier keeps ranks within one step of each other).  ``gather``
+    returns views of this rank's own table; they stay valid until the step after next.
+    """
+
+    def __init__(self, rows_per_rank: int, num_joints: int, device: torch.device,
+                 group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+
+        self._lib, self._ctypes = _lib, ctypes
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows, self.k = int(rows_per_rank), int(num_joints)
+        self.width = self.k * 3 + 6
+        grp = group if group is not None else dist.group.WORLD
+        self.tables, self.handles, self._peers, self._mc = [], [], [], []
+        for _ in range(2):
+            t = symm_mem.empty((self.world * self.rows, self.width), dtype=torch.float32,
+                               device=device)
+            h = symm_mem.rendezvous(t, group=grp)
+            self.tables.append(t)
+            self.handles.append(h)
+            ptrs = [int(p) for p in h.buffer_ptrs]
+            self._peers.append((ctypes.c_void_p * self.world)(*ptrs))
+            mc = int(getattr(h, "multicast_ptr", 0) or 0)
+            self._mc.append(mc)
+        self.multicast = all(m != 0 for m in self._mc)
+        self._turn = 0
+
+    def gather(self, preds: torch.Tensor, boxes: torch.Tensor):
+        """preds f32 [rows,K,3], boxes f32 [rows,6] of this rank -> (all_preds
+        [world*rows,K,3], all_boxes [world*rows,6]) once every rank's rows have landed."""
+        if preds.shape[0] != self.rows or boxes.shape[0] != self.rows:
+            raise ValueError(f"expected {self.rows} rows per rank, got {preds.shape[0]}")
+        if not (preds.is_cuda and preds.is_contiguous() and boxes.is_contiguous()):
+            raise ValueError("preds / boxes must be contiguous CUDA tensors")
+        i = self._turn
+        self._turn ^= 1
+        lib = self._lib
+        lib.call("pc_scatter_results", lib.device_ptr(preds), lib.device_ptr(boxes),
+                 self._peers[i], self.world, self._mc[i] if self.multicast else None,
+                 self.rank * self.rows, self.k, self.rows, lib.current_stream())
+        self.handles[i].barrier(channel=0)
+        return unpack_results(self.tables[i], self.k)
+
+
+def make_gatherer(rows_per_rank: int, num_joints: int, device: torch.device,
+                  group: Optional[dist.ProcessGroup] = None):
+    """``PeerGather`` when symmetric memory works on this box, else None (callers fall back
+    to ``all_gather_keypoints``, the NCCL collective)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+        return None
+    try:
+        return PeerGather(rows_per_rank, num_joints, device, group)
+    except Exception as e:  # no P2P / VMM support, old driver, ...
+        import warnings
+
+        warnings.warn(f"peer-memory gather unavailable ({type(e).__name__}: {e}); using NCCL")
+        return None

@@ -39,16 +39,26 @@ def _worker(rank, world, port, total, k, out_dir):
         # results that encode the global crop index, so order is checkable
         preds = idx[:, None, None] * 10 + torch.arange(k * 3, dtype=torch.float32).reshape(1, k, 3)
         boxes = idx[:, None] * 100 + torch.arange(6, dtype=torch.float32)[None]
-        all_p, all_b = pdist.all_gather_keypoints(preds, boxes, total)
+        if os.environ.get("PC_TEST_ASYNC_GATHER") == "1":
+            handles = [pdist.all_gather_keypoints(preds + j, boxes, total, async_op=True)
+                       for j in range(3)]          # several gathers in flight
+            outs = [h.wait() for h in handles]
+            for j, (p_j, _) in enumerate(outs):
+                assert torch.equal(p_j - j, outs[0][0])
+            all_p, all_b = outs[0]
+        else:
+            all_p, all_b = pdist.all_gather_keypoints(preds, boxes, total)
         np.save(os.path.join(out_dir, f"p{rank}.npy"), all_p.numpy())
         np.save(os.path.join(out_dir, f"b{rank}.npy"), all_b.numpy())
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,total", [(2, 64), (2, 33), (3, 10)])
-def test_all_gather_keypoints_gloo(tmp_path, world, total):
+@pytest.mark.parametrize("world,total,async_op", [(2, 64, False), (2, 33, False), (3, 10, False),
+                                                   (2, 33, True)])
+def test_all_gather_keypoints_gloo(tmp_path, monkeypatch, world, total, async_op):
     k = 17
+    monkeypatch.setenv("PC_TEST_ASYNC_GATHER", "1" if async_op else "0")
     port = _free_port()
     mp.spawn(_worker, args=(world, port, total, k, str(tmp_path)), nprocs=world, join=True)
     idx = np.arange(total, dtype=np.float32)

@@ -1,0 +1,56 @@
+"""Peer-memory keypoint gather (pc_scatter_results + symmetric memory) on 2 GPUs against
+the NCCL all-gather.  Skipped on boxes with one GPU."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, rows, k, out_dir):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from mindpose_b200 import dist as pdist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        g = pdist.PeerGather(rows, k, dev)
+        for step in range(3):       # both tables, reuse of the first
+            idx = torch.arange(rank * rows, (rank + 1) * rows, dtype=torch.float32, device=dev)
+            preds = (idx[:, None, None] * 10 + step +
+                     torch.arange(k * 3, dtype=torch.float32, device=dev).reshape(1, k, 3))
+            boxes = idx[:, None] * 100 + torch.arange(6, dtype=torch.float32, device=dev)[None]
+            got_p, got_b = g.gather(preds.contiguous(), boxes.contiguous())
+            want_p, want_b = pdist.all_gather_keypoints(preds, boxes, world * rows)
+            torch.cuda.synchronize()
+            assert torch.equal(got_p, want_p) and torch.equal(got_b, want_b), (rank, step)
+        np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(g.multicast)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_gather_matches_nccl_all_gather(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    world, rows, k = 2, 257, 17
+    mp.spawn(_worker, args=(world, _free_port(), rows, k, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert os.path.exists(tmp_path / f"ok{r}.npy")
