@@ -1009,8 +1009,14 @@ __device__ __forceinline__ void mask_row_slow(const BuArgs& a, const uint8_t* __
   }
 }
 
+// Warps (= row bands) per CTA of the pair kernel.  6 x 32 threads at 80 registers fit four
+// CTAs per SM: 1088 planes are then 1.84 waves of CTAs instead of 2.45, which leaves the SMs
+// less idle at the end of the grid.
+constexpr int kPairWarps = 6;
+constexpr int kPairThreads = kPairWarps * 32;
+
 // Per-band candidate buffer in shared memory (one per warp, count in a register).
-constexpr int kCandCap = 512;
+constexpr int kCandCap = 384;
 struct CandBuf {
   float* v;
   int* i;
@@ -1049,7 +1055,7 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
   const bool last_lane = ALL ? lane == 31 : x0 + 8 >= W;
   const int pb = rb >> 1, pe = re >> 1;
   const int p_end = re < H ? pe : pe - 1;
-  const int kth_rank = (M + kFastWarps - 1) / kFastWarps;
+  const int kth_rank = (M + kPairWarps - 1) / kPairWarps;
   const unsigned lt_mask = (1u << lane) - 1u;
   constexpr int kPairWarp = kPairDepth * kPairSlot;
   unsigned char* slot0 = ring + lane * 16;
@@ -1134,7 +1140,7 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
     if (lane == 0) s_kth[warp_id] = mx > 0 ? __int_as_float(mx) : -INFINITY;
     __syncwarp();
     // slots hold -inf or a positive float: signed integer order == float order
-    int o = lane < kFastWarps ? __float_as_int(s_kth[lane]) : 0x7f800000;
+    int o = lane < kPairWarps ? __float_as_int(s_kth[lane]) : 0x7f800000;
     o = __reduce_min_sync(0xffffffffu, o);
     t_lb = fmaxf(t_lb, __int_as_float(o));
   };
@@ -1255,25 +1261,25 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-constexpr int kPairBuf = kFastWarps * kCandCap;
+constexpr int kPairBuf = kPairWarps * kCandCap;
 
 template <bool NMS, bool ALL, int MINB>
-__global__ void __launch_bounds__(kFastThreads, MINB)
+__global__ void __launch_bounds__(kPairThreads, MINB)
     bottomup_decode_pairs_kernel(const BuArgs a, const uint32_t* __restrict__ zrow_all) {
-  __shared__ float s_lv[kFastWarps][32];
-  __shared__ int s_li[kFastWarps][32];
-  __shared__ int s_cnt[kFastWarps];
-  __shared__ float s_cv[kFastWarps][kCandCap];
-  __shared__ int s_ci[kFastWarps][kCandCap];
+  __shared__ float s_lv[kPairWarps][32];
+  __shared__ int s_li[kPairWarps][32];
+  __shared__ int s_cnt[kPairWarps];
+  __shared__ float s_cv[kPairWarps][kCandCap];
+  __shared__ int s_ci[kPairWarps][kCandCap];
   __shared__ float s_ov[32];
   __shared__ int s_oi[32];
   __shared__ int s_nbuf, s_nout;
-  __shared__ float s_kth[kFastWarps];
+  __shared__ float s_kth[kPairWarps];
   // pairs in flight per warp: 3 CTAs per SM only fit with a two-deep ring
   constexpr int kPairDepth = MINB >= 3 ? 2 : 3;
   constexpr int kPairWarp = kPairDepth * kPairSlot;
-  extern __shared__ __align__(16) unsigned char s_ring[];  // kFastWarps * kPairWarp
-  static_assert(kPairBuf * 8 <= kFastWarps * kPairWarp, "merge buffer must fit the ring");
+  extern __shared__ __align__(16) unsigned char s_ring[];  // kPairWarps * kPairWarp
+  static_assert(kPairBuf * 8 <= kPairWarps * kPairWarp, "merge buffer must fit the ring");
   // merge buffer: reuses the staging ring once every band is done with it
   float* s_bv = reinterpret_cast<float*>(s_ring);
   int* s_bi = reinterpret_cast<int*>(s_ring) + kPairBuf;
@@ -1291,11 +1297,11 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   float* raw_out = a.heatmap_raw ? a.heatmap_raw + ((size_t)n * a.K + k) * H * W : nullptr;
 
   // even number of rows per band
-  const int R = (((H + kFastWarps - 1) / kFastWarps) + 1) & ~1;
+  const int R = (((H + kPairWarps - 1) / kPairWarps) + 1) & ~1;
   const int rb = min(H, warp * R), re = min(H, rb + R);
 
   if (tid == 0) s_nbuf = 0, s_nout = 0;
-  if (tid < kFastWarps) s_kth[tid] = -INFINITY;
+  if (tid < kPairWarps) s_kth[tid] = -INFINITY;
   __syncthreads();
 
   CandBuf cb;
@@ -1311,7 +1317,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   {
     float tl = s_kth[0];
 #pragma unroll
-    for (int w = 1; w < kFastWarps; ++w) tl = fminf(tl, s_kth[w]);
+    for (int w = 1; w < kPairWarps; ++w) tl = fminf(tl, s_kth[w]);
     for (int e = lane; e < cb.cnt; e += 32) {
       const float v = cb.v[e];
       if (v >= tl) {
@@ -1323,7 +1329,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   }
   __syncthreads();
   const int nb = s_nbuf;
-  for (int t = tid; t < nb; t += kFastThreads) {
+  for (int t = tid; t < nb; t += kPairThreads) {
     const float v = s_bv[t];
     const int i = s_bi[t];
     int rank = 0;
@@ -1382,7 +1388,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   __syncthreads();
   if (lane < ex.count) {
     int rank = lane;
-    for (int w = 0; w < kFastWarps; ++w)
+    for (int w = 0; w < kPairWarps; ++w)
       if (w != warp) rank += count_beating(s_lv[w], s_li[w], s_cnt[w], ex.top_v, ex.top_i);
     if (rank < M) {
       const size_t o = ((size_t)n * a.K + k) * M + rank;
@@ -1523,7 +1529,7 @@ static cudaError_t launch_pairs(Kernel kernel, unsigned grid, size_t dyn, cudaSt
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kFastThreads);
+  cfg.blockDim = dim3(kPairThreads);
   cfg.dynamicSmemBytes = dyn;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1639,7 +1645,8 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
       else PC_BU_LAUNCH(CC, false, false);             \
     }                                                  \
   } while (0)
-    const bool pairs = C == 8 && two && mask2x && p->h1 % 2 == 0 && p->h1 <= 496;
+    // (rows per band + 2 halo rows must fit the 64-bit masked-row flags)
+    const bool pairs = C == 8 && two && mask2x && p->h1 % 2 == 0 && p->h1 <= 62 * kPairWarps;
     if (pairs) {
       // one word per (image, output row): which lanes see a masked pixel (stream-ordered scratch)
       uint32_t* zrow = nullptr;
@@ -1650,8 +1657,8 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
           d_mask, zrow, p->h1, p->w1, p->mask_h, p->mask_w, a.msy, rows);
       const bool all = p->w1 == 256 && p->w0 == 128;
 #define PC_BU_PAIRS(NMS_, ALL_)                                                              \
-  PC_CUDA(launch_pairs(bottomup_decode_pairs_kernel<NMS_, ALL_, 3>, grid,                    \
-                       (size_t)kFastWarps * 2 * kPairSlot, st, b, zrow))
+  PC_CUDA(launch_pairs(bottomup_decode_pairs_kernel<NMS_, ALL_, 4>, grid,                    \
+                       (size_t)kPairWarps * 2 * kPairSlot, st, b, zrow))
       if (b.use_nms) {
         if (all) PC_BU_PAIRS(true, true);
         else PC_BU_PAIRS(true, false);
