@@ -372,6 +372,9 @@ __device__ __forceinline__ RowCtx make_row(int Y, int hs, int ws, uint32_t ws3, 
 // arithmetic), a horizontal blend with weights (32-fx, fx) followed by a vertical blend
 // with (32-fy, fy); the horizontal blends are two-way dot products (dp2a) of the weight
 // pair with the channel's two bytes, paired up by a byte permute of the realigned words.
+// ROWAL: the source row pitch is a multiple of 4 bytes, so the run has the same alignment
+// in both rows and the lower row's words are the upper row's plus the pitch.
+template <bool ROWAL>
 __device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
                                                 const uint8_t* __restrict__ base4, int hs,
                                                 int ws, uint32_t ws3, int X, const RowCtx rc) {
@@ -379,8 +382,22 @@ __device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
   const int fx = X & 31, fy = rc.fy, sy = rc.sy;
   if ((uint32_t)(sx - rc.sx_lo) <= rc.sx_span) {
     const uint32_t off = rc.off + (uint32_t)sx * 3u;
-    const Six a = load_six(base4, off);
-    const Six b = load_six(base4, off + ws3);
+    Six a, b;
+    if (ROWAL) {
+      const uint8_t* pa = base4 + (off & ~3u);
+      const uint32_t* wa = reinterpret_cast<const uint32_t*>(pa);
+      const uint32_t* wb = reinterpret_cast<const uint32_t*>(pa + ws3);
+      const uint32_t sh = (off & 3u) << 3;
+      const uint32_t a0w = __ldg(wa), a1w = __ldg(wa + 1), a2w = __ldg(wa + 2);
+      const uint32_t b0w = __ldg(wb), b1w = __ldg(wb + 1), b2w = __ldg(wb + 2);
+      a.lo = __funnelshift_r(a0w, a1w, sh);
+      a.hi = __funnelshift_r(a1w, a2w, sh);
+      b.lo = __funnelshift_r(b0w, b1w, sh);
+      b.hi = __funnelshift_r(b1w, b2w, sh);
+    } else {
+      a = load_six(base4, off);
+      b = load_six(base4, off + ws3);
+    }
     // lo = r0 g0 b0 r1, hi = g1 b1 . . : pair the bytes of each channel (byte permute) and
     // take the 16-bit x 8-bit dot products with the weight pair (32 - fx, fx)
     const uint32_t wg = (32u - (uint32_t)fx) | ((uint32_t)fx << 16);
@@ -468,6 +485,9 @@ __global__ void __launch_bounds__(kWarpThreads)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* out = dst + ((size_t)crop * dst_h + row0) * dst_w * 3;
   uint32_t* stage = s_stage[warp];
+  // the fixed-point column deltas are monotone in x: the last one being 0 means all are
+  const bool axis = s_bdelta[dst_w - 1] == 0;
+  const bool rowal = (ws3 & 3u) == 0;
 
   for (int base = warp * 32; base < nquads; base += kWarpThreads) {
     const int t = base + lane;
@@ -477,23 +497,53 @@ __global__ void __launch_bounds__(kWarpThreads)
       const int x = (t - ry * wq) << 2;
       const int X0 = s_x0[ry], Y0 = s_y0[ry];
       const int4 ad = *reinterpret_cast<const int4*>(&s_adelta[x]);
-      const int4 bd = *reinterpret_cast<const int4*>(&s_bdelta[x]);
-      const int Ya = (Y0 + bd.x) >> 5, Yb = (Y0 + bd.y) >> 5;
-      const int Yc = (Y0 + bd.z) >> 5, Yd = (Y0 + bd.w) >> 5;
-      const RowCtx ra = make_row(Ya, hs, ws, ws3, delta);
-      if (Ya == Yb && Ya == Yc && Ya == Yd) {  // no rotation: one source row pair
-        p0 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
-        p1 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5, ra);
-        p2 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5, ra);
-        p3 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5, ra);
+      // (uint8 variant only: in the float32 CHW variant the extra code path costs 15
+      // registers and two resident CTAs per SM)
+      if (!NORM && axis) {  // no rotation: Y does not depend on x, one row pair per quad
+        const RowCtx ra = make_row(Y0 >> 5, hs, ws, ws3, delta);
+        if (rowal) {
+          p0 = warp_pixel3<true>(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
+          p1 = warp_pixel3<true>(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5, ra);
+          p2 = warp_pixel3<true>(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5, ra);
+          p3 = warp_pixel3<true>(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5, ra);
+        } else {
+          p0 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
+          p1 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5, ra);
+          p2 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5, ra);
+          p3 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5, ra);
+        }
       } else {
-        p0 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
-        p1 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5,
-                         make_row(Yb, hs, ws, ws3, delta));
-        p2 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5,
-                         make_row(Yc, hs, ws, ws3, delta));
-        p3 = warp_pixel3(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5,
-                         make_row(Yd, hs, ws, ws3, delta));
+        const int4 bd = *reinterpret_cast<const int4*>(&s_bdelta[x]);
+        const int Ya = (Y0 + bd.x) >> 5, Yb = (Y0 + bd.y) >> 5;
+        const int Yc = (Y0 + bd.z) >> 5, Yd = (Y0 + bd.w) >> 5;
+        const RowCtx ra = make_row(Ya, hs, ws, ws3, delta);
+        const bool same = Ya == Yb && Ya == Yc && Ya == Yd;  // small angles: one row pair
+        // Two spellings of the same thing: ptxas allocates 40 registers for the float32
+        // variant with the branch and 48 (not 54) for the uint8 variant with the selects.
+        if constexpr (NORM) {
+          if (same) {
+            p0 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
+            p1 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5, ra);
+            p2 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5, ra);
+            p3 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5, ra);
+          } else {
+            p0 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
+            p1 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5,
+                                    make_row(Yb, hs, ws, ws3, delta));
+            p2 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5,
+                                    make_row(Yc, hs, ws, ws3, delta));
+            p3 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5,
+                                    make_row(Yd, hs, ws, ws3, delta));
+          }
+        } else {
+          p0 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
+          p1 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5,
+                                  same ? ra : make_row(Yb, hs, ws, ws3, delta));
+          p2 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5,
+                                  same ? ra : make_row(Yc, hs, ws, ws3, delta));
+          p3 = warp_pixel3<false>(img, base4, hs, ws, ws3, (X0 + ad.w) >> 5,
+                                  same ? ra : make_row(Yd, hs, ws, ws3, delta));
+        }
       }
     }
     if (NORM) {
