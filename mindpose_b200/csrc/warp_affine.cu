@@ -453,6 +453,8 @@ __global__ void __launch_bounds__(kWarpThreads)
   __shared__ __align__(16) int s_bdelta[kWarpMaxDstW];
   __shared__ int s_x0[kWarp3TileRows];
   __shared__ int s_y0[kWarp3TileRows];
+  __shared__ int4 s_rowa[kWarp3TileRows];  // rotation-free crops: sy, fy, sx_lo, sx_span per row
+  __shared__ uint32_t s_rowoff[kWarp3TileRows];
   __shared__ __align__(16) uint32_t s_stage[kWarpThreads / 32][96];
 
   const int64_t crop = blockIdx.x / tiles_per_crop;
@@ -488,6 +490,14 @@ __global__ void __launch_bounds__(kWarpThreads)
   // the fixed-point column deltas are monotone in x: the last one being 0 means all are
   const bool axis = s_bdelta[dst_w - 1] == 0;
   const bool rowal = (ws3 & 3u) == 0;
+  if (!NORM && axis) {  // Y does not depend on x: one row context per output row
+    if (threadIdx.x < rows) {
+      const RowCtx rc = make_row(s_y0[threadIdx.x] >> 5, hs, ws, ws3, delta);
+      s_rowa[threadIdx.x] = make_int4(rc.sy, rc.fy, rc.sx_lo, (int)rc.sx_span);
+      s_rowoff[threadIdx.x] = rc.off;
+    }
+    __syncthreads();
+  }
 
   for (int base = warp * 32; base < nquads; base += kWarpThreads) {
     const int t = base + lane;
@@ -500,7 +510,10 @@ __global__ void __launch_bounds__(kWarpThreads)
       // (uint8 variant only: in the float32 CHW variant the extra code path costs 15
       // registers and two resident CTAs per SM)
       if (!NORM && axis) {  // no rotation: Y does not depend on x, one row pair per quad
-        const RowCtx ra = make_row(Y0 >> 5, hs, ws, ws3, delta);
+        const int4 rw = s_rowa[ry];
+        RowCtx ra;
+        ra.sy = rw.x, ra.fy = rw.y, ra.sx_lo = rw.z, ra.sx_span = (uint32_t)rw.w;
+        ra.off = s_rowoff[ry];
         if (rowal) {
           p0 = warp_pixel3<true>(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
           p1 = warp_pixel3<true>(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5, ra);
