@@ -9,10 +9,12 @@
  *
  * Conventions
  *  - All pointers named d_* are DEVICE pointers (contiguous, dense, row-major);
- *    pointers named h_* are HOST pointers.  The library never allocates, frees
- *    or retains caller memory and never synchronises the stream it is given
- *    (the *_host entry points are the exception: they own a context with
- *    scratch buffers and return after the results are in the host buffers).
+ *    pointers named h_* are HOST pointers.  The library never frees or retains
+ *    caller memory and never synchronises the stream it is given.  Exceptions:
+ *    the *_host entry points own a context with scratch buffers and return after
+ *    the results are in the host buffers; pc_bottomup_decode takes a few KB of
+ *    stream-ordered scratch (cudaMallocAsync / cudaFreeAsync on the caller's
+ *    stream, from the device's default pool).
  *  - Tensors: heatmaps float32 NCHW; images uint8 HWC; keypoints float32
  *    [N, K, 3] = (x, y, visibility).
  *  - Sizes follow the reference's config convention where noted ([w, h]).
@@ -20,7 +22,8 @@
  *    thread-local, human readable message for the last failure on this thread.
  *    Argument errors map to Python ValueError (the reference raises ValueError
  *    for bad configuration), CUDA failures to RuntimeError.
- *  - Re-entrant: no global mutable state; one stream per call.
+ *  - Re-entrant: no global mutable state except one diagnostics counter per
+ *    device (pc_bottomup_decode_stats); one stream per call.
  *  - stream is a cudaStream_t passed as void* (0 = legacy default stream).
  */
 #ifndef POSECODEC_H_
