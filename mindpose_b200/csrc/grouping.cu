@@ -56,18 +56,24 @@ __device__ float np_sum_f32(const float* a, int n, int stride) {
   return res;
 }
 
+// Warp reductions of the solver's inner loop, as single REDUX instructions instead of five
+// shuffle steps each (the loop is a chain of dependent reductions: their latency is the
+// run time of the kernel).  The float64 minimum goes through the usual order-preserving map
+// to a signed 64-bit key (no NaNs here), reduced as a signed high word and an unsigned low
+// word among the lanes that hold the minimal high word.
 __device__ __forceinline__ double warp_min_f64(double v) {
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+  long long b = __double_as_longlong(v);
+  b ^= (b >> 63) & 0x7fffffffffffffffLL;  // negative values: reverse their order
+  const int hi = (int)(b >> 32);
+  const unsigned lo = (unsigned)b;
+  const int mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  long long m = ((long long)mhi << 32) | (long long)mlo;
+  m ^= (m >> 63) & 0x7fffffffffffffffLL;
+  return __longlong_as_double(m);
 }
-__device__ __forceinline__ int warp_min_i32(int v) {
-  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ int warp_max_i32(int v) {
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
+__device__ __forceinline__ int warp_min_i32(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_max_i32(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
 struct LsapState {
   double* u;         // [kMaxDet]
