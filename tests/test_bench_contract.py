@@ -1,0 +1,53 @@
+"""The JSON line bench.py prints (latest committed run under profiles/) carries every key the
+measurement contract names, for both arms."""
+import glob
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _latest(pattern):
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
+    assert files, pattern
+    with open(files[-1]) as f:
+        return json.loads(f.read().strip().splitlines()[-1])
+
+
+def test_our_arm_line_has_the_contract_keys():
+    d = _latest("r*_bench.json")
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["scaling"] == "weak" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in r, key
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] >= 0.9 * r["algorithmic_bytes_per_launch"]
+    c = d["cpu_baseline"]
+    for key in ("value", "unit", "cores", "kind", "sample"):
+        assert key in c, key
+    assert c["kind"] in ("reference", "port")
+    e = d["e2e"]
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in e, key
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+    for key in ("sm_mhz", "sm_max_mhz", "reasons"):
+        assert key in d["clocks"], key
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    d = _latest("r*_bench_reference.json")
+    assert d["impl"] == "reference"
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
+    ours = _latest("r*_bench.json")
+    assert d["metric"] == ours["metric"] and d["unit"] == ours["unit"]
+    assert d["config"]["workload"] == ours["config"]["workload"]
