@@ -74,7 +74,7 @@ __device__ float oks_pair(const NmsArgs& a, const float* __restrict__ g,
 // dst order = stable ascending argsort of sc[0..n) reversed: rank by counting
 __device__ __forceinline__ void rank_sort(const float* sc, const int* ord, float* sc_out,
                                           int* ord_out, int n, int tid) {
-  for (int j = tid; j < n; j += kNmsThreads) {
+  for (int j = tid; j < n; j += blockDim.x) {
     const float s = sc[j];
     int rank = 0;
     for (int k = 0; k < n; ++k) {
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kNmsThreads) oks_nms_kernel(const NmsArgs a) {
   }
 
   // ---- rescoring: mean of the joint scores above vis_thr, times the box score --------
-  for (int p = tid; p < n; p += kNmsThreads) {
+  for (int p = tid; p < n; p += blockDim.x) {
     float s = score[p];
     if (a.rescore) {
       float acc = 0.f;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kNmsThreads) oks_nms_kernel(const NmsArgs a) {
   if (tid == 0) s_nkeep = 0;
   __syncthreads();
   if (!a.use_nms) {
-    for (int p = tid; p < n; p += kNmsThreads) keep[p] = p;
+    for (int p = tid; p < n; p += blockDim.x) keep[p] = p;
     if (tid == 0) a.num_keep[img] = n;
     return;
   }
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kNmsThreads) oks_nms_kernel(const NmsArgs a) {
       const int i = ord0[t];
       if (tid == 0) keep[s_nkeep++] = i;
       const float ai = area[i];
-      for (int u = t + 1 + tid; u < n; u += kNmsThreads) {
+      for (int u = t + 1 + tid; u < n; u += blockDim.x) {
         if (flag[u]) continue;
         const int j = ord0[u];
         const float ov = oks_pair(a, kp + i * stride, kp + j * stride, ai, area[j]);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kNmsThreads) oks_nms_kernel(const NmsArgs a) {
       if (tid == 0) keep[kept] = i;
       ++kept;
       const float ai = area[i];
-      for (int u = 1 + tid; u < cur; u += kNmsThreads) {
+      for (int u = 1 + tid; u < cur; u += blockDim.x) {
         const int j = ord_cur[u];
         const float ov = oks_pair(a, kp + i * stride, kp + j * stride, ai, area[j]);
         // scores * np.exp(-(overlap**2) / thr), float32
@@ -239,7 +239,11 @@ extern "C" int pc_oks_nms(const float* d_kpts, const float* d_area, float* d_sco
     a.key_vars[k] = s2 * s2;
   }
   const size_t smem = (size_t)a.cap * 5 * sizeof(float);
-  oks_nms_kernel<<<(unsigned)num_images, kNmsThreads, smem, (cudaStream_t)stream>>>(a);
+  // one thread per person up to 256: small images get small CTAs, so that many of them are
+  // resident per SM (the per-image loop is a chain of barriers: latency bound)
+  int threads = ((a.cap + 31) / 32) * 32;
+  if (threads > kNmsThreads) threads = kNmsThreads;
+  oks_nms_kernel<<<(unsigned)num_images, threads, smem, (cudaStream_t)stream>>>(a);
   PC_CUDA(cudaGetLastError());
   return PC_OK;
 }
