@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $o
 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1
 echo "pytest exit $?" >> $out/${tag}_pytest_gpu.log
 tail -4 $out/${tag}_pytest_gpu.log
-for sec in decode encode warp bottomup bu_encode refine nms; do
+for sec in decode encode warp bottomup bu_encode refine nms sweep; do
   timeout 240 python scripts/kbench.py --iters 10 --only $sec,group --json $out/${tag}_kbench_$sec.json \
     >> $out/${tag}_kbench.log 2>&1 || echo "kbench $sec failed/timeout rc=$?" >> $out/${tag}_kbench.log
 done

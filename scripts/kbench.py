@@ -42,7 +42,7 @@ def timeit(fn, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--only", default="decode,encode,warp,bottomup,group,bu_encode,refine,nms")
+    ap.add_argument("--only", default="decode,encode,warp,bottomup,group,bu_encode,refine,nms,sweep")
     ap.add_argument("--json", default="")
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -88,6 +88,27 @@ def main():
                     report(f"topdown_decode {h}x{w} {mode}{' flip' if flip else ''}", n, "crops",
                            bpu, med, mn)
             del hm, fl
+    if "sweep" in only:
+        # BASELINE config 5 on one GPU: 1 M crops of 17x64x48, flip pair + DARK, streamed as 16
+        # chunks of 65,536 crops (27 GB per chunk; the same synthetic chunk is decoded 16 times)
+        n, h, w, chunks = 65536, 64, 48, 16
+        hm = torch.rand(n, k, h, w, device=dev) * 0.02
+        hm[:, :, 20:23, 20:23] += 0.5
+        fl = torch.rand(n, k, h, w, device=dev) * 0.02
+        center = torch.rand(n, 2, device=dev) * 400
+        scale = torch.rand(n, 2, device=dev) * 2.8 + 0.2
+        score = torch.rand(n, device=dev)
+        dec = mp.create_decoder("topdown_heatmap", dark_udp_refine=True)
+        p = dec._params(k, h, w, flip_index=synth.flip_index(), shift_heatmap=True)
+
+        def sweep():
+            for _ in range(chunks):
+                codec.topdown_decode(hm, center, scale, score, flipped=fl, params=p)
+
+        med, mn = timeit(sweep, max(3, args.iters // 3))
+        report("topdown_decode sweep: 1M crops, dark flip, 16 x 65,536", n * chunks, "crops",
+               2 * k * h * w * 4 + 228, med, mn)
+        del hm, fl
     if "encode" in only:
         for cfg, n in ((synth.TOPDOWN_CONFIG, 8192), (synth.TOPDOWN_CONFIG_384, 4096)):
             w, h = cfg["heatmap_size"]
