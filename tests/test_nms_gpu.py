@@ -82,3 +82,22 @@ def test_use_nms_false_and_too_many_people(cuda_device):
     with pytest.raises(ValueError):
         dnms.rescore_and_nms(t(k).cpu(), t(a), t(s.copy()), off, 9, oks_thr=0.9)
     assert dnms.oks_nms([], 0.9) == []
+
+
+@pytest.mark.parametrize("k", [5, 8, 21])
+@pytest.mark.parametrize("vthr", [None, 0.4])
+def test_other_joint_counts_custom_sigmas_and_vis_thr(cuda_device, k, vthr):
+    """K != 17: fewer than 8 exp terms are summed in order (numpy's pairwise rule), custom
+    sigmas, and the detection-only visibility selection of oks_iou."""
+    rng = np.random.RandomState(k)
+    sig = rng.uniform(0.02, 0.11, k)
+    for seed in range(3):
+        people = 9 + 4 * seed
+        kpts, areas, scores = ggn.nms_people(200 + seed, people, k)
+        db = ggn._kpts_db(kpts, areas, scores)
+        flat = kpts.reshape(people, -1)
+        assert np.array_equal(dnms.oks_nms(db, 0.7, sigmas=sig, vis_thr=vthr, device=cuda_device),
+                              onms.oks_nms(flat, areas, scores, 0.7, sig, vthr))
+        assert np.array_equal(
+            dnms.soft_oks_nms(db, 0.7, max_dets=6, sigmas=sig, vis_thr=vthr, device=cuda_device),
+            onms.soft_oks_nms(flat, areas, scores, 0.7, 6, sig, vthr))

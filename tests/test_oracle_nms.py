@@ -57,3 +57,26 @@ def test_live_reference_agrees_on_fresh_seeds():
         assert np.array_equal(nms.oks_nms(flat, areas, scores, 0.8), ref.nms.oks_nms(db, 0.8))
         assert np.array_equal(nms.soft_oks_nms(flat, areas, scores, 0.8, 20),
                               ref.nms.soft_oks_nms(db, 0.8, max_dets=20))
+
+
+@pytest.mark.needs_reference
+def test_live_reference_agrees_for_other_joint_counts_and_vis_thr():
+    """K = 5 (numpy sums fewer than 8 terms in order), K = 21, custom sigmas, and the
+    detection-only vis_thr selection (nms.py:64)."""
+    ref = ref_loader.load()
+    rng = np.random.RandomState(3)
+    for k in (5, 8, 21):
+        sig = rng.uniform(0.02, 0.11, k)
+        for seed in range(3):
+            people = 9 + 4 * seed
+            kpts, areas, scores = ggn.nms_people(200 + seed, people, k)
+            flat = kpts.reshape(people, -1)
+            db = ggn._kpts_db(kpts, areas, scores)
+            for vthr in (None, 0.4):
+                want = ref.nms.oks_iou(flat[0], flat, areas[0], areas, sig, vthr)
+                assert np.array_equal(nms.oks_iou(flat[0], flat, areas[0], areas, sig, vthr), want)
+                assert np.array_equal(nms.oks_nms(flat, areas, scores, 0.7, sig, vthr),
+                                      ref.nms.oks_nms(db, 0.7, sigmas=sig, vis_thr=vthr))
+                assert np.array_equal(nms.soft_oks_nms(flat, areas, scores, 0.7, 6, sig, vthr),
+                                      ref.nms.soft_oks_nms(db, 0.7, max_dets=6, sigmas=sig,
+                                                           vis_thr=vthr))
