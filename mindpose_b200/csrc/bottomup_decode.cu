@@ -1656,20 +1656,25 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
       mask_zero_rows_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(
           d_mask, zrow, p->h1, p->w1, p->mask_h, p->mask_w, a.msy, rows);
       const bool all = p->w1 == 256 && p->w0 == 128;
+      // (errors are collected so that the scratch is returned to the pool on every path)
+      cudaError_t le = cudaGetLastError();  // of the row-flag kernel
 #define PC_BU_PAIRS(NMS_, ALL_)                                                              \
-  PC_CUDA(launch_pairs(bottomup_decode_pairs_kernel<NMS_, ALL_, 4>, grid,                    \
-                       (size_t)kPairWarps * 2 * kPairSlot, st, b, zrow))
-      if (b.use_nms) {
-        if (all) PC_BU_PAIRS(true, true);
-        else PC_BU_PAIRS(true, false);
-      } else {
-        if (all) PC_BU_PAIRS(false, true);
-        else PC_BU_PAIRS(false, false);
+  le = launch_pairs(bottomup_decode_pairs_kernel<NMS_, ALL_, 4>, grid,                       \
+                    (size_t)kPairWarps * 2 * kPairSlot, st, b, zrow)
+      if (le == cudaSuccess) {
+        if (b.use_nms) {
+          if (all) PC_BU_PAIRS(true, true);
+          else PC_BU_PAIRS(true, false);
+        } else {
+          if (all) PC_BU_PAIRS(false, true);
+          else PC_BU_PAIRS(false, false);
+        }
       }
 #undef PC_BU_PAIRS
-      const cudaError_t le = cudaGetLastError();
-      PC_CUDA(cudaFreeAsync(zrow, st));
+      if (le == cudaSuccess) le = cudaGetLastError();
+      const cudaError_t fe = cudaFreeAsync(zrow, st);
       PC_CUDA(le);
+      PC_CUDA(fe);
     } else if (C == 4) PC_BU_PICK(4);
     else if (C == 8) PC_BU_PICK(8);
     else PC_BU_PICK(16);
