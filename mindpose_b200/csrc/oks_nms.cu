@@ -29,6 +29,7 @@ struct NmsArgs {
   int32_t* keep;               // [P]
   int32_t* num_keep;           // [I]
   int32_t K, rescore, use_nms, soft, max_dets, use_iou_vis, cap;
+  int32_t use_matrix;  // small images: all pairwise OKS values up front, in shared memory
   float rescore_vis_thr, oks_thr, iou_vis_thr;
   double key_vars[PC_MAX_JOINTS];  // (2 sigma)^2
 };
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(kNmsThreads) oks_nms_kernel(const NmsArgs a) {
   int* ord0 = reinterpret_cast<int*>(sc1 + cap);
   int* ord1 = ord0 + cap;
   int* flag = ord1 + cap;
+  float* mat = reinterpret_cast<float*>(flag + cap);  // [n][n] when use_matrix
   __shared__ int s_nkeep;
 
   const int tid = threadIdx.x;
@@ -146,6 +148,20 @@ __global__ void __launch_bounds__(kNmsThreads) oks_nms_kernel(const NmsArgs a) {
   __syncthreads();
 
   const size_t stride = (size_t)a.K * 3;
+  // The greedy loops below are chains of barriers with one OKS evaluation (K float64 exps)
+  // per thread and step.  For small images every ordered pair (g = i, d = j) is evaluated
+  // up front instead, all threads busy, and the loops only look values up.
+  if (a.use_matrix) {
+    for (int e = tid; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e - i * n;
+      if (i != j) mat[e] = oks_pair(a, kp + i * stride, kp + j * stride, area[i], area[j]);
+    }
+    __syncthreads();
+  }
+  auto oks = [&](int i, int j, float ai) {
+    return a.use_matrix ? mat[i * n + j]
+                        : oks_pair(a, kp + i * stride, kp + j * stride, ai, area[j]);
+  };
   if (!a.soft) {
     // ---- oks_nms (nms.py:72-111): walk the order, drop what overlaps a kept person ----
     for (int t = 0; t < n; ++t) {
@@ -156,7 +172,7 @@ __global__ void __launch_bounds__(kNmsThreads) oks_nms_kernel(const NmsArgs a) {
       for (int u = t + 1 + tid; u < n; u += blockDim.x) {
         if (flag[u]) continue;
         const int j = ord0[u];
-        const float ov = oks_pair(a, kp + i * stride, kp + j * stride, ai, area[j]);
+        const float ov = oks(i, j, ai);
         if (!(ov <= a.oks_thr)) flag[u] = 1;
       }
       __syncthreads();
@@ -176,7 +192,7 @@ __global__ void __launch_bounds__(kNmsThreads) oks_nms_kernel(const NmsArgs a) {
       const float ai = area[i];
       for (int u = 1 + tid; u < cur; u += blockDim.x) {
         const int j = ord_cur[u];
-        const float ov = oks_pair(a, kp + i * stride, kp + j * stride, ai, area[j]);
+        const float ov = oks(i, j, ai);
         // scores * np.exp(-(overlap**2) / thr), float32
         const float x = __fdiv_rn(-__fmul_rn(ov, ov), a.oks_thr);
         sc_nxt[u - 1] = __fmul_rn(sc_cur[u], (float)exp((double)x));
@@ -238,11 +254,15 @@ extern "C" int pc_oks_nms(const float* d_kpts, const float* d_area, float* d_sco
     const double s2 = p->sigmas[k] * 2;  // key_vars = (sigmas * 2) ** 2
     a.key_vars[k] = s2 * s2;
   }
-  const size_t smem = (size_t)a.cap * 5 * sizeof(float);
-  // one thread per person up to 256: small images get small CTAs, so that many of them are
-  // resident per SM (the per-image loop is a chain of barriers: latency bound)
-  int threads = ((a.cap + 31) / 32) * 32;
-  if (threads > kNmsThreads) threads = kNmsThreads;
+  // images of up to 96 people (36 KB of pairwise values): matrix variant with full CTAs;
+  // else one thread per person up to 256, so that small CTAs share an SM
+  a.use_matrix = p->use_nms && a.cap <= 96;
+  const size_t smem = ((size_t)a.cap * 5 + (a.use_matrix ? (size_t)a.cap * a.cap : 0)) * sizeof(float);
+  int threads = kNmsThreads;
+  if (!a.use_matrix) {
+    threads = ((a.cap + 31) / 32) * 32;
+    if (threads > kNmsThreads) threads = kNmsThreads;
+  }
   oks_nms_kernel<<<(unsigned)num_images, threads, smem, (cudaStream_t)stream>>>(a);
   PC_CUDA(cudaGetLastError());
   return PC_OK;
