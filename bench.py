@@ -10,7 +10,8 @@ codec"): affine crop warp of 4096 u8 480x640x3 source images to 256x192x3, then
 DARK-refined decode with flip averaging of 4096 x 2 x [17,64,48] float32
 heatmaps.  Inputs are resident in HBM for `value` (5.5 GB per step >> 126 MB of
 L2, so every step streams from DRAM); `e2e` repeats the step through the
-host-buffer C-ABI front end with pinned host inputs and host results.
+host-buffer C-ABI front end with pinned host inputs and host results (of the
+source images only the rectangle each crop samples is fetched over PCIe).
 
 Prints ONE JSON line (rank 0).  Under torchrun each rank processes its own
 4096 crops (weak scaling) and the decoded keypoints are all-gathered with NCCL
@@ -329,12 +330,17 @@ def run_ours(args, wl):
         h_preds = torch.empty(n, k, 3).pin_memory()
         h_bxs = torch.empty(n, 6).pin_memory()
 
+        moved = [0, 0]   # bytes the library moved host->device / device->host in one step
+
         def e2e_step():
             _, c_h, s_h = hctx.topdown_affine(h_images.numpy(), h_boxes, cfg["image_size"],
-                                              out=h_crops.numpy())
+                                              out=h_crops.numpy(), upload=args.upload)
+            a = hctx.last_transfer_bytes()
             hctx.topdown_decode(h_heat.numpy(), c_h, s_h, h_score, flipped=h_flip.numpy(),
                                 params=dparams, out_preds=h_preds.numpy(),
                                 out_boxes=h_bxs.numpy())
+            b = hctx.last_transfer_bytes()
+            moved[0], moved[1] = a[0] + b[0], a[1] + b[1]
 
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         e2e_step()
@@ -348,11 +354,14 @@ def run_ours(args, wl):
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = images.numel() + 2 * heat.numel() * 4 + n * (16 + 8 + 8 + 4 + 8 + 8)
-        d2h = crops.numel() + n * (k * 3 + 6) * 4 + n * 16
+        # counted by the library from the copies it issued (pc_ctx_last_transfer_bytes); with
+        # the default upload only the source rectangle each crop samples crosses PCIe
         e2e = {"value": world * n * e2e_steps / dt, "unit": "crops/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3}
+               "h2d_bytes_per_step": int(moved[0]), "d2h_bytes_per_step": int(moved[1]),
+               "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+               "upload": args.upload or codec.DEFAULT_UPLOAD,
+               "h2d_bytes_per_step_whole_images": int(
+                   images.numel() + 2 * heat.numel() * 4 + n * (16 + 8 + 8 + 4 + 8 + 8))}
         hctx.close()
 
     if rank == 0:
@@ -427,6 +436,8 @@ def main():
     ap.add_argument("--crops", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--upload", default=None, choices=["full", "roi", "roi_kernel"],
+                    help="e2e: how the source images cross PCIe (default: codec.DEFAULT_UPLOAD)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="N > 1: use the NCCL all-gather instead of the peer-memory stores")

@@ -309,6 +309,9 @@ int pc_scatter_results(const float* d_preds, const float* d_boxes, void* const* 
 typedef struct pc_ctx pc_ctx;
 int pc_ctx_create(int device, int64_t scratch_bytes, pc_ctx** out);
 int pc_ctx_destroy(pc_ctx* ctx);
+/* Bytes the last *_host call on this context moved host->device and device->host
+ * (what bench.py reports as h2d_bytes_per_step / d2h_bytes_per_step). */
+int pc_ctx_last_transfer_bytes(const pc_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes);
 int pc_topdown_decode_host(pc_ctx* ctx, const float* h_heatmap, const float* h_flipped,
                            const float* h_center, const float* h_scale, const float* h_score,
                            float* h_all_preds, float* h_all_boxes,
@@ -318,12 +321,33 @@ int pc_topdown_decode_host(pc_ctx* ctx, const float* h_heatmap, const float* h_f
  * dense source image per crop, all of one size (h_images u8 [N, src_h, src_w, C]).
  * h_boxes f32 [N,4] (x,y,w,h); h_rot f32 [N] or NULL.
  * -> h_crops u8 [N, image_h, image_w, C]; optional h_center / h_scale f32 [N,2]. */
+/* upload: which bytes of each source image cross PCIe, and how.  The warp only samples the
+ * padded box of a crop (about 40 % of a 480x640 image on the bench data), so the front end
+ * can upload just that rectangle (computed on the host from the box, padded by 4 pixels) into
+ * the full-image layout the kernel reads: the crops are the same bits, the bytes outside the
+ * rectangle are never read. */
+#define PC_UPLOAD_FULL 0 /* whole source images, one contiguous copy per chunk */
+#define PC_UPLOAD_ROI 1  /* the sampled rectangle of each image, one strided DMA copy per crop */
+/* The rectangles (rows widened to 64-byte boundaries) are fetched by ONE kernel per chunk that
+ * reads the caller's PINNED host buffer through its device mapping (16-byte loads over PCIe)
+ * and writes the scratch: no per-crop copy-engine launch (4.6 us each, measured).  Needs
+ * page-locked h_images (cudaHostAlloc / cudaHostRegister / torch pin_memory) and a row pitch
+ * and image size that are multiples of 16 bytes; otherwise PC_UPLOAD_ROI is used. */
+#define PC_UPLOAD_ROI_KERNEL 2
 typedef struct pc_affine_host_params {
   int32_t src_h, src_w, channels;
   int32_t image_w, image_h; /* crop size, dataset_setting.image_size = [w, h] */
   float pixel_std, scale_padding;
   int32_t use_udp;
+  int32_t upload; /* PC_UPLOAD_* */
 } pc_affine_host_params;
+/* Host-only helper (no CUDA call): the rectangle [x0, x1) x [y0, y1) of source pixels that
+ * PC_UPLOAD_ROI uploads for one crop -> h_rect int32 [4] = (x0, y0, x1, y1), clipped to the
+ * image (empty when x1 <= x0 or y1 <= y0).  h_box f32 [4] = (x, y, w, h); rot in degrees.
+ * Returns PC_ERR_UNSUPPORTED for a box that is not finite or is degenerate (the front end
+ * then uploads the whole image). */
+int pc_crop_source_rect(const float* h_box, float rot, const pc_affine_host_params* params,
+                        int32_t* h_rect);
 int pc_topdown_affine_host(pc_ctx* ctx, const uint8_t* h_images, const float* h_boxes,
                            const float* h_rot, uint8_t* h_crops, float* h_center,
                            float* h_scale, const pc_affine_host_params* params, int64_t n);

@@ -175,8 +175,11 @@ class AffineHostParams(Structure):
         ("pixel_std", c_float),
         ("scale_padding", c_float),
         ("use_udp", c_int32),
+        ("upload", c_int32),
     ]
 
+
+UPLOAD_FULL, UPLOAD_ROI, UPLOAD_ROI_KERNEL = 0, 1, 2   # PC_UPLOAD_* of posecodec.h
 
 # name -> (restype, argtypes); one entry per function declared in posecodec.h
 _P = c_void_p
@@ -213,6 +216,8 @@ SIGNATURES = {
         c_int, [_P, _P, POINTER(c_void_p), c_int32, _P, c_int64, c_int32, c_int64, _P]),
     "pc_ctx_create": (c_int, [c_int, c_int64, POINTER(c_void_p)]),
     "pc_ctx_destroy": (c_int, [c_void_p]),
+    "pc_ctx_last_transfer_bytes": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
+    "pc_crop_source_rect": (c_int, [_P, c_float, POINTER(AffineHostParams), _P]),
     "pc_topdown_affine_host": (
         c_int,
         [c_void_p, _P, _P, _P, _P, _P, _P, POINTER(AffineHostParams), c_int64],

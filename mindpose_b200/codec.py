@@ -244,6 +244,11 @@ def topdown_decode(heatmap: torch.Tensor, center: torch.Tensor, scale: torch.Ten
     return preds, boxes
 
 
+_UPLOAD_MODES = {"full": _lib.UPLOAD_FULL, "roi": _lib.UPLOAD_ROI,
+                 "roi_kernel": _lib.UPLOAD_ROI_KERNEL}
+DEFAULT_UPLOAD = "roi_kernel"   # measured: profiles/README.md (r01r / r01s / r01t)
+
+
 class HostContext:
     """Owns a pc_ctx: device scratch + two streams for the host-buffer path."""
 
@@ -290,11 +295,25 @@ class HostContext:
                   ctypes.byref(params), n)
         return preds, boxes
 
+    def last_transfer_bytes(self):
+        """(host->device, device->host) bytes the last call on this context moved."""
+        h2d, d2h = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.call("pc_ctx_last_transfer_bytes", self._h, ctypes.byref(h2d), ctypes.byref(d2h))
+        return int(h2d.value), int(d2h.value)
+
     def topdown_affine(self, images: np.ndarray, boxes: np.ndarray, image_size,
                        rot: Optional[np.ndarray] = None, pixel_std: float = 200.0,
                        scale_padding: float = 1.25, use_udp: bool = False,
-                       out: Optional[np.ndarray] = None):
-        """images u8 [N,Hs,Ws,C] + boxes f32 [N,4] (host) -> (crops u8 [N,h,w,C], center, scale)."""
+                       out: Optional[np.ndarray] = None, upload: Optional[str] = None):
+        """images u8 [N,Hs,Ws,C] + boxes f32 [N,4] (host) -> (crops u8 [N,h,w,C], center, scale).
+
+        ``upload``: "full" copies whole source images to the device; "roi" copies only the
+        rectangle each crop samples (one strided copy per crop); "roi_kernel" lets one kernel
+        per chunk fetch the rectangles from PINNED ``images`` (falls back to "roi" for pageable
+        memory).  Same crops in every mode, fewer PCIe bytes in the last two."""
+        upload = DEFAULT_UPLOAD if upload is None else upload
+        if upload not in _UPLOAD_MODES:
+            raise ValueError(f"`upload` must be one of {sorted(_UPLOAD_MODES)}, got {upload!r}")
         if images.dtype != np.uint8 or images.ndim != 4:
             raise ValueError("`images` must be uint8 [N, Hs, Ws, C]")
         images = np.ascontiguousarray(images)
@@ -307,7 +326,7 @@ class HostContext:
         center = np.empty((n, 2), np.float32)
         scale = np.empty((n, 2), np.float32)
         p = _lib.AffineHostParams(hs, ws, c, w, h, float(pixel_std), float(scale_padding),
-                                  int(bool(use_udp)))
+                                  int(bool(use_udp)), _UPLOAD_MODES[upload])
         _lib.call("pc_topdown_affine_host", self._h, _lib.host_ptr(images), _lib.host_ptr(boxes),
                   _lib.host_ptr(rot), _lib.host_ptr(crops), _lib.host_ptr(center),
                   _lib.host_ptr(scale), ctypes.byref(p), n)

@@ -59,6 +59,7 @@ def test_struct_sizes_match_header(tmp_path):
         "pc_bottomup_decode_params": _lib.BottomUpDecodeParams,
         "pc_bottomup_encode_params": _lib.BottomUpEncodeParams,
         "pc_group_params": _lib.GroupParams,
+        "pc_affine_host_params": _lib.AffineHostParams,
     }
     src = tmp_path / "sizes.c"
     body = "\n".join(f'  printf("{n} %zu\\n", sizeof({n}));' for n in structs)

@@ -192,6 +192,56 @@ def test_decode_host_front_end_matches_device_path(cuda_device):
     assert np.array_equal(hp, dp.cpu().numpy()) and np.array_equal(hb, db.cpu().numpy())
 
 
+
+@pytest.mark.parametrize("use_udp", [False, True])
+def test_affine_host_front_end_upload_modes_match_device_path(cuda_device, use_udp):
+    """pc_topdown_affine_host with whole-image upload and with the two rectangle uploads
+    gives the crops of the device path bit for bit -- with rotations, boxes that leave the
+    image, a degenerate box, and the context scratch holding OTHER images first (a kernel
+    that sampled outside the uploaded rectangle would read those)."""
+    n, hs, ws = 40, 240, 320
+    images, boxes = synth.source_images_and_boxes(n, hs, ws, seed=11)
+    rng = np.random.RandomState(11)
+    boxes[1] = [-60.0, -40.0, 150.0, 200.0]          # leaves the image top-left
+    boxes[2] = [250.0, 180.0, 200.0, 160.0]          # leaves it bottom-right
+    boxes[3] = [-500.0, -500.0, 50.0, 60.0]          # never touches it: all border
+    boxes[4] = [100.0, 100.0, 0.0, 0.0]              # degenerate
+    boxes[5] = [0.0, 0.0, float(ws), float(hs)]      # the whole image (+ padding)
+    rot = np.zeros(n, np.float32)
+    rot[::3] = rng.uniform(-80, 80, len(rot[::3])).astype(np.float32)
+    rot[7] = 180.0
+    cfg = synth.TOPDOWN_CONFIG
+    dev = cuda_device
+    bt = mp.create_transform("topdown_box_to_center_scale", is_train=False, config=cfg)
+    at = mp.create_transform("topdown_affine", is_train=False, config=cfg, use_udp=use_udp)
+    c, s = bt.box_to_center_scale_batch(_t(boxes, dev))
+    want, _ = at.affine_batch(_t(images, dev), c, s, _t(rot, dev))
+    want = want.cpu().numpy()
+    other = rng.randint(0, 256, size=images.shape, dtype=np.uint8)
+    ctx = codec.HostContext(0, scratch_bytes=32 << 20)    # several chunks per slot
+    try:
+        sent = {}
+        pinned = torch.from_numpy(images).pin_memory()
+        for mode, src in (("full", images), ("roi", images), ("roi_kernel", pinned.numpy()),
+                          ("roi_kernel", images)):      # pageable: falls back to "roi"
+            ctx.topdown_affine(other, boxes, cfg["image_size"], rot=rot, use_udp=use_udp,
+                               upload="full")             # poison the scratch
+            crops, hc, hsc = ctx.topdown_affine(src, boxes, cfg["image_size"], rot=rot,
+                                                use_udp=use_udp, upload=mode)
+            key = mode + ("_pageable" if mode == "roi_kernel" and src is images else "")
+            sent[key] = ctx.last_transfer_bytes()
+            bad = [i for i in range(n) if not np.array_equal(crops[i], want[i])]
+            assert not bad, (key, bad)
+            assert np.array_equal(hc, c.cpu().numpy()) and np.array_equal(hsc, s.cpu().numpy())
+        assert sent["full"][0] >= images.size
+        assert sent["roi"][0] < sent["roi_kernel"][0] < sent["full"][0]   # 64-byte row spans
+        assert sent["roi_kernel_pageable"][0] == sent["roi"][0]
+        with pytest.raises(ValueError):
+            ctx.topdown_affine(images, boxes, cfg["image_size"], upload="some")
+    finally:
+        ctx.close()
+
+
 # --------------------------------------------------------------------- encode
 @pytest.mark.parametrize("cfg", [synth.TOPDOWN_CONFIG, synth.TOPDOWN_CONFIG_384])
 @pytest.mark.parametrize("use_udp", [False, True])
