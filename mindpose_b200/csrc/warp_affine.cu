@@ -374,13 +374,14 @@ __device__ __forceinline__ RowCtx make_row(int Y, int hs, int ws, uint32_t ws3, 
 // pair with the channel's two bytes, paired up by a byte permute of the realigned words.
 // ROWAL: the source row pitch is a multiple of 4 bytes, so the run has the same alignment
 // in both rows and the lower row's words are the upper row's plus the pitch.
+// Interior pixel: all four taps inside the image and the aligned words of the run inside
+// the buffer (the caller has checked sx against [rc.sx_lo, rc.sx_lo + rc.sx_span]).
 template <bool ROWAL>
-__device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
-                                                const uint8_t* __restrict__ base4, int hs,
-                                                int ws, uint32_t ws3, int X, const RowCtx rc) {
+__device__ __forceinline__ uint32_t warp_pixel3_interior(const uint8_t* __restrict__ base4,
+                                                         uint32_t ws3, int X, const RowCtx rc) {
   const int sx = X >> 5;
-  const int fx = X & 31, fy = rc.fy, sy = rc.sy;
-  if ((uint32_t)(sx - rc.sx_lo) <= rc.sx_span) {
+  const int fx = X & 31, fy = rc.fy;
+  {
     const uint32_t off = rc.off + (uint32_t)sx * 3u;
     Six a, b;
     if (ROWAL) {
@@ -403,16 +404,27 @@ __device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
     const uint32_t wg = (32u - (uint32_t)fx) | ((uint32_t)fx << 16);
     const uint32_t arg = __byte_perm(a.lo, a.hi, 0x4130), abb = __byte_perm(a.lo, a.hi, 0x0052);
     const uint32_t brg = __byte_perm(b.lo, b.hi, 0x4130), bbb = __byte_perm(b.lo, b.hi, 0x0052);
-    const uint32_t a0 = __dp2a_lo(wg, arg, 0u), a1 = __dp2a_hi(wg, arg, 0u);
-    const uint32_t a2 = __dp2a_lo(wg, abb, 0u);
-    const uint32_t b0 = __dp2a_lo(wg, brg, 0u), b1 = __dp2a_hi(wg, brg, 0u);
-    const uint32_t b2 = __dp2a_lo(wg, bbb, 0u);
+    // The vertical weights are folded into the weight pairs: both 16-bit halves of wg scale
+    // by gy (uy) in one multiply without a carry between them (products <= 1024), so each
+    // channel is two chained dot products -- the same integer sum as blending horizontally,
+    // then vertically.
     const uint32_t gy = 32u - (uint32_t)fy, uy = (uint32_t)fy;
-    const uint32_t c0 = (gy * a0 + uy * b0 + 512u) >> 10;
-    const uint32_t c1 = (gy * a1 + uy * b1 + 512u) >> 10;
-    const uint32_t c2 = (gy * a2 + uy * b2 + 512u) >> 10;
+    const uint32_t wt = wg * gy, wu = wg * uy;
+    const uint32_t c0 = __dp2a_lo(wu, brg, __dp2a_lo(wt, arg, 512u)) >> 10;
+    const uint32_t c1 = __dp2a_hi(wu, brg, __dp2a_hi(wt, arg, 512u)) >> 10;
+    const uint32_t c2 = __dp2a_lo(wu, bbb, __dp2a_lo(wt, abb, 512u)) >> 10;
     return __byte_perm(__byte_perm(c0, c1, 0x0040), c2, 0x5410);  // byte 3 = high byte of c2 = 0
   }
+}
+
+template <bool ROWAL>
+__device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
+                                                const uint8_t* __restrict__ base4, int hs,
+                                                int ws, uint32_t ws3, int X, const RowCtx rc) {
+  const int sx = X >> 5;
+  const int fx = X & 31, fy = rc.fy, sy = rc.sy;
+  if ((uint32_t)(sx - rc.sx_lo) <= rc.sx_span)
+    return warp_pixel3_interior<ROWAL>(base4, ws3, X, rc);
   if (sx >= ws || sx + 1 < 0 || sy >= hs || sy + 1 < 0) return 0u;
   const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy);
   const int w10 = (32 - fx) * fy, w11 = fx * fy;
@@ -442,7 +454,10 @@ struct NormArgs {
 //   (mindpose/data/data_factory.py:127-138) -- fused into the store: float32 CHW planes,
 //   (pixel - mean[c]) / std[c] in float32, one 16-byte store per channel and thread
 //   (dst_w % 4 == 0).  The uint8 crop is never written.
-template <bool NORM>
+// QUAD (rotation-free crops of the uint8 variant): the fixed-point column deltas are monotone
+// in x, so a quad whose first and last pixel are interior is interior as a whole -- one range
+// test per quad, and the four pixels' tap loads sit in one basic block.
+template <bool NORM, bool QUAD>
 __global__ void __launch_bounds__(kWarpThreads)
     warp_affine_u8x3_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
                             const int32_t* __restrict__ src_hw, const double* __restrict__ inv,
@@ -514,7 +529,23 @@ __global__ void __launch_bounds__(kWarpThreads)
         RowCtx ra;
         ra.sy = rw.x, ra.fy = rw.y, ra.sx_lo = rw.z, ra.sx_span = (uint32_t)rw.w;
         ra.off = s_rowoff[ry];
-        if (rowal) {
+        const int Xa = (X0 + ad.x) >> 5, Xd = (X0 + ad.w) >> 5;
+        const int sx_min = min(Xa, Xd) >> 5, sx_max = max(Xa, Xd) >> 5;
+        if (QUAD && (uint32_t)(sx_min - ra.sx_lo) <= ra.sx_span &&
+            (uint32_t)(sx_max - ra.sx_lo) <= ra.sx_span) {
+          const int Xb = (X0 + ad.y) >> 5, Xc = (X0 + ad.z) >> 5;
+          if (rowal) {
+            p0 = warp_pixel3_interior<true>(base4, ws3, Xa, ra);
+            p1 = warp_pixel3_interior<true>(base4, ws3, Xb, ra);
+            p2 = warp_pixel3_interior<true>(base4, ws3, Xc, ra);
+            p3 = warp_pixel3_interior<true>(base4, ws3, Xd, ra);
+          } else {
+            p0 = warp_pixel3_interior<false>(base4, ws3, Xa, ra);
+            p1 = warp_pixel3_interior<false>(base4, ws3, Xb, ra);
+            p2 = warp_pixel3_interior<false>(base4, ws3, Xc, ra);
+            p3 = warp_pixel3_interior<false>(base4, ws3, Xd, ra);
+          }
+        } else if (rowal) {
           p0 = warp_pixel3<true>(img, base4, hs, ws, ws3, (X0 + ad.x) >> 5, ra);
           p1 = warp_pixel3<true>(img, base4, hs, ws, ws3, (X0 + ad.y) >> 5, ra);
           p2 = warp_pixel3<true>(img, base4, hs, ws, ws3, (X0 + ad.z) >> 5, ra);
@@ -674,7 +705,7 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
     const int tiles3 = (p->dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
     const int64_t grid3 = n * tiles3;
     PC_REQUIRE(grid3 < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_warp_affine_u8: batch too large");
-    warp_affine_u8x3_kernel<false><<<(unsigned)grid3, kWarpThreads, 0, st>>>(
+    warp_affine_u8x3_kernel<false, true><<<(unsigned)grid3, kWarpThreads, 0, st>>>(
         d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3,
         make_fastdiv((uint32_t)(p->dst_w >> 2)), NormArgs());
     PC_CUDA(cudaGetLastError());
@@ -728,7 +759,7 @@ extern "C" int pc_warp_affine_u8_norm_chw(const uint8_t* d_src, const int64_t* d
     na.mean[c] = p->mean[c];
     na.std[c] = p->std[c];
   }
-  warp_affine_u8x3_kernel<true><<<(unsigned)grid3, kWarpThreads, 0, (cudaStream_t)stream>>>(
+  warp_affine_u8x3_kernel<true, false><<<(unsigned)grid3, kWarpThreads, 0, (cudaStream_t)stream>>>(
       d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3,
       make_fastdiv((uint32_t)(p->dst_w >> 2)), na);
   PC_CUDA(cudaGetLastError());
