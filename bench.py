@@ -2,7 +2,9 @@
 """bench.py -- heatmap-codec throughput on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload hrnet_eval|sb_r50|udp_w48] [--crops C]
+                    [--crops C] [--upload full|roi|roi_kernel] [--nccl-gather]
+
+(the other BASELINE configs are parity-test cases and rows of scripts/kbench.py, not bench lines)
 
 One "step" is one pass of the hot path over one batch of synthetic input.
 Default workload (BASELINE.json configs[1], "HRNet-W32 256x192 top-down eval
