@@ -5,4 +5,4 @@ run "4096 plain flip noise 20"
 run "4096 plain noflip noise 20"
 run "8192 orig flip noise 20"
 run "8192 shift noflip noise 20"
-timeout 300 python scripts/stress_decode.py 4096 30 2>&1 | tail -14
+timeout 300 python tests/stress/stress_decode.py 4096 30 2>&1 | tail -14

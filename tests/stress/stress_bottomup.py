@@ -1,12 +1,12 @@
 """Randomised parity stress of pc_bottomup_decode (pair kernel shapes) against the oracle.
-Development aid: python scripts/stress_bottomup.py [cases]"""
+Development aid: python tests/stress/stress_bottomup.py [cases]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import mindpose_b200 as mp  # noqa: E402
 from mindpose_b200 import bottomup, synth  # noqa: E402

@@ -1,12 +1,12 @@
 """Randomised parity stress of pc_oks_nms against the oracle (hard + soft, ties, iou vis_thr).
-Development aid: python scripts/stress_nms.py [cases]"""
+Development aid: python tests/stress/stress_nms.py [cases]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from mindpose_b200 import nms as dnms  # noqa: E402
 from oracle import gen_golden_nms as ggn  # noqa: E402

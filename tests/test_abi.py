@@ -98,6 +98,14 @@ def test_argument_errors_raise_value_error_without_gpu(lib):
     b.sigma, b.tag_per_joint = 2.0, 1
     with pytest.raises(ValueError, match="exeeds the maximum num"):  # the reference's message
         _lib.call("pc_bottomup_encode", 0, 0, 0, ctypes.byref(b), 1, 0)
+    # host-buffer front end: argument checks come before any CUDA call
+    with pytest.raises(ValueError, match="ctx is NULL"):
+        _lib.call("pc_ctx_last_transfer_bytes", None, None, None)
+    a = _lib.AffineHostParams(480, 640, 3, 192, 256, 200.0, 1.25, 0, _lib.UPLOAD_ROI)
+    with pytest.raises(ValueError, match="NULL pointer"):
+        _lib.call("pc_crop_source_rect", None, ctypes.c_float(0.0), ctypes.byref(a), None)
+    with pytest.raises(ValueError, match="ctx / params is NULL"):
+        _lib.call("pc_topdown_affine_host", None, 0, 0, 0, 0, 0, 0, ctypes.byref(a), 1)
 
 
 def test_missing_library_fails_loudly(monkeypatch):
