@@ -305,7 +305,10 @@ int pc_scatter_results(const float* d_preds, const float* d_boxes, void* const* 
 /* ---- host-buffer front end (what the e2e number is measured through) ----
  * Same decode as pc_topdown_decode but every pointer is a HOST pointer.  The
  * context owns device scratch and two streams; crops are streamed through in
- * chunks so the host->device copy of chunk i+1 overlaps the kernel of chunk i. */
+ * chunks so the host->device copy of chunk i+1 overlaps the kernel of chunk i.
+ * A context serves one call at a time (one per host thread; any number of
+ * contexts may exist); the *_host calls return after their results are in the
+ * host buffers. */
 typedef struct pc_ctx pc_ctx;
 int pc_ctx_create(int device, int64_t scratch_bytes, pc_ctx** out);
 int pc_ctx_destroy(pc_ctx* ctx);
