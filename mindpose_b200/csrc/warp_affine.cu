@@ -457,6 +457,9 @@ struct NormArgs {
 // QUAD (rotation-free crops of the uint8 variant): the fixed-point column deltas are monotone
 // in x, so a quad whose first and last pixel are interior is interior as a whole -- one range
 // test per quad, and the four pixels' tap loads sit in one basic block.
+#ifndef PC_WARP_COLUMN_MAP
+#define PC_WARP_COLUMN_MAP 0
+#endif
 template <bool NORM, bool QUAD>
 __global__ void __launch_bounds__(kWarpThreads)
     warp_affine_u8x3_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
@@ -514,6 +517,43 @@ __global__ void __launch_bounds__(kWarpThreads)
     __syncthreads();
   }
 
+#if PC_WARP_COLUMN_MAP
+  // Experiment for round 2 (off, unmeasured: DESIGN.md section 9).  Rotation-free crops whose
+  // width is a multiple of 32: a lane owns ONE output column and four rows of it, so the 32
+  // lanes of a tap load read 5.7 bytes apart instead of 23 (5.8 instead of 15-17 sectors per
+  // load: scripts/warp_sector_model.py) and the per-column X offset is shared by four pixels.
+  // A row's 32 pixels (96 bytes) are packed into 24 words with one shuffle per lane.
+  if (!NORM && axis && (dst_w & 31) == 0) {
+    const int groups = dst_w >> 5, rgroups = (rows + 3) >> 2;
+    for (int item = warp; item < groups * rgroups; item += kWarpThreads / 32) {
+      const int rq = item / groups, g = item - rq * groups;
+      const int x = (g << 5) + lane;
+      const int ad = s_adelta[x];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ry = 4 * rq + j;
+        if (ry >= rows) break;  // warp-uniform
+        const int4 rw = s_rowa[ry];
+        RowCtx ra;
+        ra.sy = rw.x, ra.fy = rw.y, ra.sx_lo = rw.z, ra.sx_span = (uint32_t)rw.w;
+        ra.off = s_rowoff[ry];
+        const int X = (s_x0[ry] + ad) >> 5;
+        const uint32_t p = rowal ? warp_pixel3<true>(img, base4, hs, ws, ws3, X, ra)
+                                 : warp_pixel3<false>(img, base4, hs, ws, ws3, X, ra);
+        // bytes of four neighbouring pixels p0 p1 p2 p3 (24 bits each) as three words:
+        // word k of the group = (p_k >> 8k) | (p_{k+1} << (24 - 8k)), k = 0, 1, 2
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, p, 1);
+        const int k = lane & 3;
+        if (k < 3) {
+          const uint32_t w = (p >> (8 * k)) | (nxt << (24 - 8 * k));
+          uint8_t* o = out + ((size_t)ry * dst_w + (g << 5)) * 3 + (((lane >> 2) * 3 + k) << 2);
+          asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(o), "r"(w) : "memory");
+        }
+      }
+    }
+    return;
+  }
+#endif
   for (int base = warp * 32; base < nquads; base += kWarpThreads) {
     const int t = base + lane;
     uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
