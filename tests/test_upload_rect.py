@@ -53,6 +53,33 @@ def test_rectangle_contains_every_sampled_pixel(use_udp, image_size):
     assert saved > 0   # the rectangle is not simply the whole image
 
 
+@pytest.mark.parametrize("use_udp", [False, True])
+def test_rectangle_for_extreme_boxes_and_right_angles(use_udp):
+    """Tiny boxes (a few source pixels blown up to the whole crop), boxes much larger than
+    the image, right-angle rotations, another scale_padding."""
+    rng = np.random.RandomState(7 + use_udp)
+    hs, ws = 72, 96
+    image = rng.randint(1, 256, size=(hs, ws, 3), dtype=np.uint8)
+    cases = [([40.3, 30.2, 1.0, 1.4], 0.0), ([10.0, 10.0, 2.5, 2.5], 37.0),
+             ([-300.0, -200.0, 900.0, 700.0], 0.0), ([-300.0, -200.0, 900.0, 700.0], 45.0),
+             ([20.0, 15.0, 50.0, 40.0], 90.0), ([20.0, 15.0, 50.0, 40.0], -90.0),
+             ([20.0, 15.0, 50.0, 40.0], 180.0), ([20.0, 15.0, 50.0, 40.0], 270.0),
+             ([0.0, 0.0, 96.0, 72.0], 0.0), ([95.0, 71.0, 3.0, 3.0], 0.0),
+             ([-2.0, -2.0, 4.0, 4.0], 12.0), ([60.0, 5.0, 30.0, 66.0], -33.3)]
+    for box, rot in cases:
+        for pad in (1.25, 1.0):
+            x0, y0, x1, y1 = _rect(box, rot, hs, ws, (48, 64), use_udp, scale_padding=pad)
+            c, sc = affine.box_to_center_scale(tuple(np.asarray(box, np.float32)),
+                                               np.array((48, 64)), scale_padding=pad)
+            m = (affine.udp_matrix(c, sc, rot, np.array((48, 64))) if use_udp
+                 else affine.affine_matrix(c, sc, rot, np.array((48, 64))))
+            want = warp.warp_affine_u8(image, m, (48, 64))
+            poisoned = rng.randint(0, 256, size=image.shape, dtype=np.uint8)
+            if x1 > x0 and y1 > y0:
+                poisoned[y0:y1, x0:x1] = image[y0:y1, x0:x1]
+            assert np.array_equal(warp.warp_affine_u8(poisoned, m, (48, 64)), want), (box, rot, pad)
+
+
 def test_rectangle_is_tight_for_an_axis_aligned_crop():
     # 100 x 133.33 box -> 125 x 166.7 source pixels around (150, 200)
     x0, y0, x1, y1 = _rect([100, 133.333, 100, 133.333], 0.0, 480, 640, (192, 256), False)
