@@ -226,6 +226,9 @@ static bool crop_source_rect(const float* box, float rot_deg, const pc_affine_ho
   // a degenerate box gives a singular matrix, whose "inverse" (all zeros in cv::warpAffine)
   // samples pixel (0, 0) for the whole crop: not a rectangle around the box
   if (!(sw >= 1.0 && sh >= 1.0)) return false;
+  // the device computes centre and scale in float32: beyond 1e5 pixels its rounding (ulp
+  // 0.008 at 1e5) is no longer small against the padding
+  if (!(fabs(cx) <= 1e5 && fabs(cy) <= 1e5 && sw <= 1e5 && sh <= 1e5)) return false;
   // half sizes of the sampled rectangle along the crop's own axes, in source pixels
   const double a = 0.5 * sw;
   const double b = p->use_udp ? 0.5 * sh : 0.5 * sw * (double)p->image_h / (double)p->image_w;

@@ -98,6 +98,11 @@ def test_rectangle_edge_cases():
         _rect([float("nan"), 0, 10, 10], 0.0, 240, 320, (192, 256), False)
     with pytest.raises(ValueError):
         _rect([0, 0, float("inf"), 10], 0.0, 240, 320, (192, 256), False)
+    # coordinates where the device's float32 centre / scale round by more than the padding allows
+    with pytest.raises(ValueError):
+        _rect([3e5, 0, 10, 10], 0.0, 240, 320, (192, 256), False)
+    with pytest.raises(ValueError):
+        _rect([0, 0, 2e5, 10], 0.0, 240, 320, (192, 256), False)
     # degenerate: the singular matrix's "inverse" samples pixel (0, 0), not the box
     with pytest.raises(ValueError):
         _rect([100, 100, 0, 0], 0.0, 240, 320, (192, 256), False)
