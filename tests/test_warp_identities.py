@@ -58,3 +58,16 @@ def test_column_deltas_are_monotone_so_a_quad_is_bounded_by_its_end_pixels():
     q = sx[: 1024 // 4 * 4].reshape(-1, 4)
     assert (np.minimum(q[:, 0], q[:, 3]) == q.min(1)).all()
     assert (np.maximum(q[:, 0], q[:, 3]) == q.max(1)).all()
+
+
+def test_three_word_packing_of_four_pixels_from_one_neighbour():
+    """Column-per-lane mapping (PC_WARP_COLUMN_MAP): lane k of a group of
+    four holds pixel p_k = r | g << 8 | b << 16 and its right neighbour's; word k of the
+    group's 12 output bytes is (p_k >> 8k) | (p_{k+1} << (24 - 8k)) for k = 0, 1, 2."""
+    rng = np.random.RandomState(3)
+    rgb = rng.randint(0, 256, size=(1000, 4, 3), dtype=np.uint8)
+    p = (rgb[..., 0].astype(np.uint64) | (rgb[..., 1].astype(np.uint64) << 8)
+         | (rgb[..., 2].astype(np.uint64) << 16))
+    words = np.stack([((p[:, k] >> (8 * k)) | (p[:, k + 1] << (24 - 8 * k))) & 0xFFFFFFFF
+                      for k in range(3)], axis=1).astype("<u4")
+    assert np.array_equal(words.view(np.uint8).reshape(1000, 12), rgb.reshape(1000, 12))
