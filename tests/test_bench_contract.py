@@ -51,3 +51,31 @@ def test_reference_arm_line_has_the_contract_keys():
     ours = _latest("r*_bench.json")
     assert d["metric"] == ours["metric"] and d["unit"] == ours["unit"]
     assert d["config"]["workload"] == ours["config"]["workload"]
+
+
+def test_reference_arm_runs_on_rank_0_only():
+    """Under torchrun the reference arm prints on rank 0; the other ranks exit 0 without work
+    (no CUDA, no process group)."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--gpus", "2", "--steps", "1", "--warmup", "1"], env=env,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == ""
+
+
+def test_our_arm_fails_loudly_without_a_gpu():
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.is_available():
+        return  # on the GPU box the arm runs; the driver times it
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
+    assert r.stdout.strip() == ""   # no line, and certainly no CPU-fallback number
