@@ -517,43 +517,6 @@ __global__ void __launch_bounds__(kWarpThreads)
     __syncthreads();
   }
 
-#if PC_WARP_COLUMN_MAP
-  // Experiment for round 2 (off, unmeasured: DESIGN.md section 9).  Rotation-free crops whose
-  // width is a multiple of 32: a lane owns ONE output column and four rows of it, so the 32
-  // lanes of a tap load read 5.7 bytes apart instead of 23 (5.8 instead of 15-17 sectors per
-  // load: scripts/warp_sector_model.py) and the per-column X offset is shared by four pixels.
-  // A row's 32 pixels (96 bytes) are packed into 24 words with one shuffle per lane.
-  if (!NORM && axis && (dst_w & 31) == 0) {
-    const int groups = dst_w >> 5, rgroups = (rows + 3) >> 2;
-    for (int item = warp; item < groups * rgroups; item += kWarpThreads / 32) {
-      const int rq = item / groups, g = item - rq * groups;
-      const int x = (g << 5) + lane;
-      const int ad = s_adelta[x];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ry = 4 * rq + j;
-        if (ry >= rows) break;  // warp-uniform
-        const int4 rw = s_rowa[ry];
-        RowCtx ra;
-        ra.sy = rw.x, ra.fy = rw.y, ra.sx_lo = rw.z, ra.sx_span = (uint32_t)rw.w;
-        ra.off = s_rowoff[ry];
-        const int X = (s_x0[ry] + ad) >> 5;
-        const uint32_t p = rowal ? warp_pixel3<true>(img, base4, hs, ws, ws3, X, ra)
-                                 : warp_pixel3<false>(img, base4, hs, ws, ws3, X, ra);
-        // bytes of four neighbouring pixels p0 p1 p2 p3 (24 bits each) as three words:
-        // word k of the group = (p_k >> 8k) | (p_{k+1} << (24 - 8k)), k = 0, 1, 2
-        const uint32_t nxt = __shfl_down_sync(0xffffffffu, p, 1);
-        const int k = lane & 3;
-        if (k < 3) {
-          const uint32_t w = (p >> (8 * k)) | (nxt << (24 - 8 * k));
-          uint8_t* o = out + ((size_t)ry * dst_w + (g << 5)) * 3 + (((lane >> 2) * 3 + k) << 2);
-          asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(o), "r"(w) : "memory");
-        }
-      }
-    }
-    return;
-  }
-#endif
   for (int base = warp * 32; base < nquads; base += kWarpThreads) {
     const int t = base + lane;
     uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
@@ -665,6 +628,96 @@ __global__ void __launch_bounds__(kWarpThreads)
   }
 }
 
+#if PC_WARP_COLUMN_MAP
+// Experiment for round 2 (off, unmeasured: DESIGN.md section 9).  Crops whose width is a
+// multiple of 32: a lane owns ONE output column and four rows of it, so the 32 lanes of a tap
+// load read 5.7 bytes apart instead of 23 (5.8 instead of 15-17 sectors per load:
+// scripts/warp_sector_model.py) and the per-column X offset is shared by four pixels.  A row's
+// 32 pixels (96 bytes) are packed into 24 words with one shuffle per lane.  Rotated crops
+// (training-time augmentation) take a plain per-pixel loop.  44 registers, 4.5 KB shared memory.
+__global__ void __launch_bounds__(kWarpThreads)
+    warp_affine_u8x3_cols_kernel(const uint8_t* __restrict__ src,
+                                 const int64_t* __restrict__ src_off,
+                                 const int32_t* __restrict__ src_hw,
+                                 const double* __restrict__ inv, uint8_t* __restrict__ dst,
+                                 int dst_w, int dst_h, int tiles_per_crop) {
+  __shared__ int s_adelta[kWarpMaxDstW];
+  __shared__ int s_x0[kWarp3TileRows];
+  __shared__ int s_y0[kWarp3TileRows];
+  __shared__ int4 s_rowa[kWarp3TileRows];
+  __shared__ uint32_t s_rowoff[kWarp3TileRows];
+  const int64_t crop = blockIdx.x / tiles_per_crop;
+  const int tile = blockIdx.x - (int)(crop * tiles_per_crop);
+  const int row0 = tile * kWarp3TileRows;
+  const int rows = min(kWarp3TileRows, dst_h - row0);
+  const double* m = inv + 6 * crop;
+  const double m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5];
+  // rint(m10 * x * 1024) is 0 for every column iff it is for the last one (monotone)
+  const bool axis =
+      __double2int_rn(__dmul_rn(__dmul_rn(m10, (double)(dst_w - 1)), 1024.0)) == 0;
+  const int hs = src_hw[2 * crop], ws = src_hw[2 * crop + 1];
+  const uint8_t* img = src + src_off[crop];
+  const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(img) & 3u);
+  const uint8_t* base4 = img - delta;
+  const uint32_t ws3 = (uint32_t)ws * 3u;
+  for (int x = threadIdx.x; x < dst_w; x += blockDim.x)
+    s_adelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m00, (double)x), 1024.0));
+  if (threadIdx.x < rows) {
+    const double y = (double)(row0 + threadIdx.x);
+    s_x0[threadIdx.x] =
+        __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m01, y), m02), 1024.0)) + 16;
+    const int y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m11, y), m12), 1024.0)) + 16;
+    s_y0[threadIdx.x] = y0;
+    const RowCtx rc = make_row(y0 >> 5, hs, ws, ws3, delta);
+    s_rowa[threadIdx.x] = make_int4(rc.sy, rc.fy, rc.sx_lo, (int)rc.sx_span);
+    s_rowoff[threadIdx.x] = rc.off;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* out = dst + ((size_t)crop * dst_h + row0) * dst_w * 3;
+  if (!axis) {  // rotated crop: plain per-pixel path
+    for (int t = threadIdx.x; t < rows * dst_w; t += kWarpThreads) {
+      const int ry = t / dst_w, x = t - ry * dst_w;
+      const int bd = __double2int_rn(__dmul_rn(__dmul_rn(m10, (double)x), 1024.0));
+      const RowCtx rc = make_row((s_y0[ry] + bd) >> 5, hs, ws, ws3, delta);
+      const uint32_t p =
+          warp_pixel3<false>(img, base4, hs, ws, ws3, (s_x0[ry] + s_adelta[x]) >> 5, rc);
+      uint8_t* o = out + (size_t)t * 3;
+      o[0] = (uint8_t)p, o[1] = (uint8_t)(p >> 8), o[2] = (uint8_t)(p >> 16);
+    }
+    return;
+  }
+  const bool rowal = (ws3 & 3u) == 0;
+  const int groups = dst_w >> 5, rgroups = (rows + 3) >> 2;
+  for (int item = warp; item < groups * rgroups; item += kWarpThreads / 32) {
+    const int rq = item / groups, g = item - rq * groups;
+    const int ad = s_adelta[(g << 5) + lane];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ry = 4 * rq + j;
+      if (ry >= rows) break;  // warp-uniform
+      const int4 rw = s_rowa[ry];
+      RowCtx ra;
+      ra.sy = rw.x, ra.fy = rw.y, ra.sx_lo = rw.z, ra.sx_span = (uint32_t)rw.w;
+      ra.off = s_rowoff[ry];
+      const int X = (s_x0[ry] + ad) >> 5;
+      const uint32_t p = rowal ? warp_pixel3<true>(img, base4, hs, ws, ws3, X, ra)
+                               : warp_pixel3<false>(img, base4, hs, ws, ws3, X, ra);
+      // bytes of four neighbouring pixels p0 p1 p2 p3 (24 bits each) as three words:
+      // word k of the group = (p_k >> 8k) | (p_{k+1} << (24 - 8k)), k = 0, 1, 2
+      // (tests/test_warp_identities.py)
+      const uint32_t nxt = __shfl_down_sync(0xffffffffu, p, 1);
+      const int k = lane & 3;
+      if (k < 3) {
+        const uint32_t w = (p >> (8 * k)) | (nxt << (24 - 8 * k));
+        uint8_t* o = out + ((size_t)ry * dst_w + (g << 5)) * 3 + (((lane >> 2) * 3 + k) << 2);
+        asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(o), "r"(w) : "memory");
+      }
+    }
+  }
+}
+#endif  // PC_WARP_COLUMN_MAP
+
 }  // namespace pc
 
 using namespace pc;
@@ -745,6 +798,14 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
     const int tiles3 = (p->dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
     const int64_t grid3 = n * tiles3;
     PC_REQUIRE(grid3 < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_warp_affine_u8: batch too large");
+#if PC_WARP_COLUMN_MAP
+    if (p->dst_w % 32 == 0) {
+      warp_affine_u8x3_cols_kernel<<<(unsigned)grid3, kWarpThreads, 0, st>>>(
+          d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3);
+      PC_CUDA(cudaGetLastError());
+      return PC_OK;
+    }
+#endif
     warp_affine_u8x3_kernel<false, true><<<(unsigned)grid3, kWarpThreads, 0, st>>>(
         d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3,
         make_fastdiv((uint32_t)(p->dst_w >> 2)), NormArgs());
