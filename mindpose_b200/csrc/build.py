@@ -46,8 +46,19 @@ def _nvcc() -> str:
     return exe
 
 
+def _extra_defines():
+    """Experiment switches (e.g. ``PC_NVCC_DEFINES="-DPC_WARP_COLUMN_MAP=1"``): part of the
+    fingerprint, so a library built with them is rebuilt by the next plain build()."""
+    extra = os.environ.get("PC_NVCC_DEFINES", "").split()
+    bad = [d for d in extra if not d.startswith("-D")]
+    if bad:
+        raise RuntimeError(f"PC_NVCC_DEFINES may only hold -D switches, got {bad}")
+    return extra
+
+
 def _fingerprint() -> str:
     h = hashlib.sha256()
+    h.update(" ".join(_extra_defines()).encode())
     for rel in SOURCES + HEADERS + ["build.py"]:
         with open(os.path.join(HERE, rel), "rb") as f:
             h.update(f.read())
@@ -66,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *_extra_defines(), "-c", os.path.join(HERE, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []
