@@ -15,6 +15,7 @@ for sec in decode encode warp bottomup bu_encode refine nms sweep; do
     >> $out/${tag}_kbench.log 2>&1 || echo "kbench $sec failed/timeout rc=$?" >> $out/${tag}_kbench.log
 done
 cat $out/${tag}_kbench.log
+timeout 200 python scripts/e2e_upload_ab.py > $out/${tag}_upload_ab.log 2>&1 || echo "upload A/B failed rc=$?"
 timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 echo "bench exit $?"; cat $out/${tag}_bench.json; tail -3 $out/${tag}_bench.err
 if [ "$2" = "ncu" ]; then
