@@ -6,49 +6,62 @@ Same contract as the reference's ``mindpose/register.py:12-59``:
   ``obj.__name__`` and, when given, under ``extra_name`` as well (``:20-36``);
 * registering a name twice logs a warning and the newer object wins (``:13-14``);
 * ``entrypoint(module, name)`` returns the object or raises ``ValueError``
-  listing what is known (``:49-59``);
+  listing what is known (``:49-59``; the message text, typos included, is the
+  reference's, because callers and tests match on it);
 * ``list_modules()`` / ``list_components(module)`` return sorted names.
 """
 import logging
 from typing import Any, Callable, Dict, List
 
-_REGISTRY: Dict[str, Dict[str, Callable[..., Any]]] = {}
+Component = Callable[..., Any]
 
 
-def _file(module_name: str, name: str, obj: Callable[..., Any]) -> None:
-    table = _REGISTRY.setdefault(module_name, {})
-    if name in table:
-        logging.warning(f"`{name}` is already registered")
-    table[name] = obj
+class _Registry:
+    """module name -> {component name -> object}; one instance per process."""
 
+    def __init__(self) -> None:
+        self._tables: Dict[str, Dict[str, Component]] = {}
 
-def register(module_name: str, extra_name: str = "") -> Callable[..., Any]:
-    def decorate(obj: Callable[..., Any]) -> Callable[..., Any]:
-        _file(module_name, obj.__name__, obj)
-        if extra_name:
-            _file(module_name, extra_name, obj)
+    def add(self, module: str, names, obj: Component) -> Component:
+        table = self._tables.setdefault(module, {})
+        for name in names:
+            if name in table:
+                logging.warning(f"`{name}` is already registered")
+            table[name] = obj
         return obj
 
-    return decorate
+    def modules(self) -> List[str]:
+        return sorted(self._tables)
+
+    def components(self, module: str) -> List[str]:
+        return sorted(self._tables.get(module, ()))
+
+    def lookup(self, module: str, name: str) -> Component:
+        table = self._tables.get(module)
+        if table is None:
+            raise ValueError(f"Unkown module `{module}`. Supported modules: {self.modules()}")
+        try:
+            return table[name]
+        except KeyError:
+            raise ValueError(f"Unkown components `{name}`. Supported componetns in "
+                             f"`{module}`: {self.components(module)}") from None
+
+
+_REGISTRY = _Registry()
+
+
+def register(module_name: str, extra_name: str = "") -> Callable[[Component], Component]:
+    names = lambda obj: [obj.__name__] + ([extra_name] if extra_name else [])  # noqa: E731
+    return lambda obj: _REGISTRY.add(module_name, names(obj), obj)
 
 
 def list_modules() -> List[str]:
-    return sorted(_REGISTRY)
+    return _REGISTRY.modules()
 
 
 def list_components(module: str) -> List[str]:
-    return sorted(_REGISTRY.get(module, {}))
+    return _REGISTRY.components(module)
 
 
-def entrypoint(module_name: str, component_name: str) -> Callable[..., Any]:
-    if module_name not in _REGISTRY:
-        raise ValueError(
-            f"Unkown module `{module_name}`. Supported modules: {list_modules()}"
-        )
-    table = _REGISTRY[module_name]
-    if component_name not in table:
-        raise ValueError(
-            f"Unkown components `{component_name}`. "
-            f"Supported componetns in `{module_name}`: {list_components(module_name)}"
-        )
-    return table[component_name]
+def entrypoint(module_name: str, component_name: str) -> Component:
+    return _REGISTRY.lookup(module_name, component_name)
