@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PC_VERSION 100 /* 0.1.0 */
+#define PC_VERSION 101 /* 0.1.1 */
 
 typedef enum pc_status {
   PC_OK = 0,
@@ -283,10 +283,21 @@ typedef struct pc_oks_nms_params {
   float iou_vis_thr;       /* oks_iou vis_thr: joints of the DETECTION above it (nms.py:64) */
   int32_t max_people_per_image; /* >= max_i(offset[i+1] - offset[i]); <= PC_NMS_MAX_PEOPLE */
   double sigmas[PC_MAX_JOINTS];
+  double rescore_vis_thr_f64; /* pc_oks_nms_f64 only: the thresholds as Python floats */
+  double iou_vis_thr_f64;
 } pc_oks_nms_params;
 int pc_oks_nms(const float* d_kpts, const float* d_area, float* d_score,
                const int32_t* d_image_offset, int32_t* d_keep, int32_t* d_num_keep,
                const pc_oks_nms_params* params, int64_t num_images, void* stream);
+/* The same for records that hold Python floats, which is what the reference's inferencer
+ * emits (`pred.tolist()`, `box.tolist()`: mindpose/engine/inferencer/topdown_inferencer.py:
+ * 135-140): numpy then runs the rescoring, dx**2 + dy**2, the areas and the sort keys in
+ * float64 (the OKS values stay float32, nms.py:56).  d_kpts f64 [P,K,3], d_area f64 [P],
+ * d_score f64 [P]; thresholds from the *_f64 fields (oks_thr stays float32: it is only
+ * compared with float32 OKS values). */
+int pc_oks_nms_f64(const double* d_kpts, const double* d_area, double* d_score,
+                   const int32_t* d_image_offset, int32_t* d_keep, int32_t* d_num_keep,
+                   const pc_oks_nms_params* params, int64_t num_images, void* stream);
 
 /* ---- E: all-gather of the decoded keypoints over peer memory --------------
  * Not in the reference (it evaluates on rank 0, mindpose/callbacks/eval_callback.py:

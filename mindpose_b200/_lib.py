@@ -35,7 +35,9 @@ PC_ERR_CUDA = -3
 PC_ERR_NO_DEVICE = -4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libposecodec.so")
+# POSECODEC_LIB: development override used to A/B two builds of the library in one session
+# (scripts/gpu_ab.sh); it must still be a libposecodec build -- every symbol is checked on load.
+LIB_PATH = os.environ.get("POSECODEC_LIB") or os.path.join(_HERE, "csrc", "libposecodec.so")
 
 
 class BoxParams(Structure):
@@ -162,6 +164,8 @@ class OksNmsParams(Structure):
         ("iou_vis_thr", c_float),
         ("max_people_per_image", c_int32),
         ("sigmas", ctypes.c_double * PC_MAX_JOINTS),
+        ("rescore_vis_thr_f64", c_double),
+        ("iou_vis_thr_f64", c_double),
     ]
 
 
@@ -212,6 +216,7 @@ SIGNATURES = {
     ),
     "pc_refine_missing": (c_int, [_P, _P, _P, _P, _P, POINTER(RefineParams), c_int64, _P]),
     "pc_oks_nms": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(OksNmsParams), c_int64, _P]),
+    "pc_oks_nms_f64": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(OksNmsParams), c_int64, _P]),
     "pc_scatter_results": (
         c_int, [_P, _P, POINTER(c_void_p), c_int32, _P, c_int64, c_int32, c_int64, _P]),
     "pc_ctx_create": (c_int, [c_int, c_int64, POINTER(c_void_p)]),

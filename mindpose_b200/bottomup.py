@@ -33,22 +33,29 @@ def decode(decoder, heatmap: List[torch.Tensor], tagging_heatmap: List[torch.Ten
         raise ValueError("the CUDA decoder supports with_ae_loss=[True, False], tag_per_joint=True")
     if len(heatmap) != stages or len(tagging_heatmap) != 1:
         raise ValueError("expected one heatmap per stage and one tag map")
-    # recover the contiguous network outputs the views were sliced from
-    if raw is not None:
-        out0 = raw[0]
-        out1 = raw[1] if stages == 2 else None
-    else:
-        out0 = heatmap[0]._base if heatmap[0]._base is not None else None
-        out1 = None
-        if stages == 2:
-            out1 = heatmap[1]._base if heatmap[1]._base is not None else heatmap[1]
-    if out0 is None or not _same_storage_view(heatmap[0], out0, 0) \
-            or not _same_storage_view(tagging_heatmap[0], out0, k) or out0.shape[1] != 2 * k:
+    # recover the contiguous first-stage output the two views were sliced from; a candidate
+    # (the caller's `raw[0]` or the view's base) is only used when both views are provably
+    # its channel slices -- same pointer arithmetic, strides, N, H and W
+    out0 = raw[0] if raw is not None else heatmap[0]._base
+    if out0 is None or out0.dim() != 4 or out0.shape[1] != 2 * k \
+            or not _same_storage_view(heatmap[0], out0, 0) \
+            or not _same_storage_view(tagging_heatmap[0], out0, k):
         # views of something else: pack heat | tag into one contiguous tensor
         out0 = torch.cat([heatmap[0], tagging_heatmap[0]], dim=1).contiguous()
+    out1 = None
     if stages == 2:
-        if out1 is None or out1.shape[1] != k or not out1.is_contiguous():
-            out1 = heatmap[1].contiguous()
+        # the second stage is one tensor of K channels: the view itself is what is decoded
+        # (a batch-sliced view has a contiguous base of the same K channels but other images,
+        # so the base is never substituted for it)
+        out1 = heatmap[1]
+        if raw is not None and _same_storage_view(out1, raw[1], 0) and raw[1].shape[1] == k:
+            out1 = raw[1]
+        if out1.dim() != 4 or out1.shape[1] != k:
+            raise ValueError(f"heatmap[1] must be [N, {k}, H, W]")
+        if not out1.is_contiguous():
+            out1 = out1.contiguous()
+        if out1.shape[0] != out0.shape[0]:
+            raise ValueError("heatmap[0] and heatmap[1] hold different numbers of images")
     for t in (out0, out1):
         if t is not None and (not t.is_cuda or t.dtype != torch.float32):
             raise ValueError("network outputs must be float32 CUDA tensors")

@@ -65,18 +65,31 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """variant: build an experiment library next to the shipped one
+    (libposecodec_<variant>.so, objects under build/<variant>/; select it at run time with
+    POSECODEC_LIB) without touching libposecodec.so or its stamp."""
+    if variant:
+        return _build_into(os.path.join(HERE, f"libposecodec_{variant}.so"),
+                           os.path.join(HERE, "build", variant), verbose)
     fp = _fingerprint()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as f:
             if f.read().strip() == fp:
                 return LIB
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    _build_into(LIB, os.path.join(HERE, "build"), verbose)
+    with open(STAMP, "w") as f:
+        f.write(fp)
+    return LIB
+
+
+def _build_into(lib_path: str, obj_dir: str, verbose: bool) -> str:
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, *_extra_defines(), "-c", os.path.join(HERE, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -86,23 +99,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, _ = p.communicate()
         log.append(f"== {src} ==\n{out}")
         failed |= p.returncode != 0
-    with open(os.path.join(HERE, "build", "nvcc.log"), "w") as f:
+    with open(os.path.join(obj_dir, "nvcc.log"), "w") as f:
         f.write("\n".join(log))
     if verbose or failed:
         print("\n".join(log))
     if failed:
-        raise RuntimeError("nvcc failed; see mindpose_b200/csrc/build/nvcc.log")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
+        raise RuntimeError(f"nvcc failed; see {os.path.join(obj_dir, 'nvcc.log')}")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path, *objs,
             "-Xlinker", "--exclude-libs,ALL"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         print(r.stdout)
-        raise RuntimeError("link of libposecodec.so failed")
-    with open(STAMP, "w") as f:
-        f.write(fp)
-    return LIB
+        raise RuntimeError(f"link of {os.path.basename(lib_path)} failed")
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    variant = ""
+    if "--variant" in sys.argv:
+        variant = sys.argv[sys.argv.index("--variant") + 1]
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=variant)
     print(path)

@@ -81,6 +81,11 @@ struct pc_ctx {
   float* d_small[2];  // center | scale | score | preds | boxes per chunk
   int64_t small_floats;
   int64_t last_h2d_bytes, last_d2h_bytes;  // of the last *_host call
+  // host-side tables of pc_topdown_affine_host (offsets, sizes, fetch jobs of one chunk)
+  int64_t* h_off;
+  int32_t* h_hw;
+  int4* h_jobs;
+  int64_t h_cap;
 };
 
 static const int64_t kMaxChunkCrops = 1 << 16;
@@ -127,6 +132,9 @@ extern "C" int pc_ctx_destroy(pc_ctx* c) {
     if (c->d_maps[s]) cudaFree(c->d_maps[s]);
     if (c->d_small[s]) cudaFree(c->d_small[s]);
   }
+  free(c->h_off);
+  free(c->h_hw);
+  free(c->h_jobs);
   delete c;
   return PC_OK;
 }
@@ -167,9 +175,9 @@ extern "C" int pc_topdown_decode_host(pc_ctx* c, const float* h_heatmap, const f
              (long long)crop_bytes);
   c->last_h2d_bytes = n * (crop_bytes + 5 * (int64_t)sizeof(float));
   c->last_d2h_bytes = n * (K * 3 + 6) * (int64_t)sizeof(float);
-  int rc = PC_OK;
-  int slot = 0;
-  for (int64_t i0 = 0; i0 < n && rc == PC_OK; i0 += chunk, slot ^= 1) {
+  // One chunk: every failure returns from the lambda only, so that the two streams are
+  // always drained below before the caller gets its host buffers back.
+  auto run_chunk = [&](int64_t i0, int slot) -> int {
     const int64_t m = (n - i0 < chunk) ? n - i0 : chunk;
     cudaStream_t st = c->stream[slot];
     float* d_hm = reinterpret_cast<float*>(c->d_maps[slot]);
@@ -190,13 +198,19 @@ extern "C" int pc_topdown_decode_host(pc_ctx* c, const float* h_heatmap, const f
                             cudaMemcpyHostToDevice, st));
     PC_CUDA(cudaMemcpyAsync(d_score, h_score + i0, sizeof(float) * m, cudaMemcpyHostToDevice,
                             st));
-    rc = pc_topdown_decode(d_hm, d_fl, d_center, d_scale, d_score, d_preds, d_boxes, p, m, st);
-    if (rc != PC_OK) break;
+    const int rc =
+        pc_topdown_decode(d_hm, d_fl, d_center, d_scale, d_score, d_preds, d_boxes, p, m, st);
+    if (rc != PC_OK) return rc;
     PC_CUDA(cudaMemcpyAsync(h_all_preds + i0 * K * 3, d_preds, sizeof(float) * m * K * 3,
                             cudaMemcpyDeviceToHost, st));
     PC_CUDA(cudaMemcpyAsync(h_all_boxes + i0 * 6, d_boxes, sizeof(float) * m * 6,
                             cudaMemcpyDeviceToHost, st));
-  }
+    return PC_OK;
+  };
+  int rc = PC_OK;
+  int slot = 0;
+  for (int64_t i0 = 0; i0 < n && rc == PC_OK; i0 += chunk, slot ^= 1) rc = run_chunk(i0, slot);
+  // single exit: copies and kernels already enqueued may still touch the caller's buffers
   cudaError_t e0 = cudaStreamSynchronize(c->stream[0]);
   cudaError_t e1 = cudaStreamSynchronize(c->stream[1]);
   if (rc != PC_OK) return rc;
@@ -331,21 +345,21 @@ extern "C" int pc_topdown_affine_host(pc_ctx* c, const uint8_t* h_images, const 
   pc_box_params bp = {p->image_w, p->image_h, p->pixel_std, p->scale_padding};
   pc_affine_params ap = {p->image_w, p->image_h, p->pixel_std, p->use_udp};
   pc_warp_params wp = {p->image_w, p->image_h, p->channels};
-  // offsets / sizes are the same for every chunk: build once on the host
-  static thread_local int64_t* h_off = nullptr;
-  static thread_local int32_t* h_hw = nullptr;
-  static thread_local int4* h_jobs = nullptr;
-  static thread_local int64_t h_cap = 0;
-  if (h_cap < chunk) {
-    free(h_off);
-    free(h_hw);
-    free(h_jobs);
-    h_off = (int64_t*)malloc(sizeof(int64_t) * chunk);
-    h_hw = (int32_t*)malloc(sizeof(int32_t) * 2 * chunk);
-    h_jobs = (int4*)malloc(sizeof(int4) * chunk);
-    h_cap = chunk;
+  // offsets / sizes are the same for every chunk: build once on the host (tables owned by
+  // the context, freed by pc_ctx_destroy)
+  if (c->h_cap < chunk) {
+    free(c->h_off);
+    free(c->h_hw);
+    free(c->h_jobs);
+    c->h_off = (int64_t*)malloc(sizeof(int64_t) * chunk);
+    c->h_hw = (int32_t*)malloc(sizeof(int32_t) * 2 * chunk);
+    c->h_jobs = (int4*)malloc(sizeof(int4) * chunk);
+    c->h_cap = (c->h_off && c->h_hw && c->h_jobs) ? chunk : 0;
   }
-  PC_REQUIRE(h_off && h_hw && h_jobs, PC_ERR_CUDA, "pc_topdown_affine_host: out of host memory");
+  int64_t* const h_off = c->h_off;
+  int32_t* const h_hw = c->h_hw;
+  int4* const h_jobs = c->h_jobs;
+  PC_REQUIRE(c->h_cap >= chunk, PC_ERR_CUDA, "pc_topdown_affine_host: out of host memory");
   // the fetch kernel needs the device mapping of a page-locked source and 16-byte geometry
   const int64_t pitch = (int64_t)p->src_w * p->channels;
   int upload = p->upload;
@@ -364,9 +378,10 @@ extern "C" int pc_topdown_affine_host(pc_ctx* c, const uint8_t* h_images, const 
   int64_t h2d = n * (int64_t)(16 + (h_rot ? 4 : 0) + 8 + 8);
   c->last_h2d_bytes = 0;
   c->last_d2h_bytes = n * (dst_bytes + (h_center ? 8 : 0) + (h_scale ? 8 : 0));
-  int rc = PC_OK;
-  int slot = 0;
-  for (int64_t i0 = 0; i0 < n && rc == PC_OK; i0 += chunk, slot ^= 1) {
+  // One chunk (failures return from the lambda only: the streams are drained below).  The
+  // pageable h_jobs / h_off / h_hw tables may be rewritten for the next chunk at once:
+  // cudaMemcpyAsync from pageable memory returns after staging the source.
+  auto run_chunk = [&](int64_t i0, int slot) -> int {
     const int64_t m = (n - i0 < chunk) ? n - i0 : chunk;
     cudaStream_t st = c->stream[slot];
     unsigned char* base = c->d_maps[slot];
@@ -436,12 +451,12 @@ extern "C" int pc_topdown_affine_host(pc_ctx* c, const uint8_t* h_images, const 
       PC_CUDA(cudaMemcpyAsync(d_rot, h_rot + i0, sizeof(float) * m, cudaMemcpyHostToDevice, st));
     PC_CUDA(cudaMemcpyAsync(d_off, h_off, sizeof(int64_t) * m, cudaMemcpyHostToDevice, st));
     PC_CUDA(cudaMemcpyAsync(d_hw, h_hw, sizeof(int32_t) * 2 * m, cudaMemcpyHostToDevice, st));
-    rc = pc_box_to_center_scale(d_boxes, d_center, d_scale, &bp, m, st);
+    int rc = pc_box_to_center_scale(d_boxes, d_center, d_scale, &bp, m, st);
     if (rc == PC_OK)
       rc = pc_affine_matrices(d_center, d_scale, h_rot ? d_rot : nullptr, d_fwd, d_inv, &ap, m,
                               st);
     if (rc == PC_OK) rc = pc_warp_affine_u8(d_src, d_off, d_hw, d_inv, d_dst, &wp, m, st);
-    if (rc != PC_OK) break;
+    if (rc != PC_OK) return rc;
     PC_CUDA(cudaMemcpyAsync(h_crops + i0 * dst_bytes, d_dst, (size_t)(m * dst_bytes),
                             cudaMemcpyDeviceToHost, st));
     if (h_center)
@@ -450,8 +465,13 @@ extern "C" int pc_topdown_affine_host(pc_ctx* c, const uint8_t* h_images, const 
     if (h_scale)
       PC_CUDA(cudaMemcpyAsync(h_scale + 2 * i0, d_scale, sizeof(float) * 2 * m,
                               cudaMemcpyDeviceToHost, st));
-  }
+    return PC_OK;
+  };
+  int rc = PC_OK;
+  int slot = 0;
+  for (int64_t i0 = 0; i0 < n && rc == PC_OK; i0 += chunk, slot ^= 1) rc = run_chunk(i0, slot);
   c->last_h2d_bytes = h2d;
+  // single exit: copies and kernels already enqueued may still touch the caller's buffers
   cudaError_t e0 = cudaStreamSynchronize(c->stream[0]);
   cudaError_t e1 = cudaStreamSynchronize(c->stream[1]);
   if (rc != PC_OK) return rc;

@@ -24,17 +24,20 @@ def rescore_and_nms(kpts: torch.Tensor, area: torch.Tensor, score: torch.Tensor,
                     oks_thr: float, rescore_vis_thr: Optional[float] = None, use_nms: bool = True,
                     soft: bool = False, max_dets: int = 20, sigmas=None,
                     iou_vis_thr: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """One ``pc_oks_nms`` launch over all images.
+    """One ``pc_oks_nms`` / ``pc_oks_nms_f64`` launch over all images.
 
-    kpts f32 [P,K,3], area f32 [P], score f32 [P] (rescored IN PLACE when
-    ``rescore_vis_thr`` is given), image_offset i32 [I+1]; all CUDA tensors.
+    kpts [P,K,3], area [P], score [P] (rescored IN PLACE when ``rescore_vis_thr`` is given),
+    all float32 or all float64 -- the precision numpy would compute in for the caller's
+    records: float32 ndarrays stay float32, Python floats (``.tolist()`` records, what the
+    reference's inferencer emits) are float64; image_offset i32 [I+1]; all CUDA tensors.
     Returns (keep i32 [P], num_keep i32 [I]): per image the kept people as local indices in
     keep order, padded with -1."""
     for t, name in ((kpts, "kpts"), (area, "area"), (score, "score"), (image_offset, "image_offset")):
         if not (isinstance(t, torch.Tensor) and t.is_cuda):
             raise ValueError(f"`{name}` must be a CUDA tensor (there is no CPU fallback)")
-    if kpts.dtype != torch.float32 or area.dtype != torch.float32 or score.dtype != torch.float32:
-        raise ValueError("kpts, area and score must be float32")
+    if kpts.dtype not in (torch.float32, torch.float64) or area.dtype != kpts.dtype \
+            or score.dtype != kpts.dtype:
+        raise ValueError("kpts, area and score must be all float32 or all float64")
     if image_offset.dtype != torch.int32:
         raise ValueError("image_offset must be int32")
     if kpts.dim() != 3 or kpts.shape[2] != 3:
@@ -53,9 +56,10 @@ def rescore_and_nms(kpts: torch.Tensor, area: torch.Tensor, score: torch.Tensor,
     p.soft = int(bool(soft))
     p.max_dets = int(max_dets)
     p.use_iou_vis_thr = int(iou_vis_thr is not None)
-    p.rescore_vis_thr = float(rescore_vis_thr) if rescore_vis_thr is not None else 0.0
+    p.rescore_vis_thr = p.rescore_vis_thr_f64 = \
+        float(rescore_vis_thr) if rescore_vis_thr is not None else 0.0
     p.oks_thr = float(oks_thr)
-    p.iou_vis_thr = float(iou_vis_thr) if iou_vis_thr is not None else 0.0
+    p.iou_vis_thr = p.iou_vis_thr_f64 = float(iou_vis_thr) if iou_vis_thr is not None else 0.0
     p.max_people_per_image = int(max_people_per_image)
     for j in range(k):
         p.sigmas[j] = float(sig[j])
@@ -63,19 +67,33 @@ def rescore_and_nms(kpts: torch.Tensor, area: torch.Tensor, score: torch.Tensor,
     keep = torch.empty(people, dtype=torch.int32, device=dev)
     num_keep = torch.empty(max(num_images, 0), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        _lib.call("pc_oks_nms", _lib.device_ptr(kpts), _lib.device_ptr(area),
+        entry = "pc_oks_nms_f64" if kpts.dtype == torch.float64 else "pc_oks_nms"
+        _lib.call(entry, _lib.device_ptr(kpts), _lib.device_ptr(area),
                   _lib.device_ptr(score), _lib.device_ptr(image_offset), _lib.device_ptr(keep),
                   _lib.device_ptr(num_keep), ctypes.byref(p), num_images, _lib.current_stream())
     return keep, num_keep
+
+
+def _numpy_precision(*arrays) -> np.dtype:
+    """float32 only if numpy itself would stay in float32 for every input (all float32
+    ndarrays / scalars); anything else -- Python floats, float64, a mix -- is float64.  (In a
+    mix numpy would keep the float32 parts in float32 a little longer; the kernel widens
+    first, a difference of at most one float32 ulp in dx, dy before squaring.)"""
+    return np.dtype(np.float32) if all(a.dtype == np.float32 for a in arrays) \
+        else np.dtype(np.float64)
 
 
 def _single_image(kpts_db, thr, soft, max_dets, sigmas, vis_thr, device):
     if not kpts_db:
         return []
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-    kpts = np.stack([np.asarray(k["keypoints"], dtype=np.float32).reshape(-1, 3) for k in kpts_db])
-    area = np.asarray([k["area"] for k in kpts_db], dtype=np.float32)
-    score = np.asarray([k["score"] for k in kpts_db], dtype=np.float32)
+    # exactly the arrays the reference builds (nms.py:92-94); their dtype is the precision
+    kpts = np.array([np.asarray(k["keypoints"]).flatten() for k in kpts_db])
+    area = np.array([k["area"] for k in kpts_db])
+    score = np.array([k["score"] for k in kpts_db])
+    dt = _numpy_precision(kpts, area, score)
+    kpts = np.ascontiguousarray(kpts.reshape(len(kpts_db), -1, 3), dtype=dt)
+    area, score = area.astype(dt), score.astype(dt)
     n = len(kpts_db)
     off = torch.tensor([0, n], dtype=torch.int32, device=dev)
     keep, num = rescore_and_nms(torch.from_numpy(kpts).to(dev), torch.from_numpy(area).to(dev),
@@ -121,10 +139,14 @@ def evaluate_records(records: Sequence[Dict[str, Any]], config: Dict[str, Any], 
         return []
     counts = [len(g) for g in groups]
     offset = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
-    kpts = torch.from_numpy(np.stack([np.asarray(r["pred"], dtype=np.float32) for r in flat])).to(dev)
-    boxes = np.stack([np.asarray(r["box"], dtype=np.float32) for r in flat])
-    area = torch.from_numpy(np.ascontiguousarray(boxes[:, 4])).to(dev)
-    score = torch.from_numpy(np.ascontiguousarray(boxes[:, 5])).to(dev)
+    # records as the inferencer emits them hold Python lists (`.tolist()`): the reference then
+    # computes in float64; float32 ndarrays stay float32 (see _numpy_precision)
+    kp_np = np.stack([np.asarray(r["pred"]) for r in flat])
+    boxes = np.stack([np.asarray(r["box"]) for r in flat])
+    dt = _numpy_precision(kp_np, boxes)
+    kpts = torch.from_numpy(np.ascontiguousarray(kp_np, dtype=dt)).to(dev)
+    area = torch.from_numpy(np.ascontiguousarray(boxes[:, 4], dtype=dt)).to(dev)
+    score = torch.from_numpy(np.ascontiguousarray(boxes[:, 5], dtype=dt)).to(dev)
     keep, num = rescore_and_nms(
         kpts, area, score, torch.from_numpy(offset).to(dev), max(counts),
         oks_thr=config["oks_thr"], rescore_vis_thr=config["vis_thr"],

@@ -50,7 +50,12 @@ def nms_people(seed, people, k=17):
     return kpts, areas, scores
 
 
-def _kpts_db(kpts, areas, scores):
+def _kpts_db(kpts, areas, scores, as_lists=False):
+    """as_lists: Python lists / floats, what records look like after the inferencer's
+    ``.tolist()`` (topdown_inferencer.py:135-140) -- numpy then computes in float64."""
+    if as_lists:
+        return [dict(keypoints=kpts[p].tolist(), area=float(areas[p]), score=float(scores[p]))
+                for p in range(len(kpts))]
     return [dict(keypoints=kpts[p], area=areas[p], score=scores[p]) for p in range(len(kpts))]
 
 
@@ -81,8 +86,7 @@ def run_reference_eval(records, name2id, cfg, num_joints=17):
     got = {}
 
     def capture(valid_kpts, path):
-        got["kept"] = [[(int(p["bbox_id"]), np.float32(p["score"])) for p in img]
-                       for img in valid_kpts]
+        got["kept"] = [[(int(p["bbox_id"]), p["score"]) for p in img] for img in valid_kpts]
         raise _Captured()
 
     ev._write_coco_keypoint_results = capture
@@ -94,9 +98,10 @@ def run_reference_eval(records, name2id, cfg, num_joints=17):
     return got["kept"]
 
 
-def eval_records(images, max_people, seed, k=17):
-    """Inference records as the top-down inferencer emits them
-    (topdown_inferencer.py:111-131): pred f32 [k,3], box f32 [6], bbox_id, image_path.
+def eval_records(images, max_people, seed, k=17, as_lists=False):
+    """Inference records: pred [k,3], box [6], bbox_id, image_path.  as_lists=True gives them
+    exactly as the top-down inferencer emits them (``pred.tolist()``, ``box.tolist()``,
+    topdown_inferencer.py:135-140); False keeps float32 ndarrays.
     Some bbox_ids are duplicated (flip-test style repeats)."""
     rng = np.random.RandomState(seed)
     records = []
@@ -118,7 +123,10 @@ def eval_records(images, max_people, seed, k=17):
                 records.append(dup)
             bbox_id += 1
     order = rng.permutation(len(records))
-    return [records[i] for i in order]
+    records = [records[i] for i in order]
+    if as_lists:
+        records = [dict(r, pred=r["pred"].tolist(), box=r["box"].tolist()) for r in records]
+    return records
 
 
 def main():
@@ -134,6 +142,14 @@ def main():
             ref.nms.soft_oks_nms(db, thr, max_dets=20, sigmas=sig, vis_thr=vthr), dtype=np.int64)
         flat = kpts.reshape(people, -1)
         out[f"nms{ci}_iou"] = ref.nms.oks_iou(flat[0], flat, areas[0], areas, sig, vthr)
+        dbl = _kpts_db(kpts, areas, scores, as_lists=True)      # float64 arithmetic
+        out[f"nmsL{ci}_keep"] = np.asarray(ref.nms.oks_nms(dbl, thr, sigmas=sig, vis_thr=vthr),
+                                           dtype=np.int64)
+        out[f"nmsL{ci}_soft"] = np.asarray(
+            ref.nms.soft_oks_nms(dbl, thr, max_dets=20, sigmas=sig, vis_thr=vthr), dtype=np.int64)
+        f64 = flat.astype(np.float64)
+        out[f"nmsL{ci}_iou"] = ref.nms.oks_iou(f64[0], f64, float(areas[0]),
+                                               areas.astype(np.float64), sig, vthr)
     sigmas = (np.array([.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1.07, 1.07,
                         .87, .87, .89, .89]) / 10.0).tolist()
     for ci, (images, max_people, seed, soft) in enumerate(EVAL_CASES):
@@ -144,6 +160,12 @@ def main():
         out[f"eval{ci}_counts"] = np.asarray([len(img) for img in kept], dtype=np.int64)
         out[f"eval{ci}_bbox_ids"] = np.asarray([b for img in kept for b, _ in img], dtype=np.int64)
         out[f"eval{ci}_scores"] = np.asarray([s for img in kept for _, s in img], dtype=np.float32)
+        # the same records as lists (the inferencer's own format): float64 rescoring and NMS
+        kept = run_reference_eval(eval_records(images, max_people, seed, as_lists=True), name2id,
+                                  cfg)
+        out[f"evalL{ci}_counts"] = np.asarray([len(img) for img in kept], dtype=np.int64)
+        out[f"evalL{ci}_bbox_ids"] = np.asarray([b for img in kept for b, _ in img], dtype=np.int64)
+        out[f"evalL{ci}_scores"] = np.asarray([s for img in kept for _, s in img], dtype=np.float64)
     path = os.path.join(ROOT, "tests", "golden", "nms_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in list(out.items())[:6]})

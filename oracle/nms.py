@@ -11,6 +11,15 @@ PINNED: ``oracle/gen_golden_nms.py`` runs the unmodified reference functions (im
 from /root/reference) on seeded inputs; ``tests/test_oracle_nms.py`` checks this module
 against the stored outputs.
 
+Precision.  The reference computes in whatever dtype its records hold.  The inferencer emits
+``pred.tolist()`` / ``box.tolist()`` (topdown_inferencer.py:135-140): Python floats, so the
+evaluator's rescoring, ``dx**2 + dy**2``, the areas and the sort keys run in float64
+(``dtype=np.float64`` below, the CUDA entry ``pc_oks_nms_f64``).  Records holding float32
+ndarrays stay in float32 where numpy does (``dtype=np.float32``, ``pc_oks_nms``).  The notes
+below are written for float32; for float64 read "float64" for every "float32" except the OKS
+values themselves (``ious = np.zeros(..., dtype=np.float32)``, nms.py:56), the comparisons with
+``thr`` and the soft-NMS weight ``np.exp(-(overlap**2) / thr)``, which stay float32.
+
 Arithmetic notes (NumPy >= 2 promotion rules, the rules of the numpy this image and the
 golden vectors use; under NumPy 1.x ``0 + np.float32`` is float64 and the rescored
 scores differ in the last float32 bit):
@@ -39,23 +48,24 @@ COCO_SIGMAS = np.array([.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1
                         .87, .87, .89, .89]) / 10.0
 
 
-def rescore(preds, box_scores, vis_thr):
-    """preds f32 [P,K,3], box_scores f32 [P] -> rescored f32 [P]
+def rescore(preds, box_scores, vis_thr, dtype=F32):
+    """preds [P,K,3], box_scores [P] -> rescored [P], all `dtype`
     (topdown_evaluator.py:96-110)."""
-    preds = np.asarray(preds, dtype=F32)
-    out = np.zeros(len(preds), dtype=F32)
-    thr = F32(vis_thr)
+    T = np.dtype(dtype).type
+    preds = np.asarray(preds, dtype=T)
+    out = np.zeros(len(preds), dtype=T)
+    thr = T(vis_thr)
     for p in range(len(preds)):
-        acc = F32(0)
+        acc = T(0)
         cnt = 0
         for j in range(preds.shape[1]):
             t = preds[p, j, 2]
             if t > thr:
-                acc = F32(acc + t)
+                acc = T(acc + t)
                 cnt += 1
         if cnt:
-            acc = F32(acc / F32(cnt))
-        out[p] = F32(acc * F32(box_scores[p]))
+            acc = T(acc / T(cnt))
+        out[p] = T(acc * T(box_scores[p]))
     return out
 
 
@@ -91,22 +101,23 @@ def _pairwise_sum(a):
     return res
 
 
-def oks_iou(g, d, a_g, a_d, sigmas=None, vis_thr=None):
-    """g f32 [3K], d f32 [n,3K], a_g f32, a_d f32 [n] -> f32 [n] (nms.py:7-69)."""
+def oks_iou(g, d, a_g, a_d, sigmas=None, vis_thr=None, dtype=F32):
+    """g [3K], d [n,3K], a_g, a_d [n] (all `dtype`) -> f32 [n] (nms.py:7-69)."""
+    T = np.dtype(dtype).type
     sig = np.asarray(COCO_SIGMAS if sigmas is None else sigmas, dtype=np.float64)
     key_vars = (sig * 2) ** 2
-    g = np.asarray(g, dtype=F32)
-    d = np.asarray(d, dtype=F32).reshape(-1, g.size)
+    g = np.asarray(g, dtype=T)
+    d = np.asarray(d, dtype=T).reshape(-1, g.size)
     xg, yg = g[0::3], g[1::3]
     out = np.zeros(len(d), dtype=F32)
     for n in range(len(d)):
-        dx = (d[n, 0::3] - xg).astype(F32)
-        dy = (d[n, 1::3] - yg).astype(F32)
-        sq = (dx * dx + dy * dy).astype(F32)
-        area = np.float64(F32(F32(F32(a_g) + F32(a_d[n])) / F32(2))) + np.spacing(1)
+        dx = (d[n, 0::3] - xg).astype(T)
+        dy = (d[n, 1::3] - yg).astype(T)
+        sq = (dx * dx + dy * dy).astype(T)
+        area = np.float64(T(T(T(a_g) + T(a_d[n])) / T(2))) + np.spacing(1)
         e = sq.astype(np.float64) / key_vars / area / 2
         if vis_thr is not None:
-            e = e[d[n, 2::3] > F32(vis_thr)]
+            e = e[d[n, 2::3] > T(vis_thr)]
         out[n] = _pairwise_sum(np.exp(-e)) / len(e) if e.size else 0.0
     return out
 
@@ -116,34 +127,39 @@ def _argsort_desc(scores):
     return np.argsort(scores, kind="stable")[::-1]
 
 
-def oks_nms(kpts, areas, scores, thr, sigmas=None, vis_thr=None):
-    """kpts f32 [P,3K], areas f32 [P], scores f32 [P] -> kept indices (nms.py:72-111)."""
+def oks_nms(kpts, areas, scores, thr, sigmas=None, vis_thr=None, dtype=F32):
+    """kpts [P,3K], areas [P], scores [P] (all `dtype`) -> kept indices (nms.py:72-111)."""
     if len(scores) == 0:
         return np.zeros(0, dtype=np.int64)
-    order = _argsort_desc(np.asarray(scores))
+    kpts, areas = np.asarray(kpts, dtype=dtype), np.asarray(areas, dtype=dtype)
+    order = _argsort_desc(np.asarray(scores, dtype=dtype))
     keep = []
     while order.size > 0:
         i = order[0]
         keep.append(i)
-        ovr = oks_iou(kpts[i], kpts[order[1:]], areas[i], areas[order[1:]], sigmas, vis_thr)
+        ovr = oks_iou(kpts[i], kpts[order[1:]], areas[i], areas[order[1:]], sigmas, vis_thr,
+                      dtype)
         order = order[np.where(ovr <= F32(thr))[0] + 1]
     return np.asarray(keep, dtype=np.int64)
 
 
-def soft_oks_nms(kpts, areas, scores, thr, max_dets=20, sigmas=None, vis_thr=None):
+def soft_oks_nms(kpts, areas, scores, thr, max_dets=20, sigmas=None, vis_thr=None, dtype=F32):
     """-> kept indices, at most max_dets (nms.py:141-190; gaussian rescoring :114-138)."""
     if len(scores) == 0:
         return np.zeros(0, dtype=np.int64)
-    scores = np.asarray(scores, dtype=F32)
+    T = np.dtype(dtype).type
+    kpts, areas = np.asarray(kpts, dtype=T), np.asarray(areas, dtype=T)
+    scores = np.asarray(scores, dtype=T)
     order = _argsort_desc(scores)
     scores = scores[order]
     keep = []
     while order.size > 0 and len(keep) < max_dets:
         i = order[0]
-        ovr = oks_iou(kpts[i], kpts[order[1:]], areas[i], areas[order[1:]], sigmas, vis_thr)
+        ovr = oks_iou(kpts[i], kpts[order[1:]], areas[i], areas[order[1:]], sigmas, vis_thr, T)
         order = order[1:]
+        # the weight is float32 (the OKS values are); the product takes the scores' precision
         w = np.exp((-(ovr * ovr).astype(F32) / F32(thr)).astype(np.float64)).astype(F32)
-        scores = (scores[1:] * w).astype(F32)
+        scores = (scores[1:] * w.astype(T)).astype(T)
         tmp = _argsort_desc(scores)
         order = order[tmp]
         scores = scores[tmp]
@@ -151,10 +167,19 @@ def soft_oks_nms(kpts, areas, scores, thr, max_dets=20, sigmas=None, vis_thr=Non
     return np.asarray(keep, dtype=np.int64)
 
 
+def records_dtype(records):
+    """float32 when every record holds float32 ndarrays, else float64 (Python floats from
+    ``.tolist()``, float64 arrays): the dtype numpy computes in for such records."""
+    ok = all(np.asarray(r["pred"]).dtype == F32 and np.asarray(r["box"]).dtype == F32
+             for r in records)
+    return F32 if ok else np.float64
+
+
 def evaluate_records(records, vis_thr, oks_thr, use_nms=True, soft_nms=False, sigmas=None):
     """``TopDownEvaluator.eval`` up to the result file (topdown_evaluator.py:78-121):
     group the inference records by image (first-seen order), sort / de-duplicate by
     bbox_id, rescore, NMS.  -> per image: list of (bbox_id, rescored score) in keep order."""
+    T = records_dtype(records)
     by_image = {}
     for rec in records:
         by_image.setdefault(rec["image_path"].split("/")[-1], []).append(rec)
@@ -162,12 +187,13 @@ def evaluate_records(records, vis_thr, oks_thr, use_nms=True, soft_nms=False, si
     for recs in by_image.values():
         ids = np.asarray([r["bbox_id"] for r in recs])
         recs = [recs[i] for i in sort_and_unique(ids)]
-        preds = np.stack([np.asarray(r["pred"], dtype=F32) for r in recs])
-        boxes = np.stack([np.asarray(r["box"], dtype=F32) for r in recs])
-        scores = rescore(preds, boxes[:, 5], vis_thr)
+        preds = np.stack([np.asarray(r["pred"], dtype=T) for r in recs])
+        boxes = np.stack([np.asarray(r["box"], dtype=T) for r in recs])
+        scores = rescore(preds, boxes[:, 5], vis_thr, T)
         if use_nms:
             fn = soft_oks_nms if soft_nms else oks_nms
-            keep = fn(preds.reshape(len(recs), -1), boxes[:, 4], scores, oks_thr, sigmas=sigmas)
+            keep = fn(preds.reshape(len(recs), -1), boxes[:, 4], scores, oks_thr, sigmas=sigmas,
+                      dtype=T)
         else:
             keep = np.arange(len(recs))
         out.append([(int(recs[i]["bbox_id"]), scores[i]) for i in keep])

@@ -65,6 +65,31 @@ def test_decode_single_stage_and_public_decode(cuda_device):
         assert np.array_equal(g.cpu().numpy(), w)
 
 
+def test_decode_accepts_batch_sliced_views(cuda_device):
+    """`decode()` on views cut out of a larger batch (big[2:4]): the contiguous base of such
+    a view holds OTHER images, so it must never be read in place of the view."""
+    n, k, h0 = 6, 17, 32
+    d = synth.bottomup_outputs(n, k, h0, h0, mask_hw=(128, 128), seed=11, max_people=4)
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3, max_num=30)
+    big0, big1 = _t(d["out0"], cuda_device), _t(d["out1"], cuda_device)
+    mask = _t(d["mask"], cuda_device)
+    sl = slice(2, 4)
+    want = bd.decode([d["out0"][sl], d["out1"][sl]], d["mask"][sl], use_nms=True, nms_kernel=3,
+                     max_num=30)
+    heat, tag = dec.decouple_output([big0[sl], big1[sl]])
+    got = dec.decode(heat, tag, mask[sl])
+    for g, w in zip(got, want):
+        assert np.array_equal(g.cpu().numpy(), w)
+    # a channel-sliced second stage (not contiguous) is packed, not misread
+    wide = torch.cat([big1, big1.flip(1)], dim=1)
+    heat2 = [heat[0], wide[sl, :k]]
+    got = dec.decode(heat2, tag, mask[sl])
+    for g, w in zip(got, want):
+        assert np.array_equal(g.cpu().numpy(), w)
+    with pytest.raises(ValueError):
+        dec.decode([heat[0], big1[0:3]], tag, mask[sl])        # image counts differ
+
+
 def test_decode_ties_and_flat_maps(cuda_device):
     """Constant / all-zero planes: every pixel survives NMS, top-k = lowest indices."""
     n, k, h0 = 1, 17, 16

@@ -35,6 +35,35 @@ def test_evaluator_flow_matches_reference_golden(cuda_device, golden, ci):
                           g[f"eval{ci}_scores"])
 
 
+@pytest.mark.parametrize("ci", range(len(ggn.NMS_CASES)))
+def test_oks_nms_list_records_match_reference_golden(cuda_device, golden, ci):
+    """Python-float records (the inferencer's `.tolist()` format): numpy, and so
+    pc_oks_nms_f64, computes in float64."""
+    g = golden("nms_ref.npz")
+    people, seed, thr, vthr = ggn.NMS_CASES[ci]
+    kpts, areas, scores = ggn.nms_people(seed, people)
+    db = ggn._kpts_db(kpts, areas, scores, as_lists=True)
+    assert np.array_equal(dnms.oks_nms(db, thr, vis_thr=vthr, device=cuda_device), g[f"nmsL{ci}_keep"])
+    assert np.array_equal(dnms.soft_oks_nms(db, thr, max_dets=20, vis_thr=vthr, device=cuda_device),
+                          g[f"nmsL{ci}_soft"])
+
+
+@pytest.mark.parametrize("ci", range(len(ggn.EVAL_CASES)))
+def test_evaluator_flow_list_records_match_reference_golden(cuda_device, golden, ci):
+    """The records exactly as TopDownHeatMapInferencer emits them: rescored float64 scores
+    bit-exact vs TopDownEvaluator.eval of the unmodified reference."""
+    g = golden("nms_ref.npz")
+    images, max_people, seed, soft = ggn.EVAL_CASES[ci]
+    records = ggn.eval_records(images, max_people, seed, as_lists=True)
+    cfg = dict(vis_thr=0.2, oks_thr=0.9, use_nms=True, soft_nms=soft, sigmas=onms.COCO_SIGMAS)
+    kept = dnms.evaluate_records(records, cfg, device=cuda_device)
+    assert np.array_equal([len(k) for k in kept], g[f"evalL{ci}_counts"])
+    assert np.array_equal([r["bbox_id"] for k in kept for r in k], g[f"evalL{ci}_bbox_ids"])
+    got = np.asarray([r["score"] for k in kept for r in k])
+    assert got.dtype == np.float64
+    assert np.array_equal(got, g[f"evalL{ci}_scores"])
+
+
 def test_batched_nms_matches_oracle_with_ties_and_empty_images(cuda_device):
     """Many images in one launch: empty images, one person, tied scores (canonical rule),
     up to 300 people; hard and soft."""

@@ -34,6 +34,38 @@ def test_evaluator_rescoring_and_nms_match_reference_golden(golden, ci):
                           g[f"eval{ci}_scores"])       # float32 rescoring: bit-exact
 
 
+@pytest.mark.parametrize("ci", range(len(ggn.NMS_CASES)))
+def test_oks_functions_match_reference_golden_for_list_records(golden, ci):
+    """Records holding Python floats (the inferencer's `.tolist()` format): float64."""
+    g = golden("nms_ref.npz")
+    people, seed, thr, vthr = ggn.NMS_CASES[ci]
+    kpts, areas, scores = ggn.nms_people(seed, people)
+    flat = kpts.reshape(people, -1).astype(np.float64)
+    a64, s64 = areas.astype(np.float64), scores.astype(np.float64)
+    iou = nms.oks_iou(flat[0], flat, a64[0], a64, None, vthr, dtype=np.float64)
+    assert iou.dtype == np.float32
+    assert np.array_equal(iou, g[f"nmsL{ci}_iou"])
+    assert np.array_equal(nms.oks_nms(flat, a64, s64, thr, vis_thr=vthr, dtype=np.float64),
+                          g[f"nmsL{ci}_keep"])
+    assert np.array_equal(nms.soft_oks_nms(flat, a64, s64, thr, 20, vis_thr=vthr,
+                                           dtype=np.float64), g[f"nmsL{ci}_soft"])
+
+
+@pytest.mark.parametrize("ci", range(len(ggn.EVAL_CASES)))
+def test_evaluator_matches_reference_golden_for_list_records(golden, ci):
+    g = golden("nms_ref.npz")
+    images, max_people, seed, soft = ggn.EVAL_CASES[ci]
+    records = ggn.eval_records(images, max_people, seed, as_lists=True)
+    assert nms.records_dtype(records) == np.float64
+    kept = nms.evaluate_records(records, vis_thr=0.2, oks_thr=0.9, use_nms=True, soft_nms=soft,
+                                sigmas=nms.COCO_SIGMAS)
+    assert np.array_equal([len(k) for k in kept], g[f"evalL{ci}_counts"])
+    assert np.array_equal([b for k in kept for b, _ in k], g[f"evalL{ci}_bbox_ids"])
+    got = np.asarray([s for k in kept for _, s in k])
+    assert got.dtype == np.float64
+    assert np.array_equal(got, g[f"evalL{ci}_scores"])     # float64 rescoring: bit-exact
+
+
 def test_pairwise_sum_is_numpy_sum():
     rng = np.random.RandomState(0)
     for n in list(range(0, 40)) + [64, 100, 127]:
