@@ -956,45 +956,19 @@ struct PairSrc {
   int p;
 };
 
-// PC_BU_COALESCED_STAGE (experiment for round 2, off: DESIGN.md section 9).  The lane-private
-// staging below copies a lane's 32 bytes of a row with two 16-byte cp.async, so each
-// instruction touches HALF of every 32-byte sector of the row and the L2 sees every sector
-// twice (ncu: 1.49 sectors per request, lts__t_tag_requests the busiest unit).  With the
-// switch on and full-width rows (ALL: W == 256) instruction A copies the first 512 bytes of
-// the row and instruction B the second (lane L the bytes 16 L .. 16 L + 15 of them) into the
-// SAME shared-memory image (chunk k = columns 4k .. 4k+3 belongs to lane k >> 1, segment
-// k & 1); the readers then need the other lanes' copies, so the two wait sites and the point
-// before a slot is refilled take a __syncwarp.  Not measured yet.
-#ifndef PC_BU_COALESCED_STAGE
-#define PC_BU_COALESCED_STAGE 0
-#endif
-
+// (Round 2, measured and removed: staging a row as two warp-wide 512-byte halves instead of
+// lane-private 2 x 16 bytes -- half the L2 sector requests, two extra __syncwarp per pair --
+// ran 0.111 ms against 0.109 ms for this form on B200; profiles/README.md, r02a.)
 template <bool ALL>
 __device__ __forceinline__ void pair_issue(PairSrc& s, int W, int w0, int h0, int pe, int p_end,
                                            uint32_t slot, bool active) {
   if ((ALL || active) && s.p <= p_end) {
-#if PC_BU_COALESCED_STAGE
-    if (ALL) {
-      const int lane = threadIdx.x & 31;
-      const float* row = s.hi - 4 * lane;  // s.hi = row start + 8 lane
-      const uint32_t img = slot - 16 * lane + (lane & 1) * kPairSeg + (lane >> 1) * 16;
-      cp_async16_s(img, row);
-      cp_async16_s(img + 256, row + 128);
-      if (s.p < pe) {
-        cp_async16_s(img + 2 * kPairSeg, row + W);
-        cp_async16_s(img + 2 * kPairSeg + 256, row + W + 128);
-        cp_async16_s(slot + 4 * kPairSeg, s.lo);
-      }
-    } else
-#endif
-    {
-      cp_async16_s(slot, s.hi);
-      cp_async16_s(slot + kPairSeg, s.hi + 4);
-      if (s.p < pe) {
-        cp_async16_s(slot + 2 * kPairSeg, s.hi + W);
-        cp_async16_s(slot + 3 * kPairSeg, s.hi + W + 4);
-        cp_async16_s(slot + 4 * kPairSeg, s.lo);
-      }
+    cp_async16_s(slot, s.hi);
+    cp_async16_s(slot + kPairSeg, s.hi + 4);
+    if (s.p < pe) {
+      cp_async16_s(slot + 2 * kPairSeg, s.hi + W);
+      cp_async16_s(slot + 3 * kPairSeg, s.hi + W + 4);
+      cp_async16_s(slot + 4 * kPairSeg, s.lo);
     }
   }
   cp_async_commit();  // one group per pair, empty past the end: wait_group 1 stays exact
@@ -1227,9 +1201,6 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
   int tog = 0;  // byte offset of pair p's slot in the ring
   for (int p = pb; p < pe; ++p) {
     cp_async_wait_pending<kPairDepth - 1>();
-#if PC_BU_COALESCED_STAGE
-    if (ALL) __syncwarp();  // the slot holds other lanes' copies too
-#endif
     const unsigned char* slot = slot0 + tog;
     const float4 a0 = *reinterpret_cast<const float4*>(slot);
     const float4 a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);
@@ -1237,9 +1208,6 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
     const float4 b1 = *reinterpret_cast<const float4*>(slot + 3 * kPairSeg);
     const float4 q = *reinterpret_cast<const float4*>(slot + 4 * kPairSeg);
     // (inactive lanes read stale bytes: nothing they compute reaches an active lane)
-#if PC_BU_COALESCED_STAGE
-    if (ALL) __syncwarp();  // every lane has read the slot before other lanes refill it
-#endif
     pair_issue<ALL>(src, W, w0, h0, pe, p_end, sa0 + tog, active);
     tog = tog + kPairSlot == kPairWarp ? 0 : tog + kPairSlot;
     float hN[8];
@@ -1282,9 +1250,6 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
     for (int c = 0; c < 8; ++c) vN[c] = -INFINITY;
     if (re < H) {
       cp_async_wait_pending<kPairDepth - 1>();
-#if PC_BU_COALESCED_STAGE
-      if (ALL) __syncwarp();
-#endif
       const unsigned char* slot = slot0 + tog;
       const float4 a0 = *reinterpret_cast<const float4*>(slot);
       const float4 a1 = *reinterpret_cast<const float4*>(slot + kPairSeg);

@@ -47,7 +47,7 @@ def _nvcc() -> str:
 
 
 def _extra_defines():
-    """Experiment switches (e.g. ``PC_NVCC_DEFINES="-DPC_WARP_COLUMN_MAP=1"``): part of the
+    """Experiment switches (``PC_NVCC_DEFINES="-DPC_SOME_SWITCH=1"``): part of the
     fingerprint, so a library built with them is rebuilt by the next plain build()."""
     extra = os.environ.get("PC_NVCC_DEFINES", "").split()
     bad = [d for d in extra if not d.startswith("-D")]

@@ -457,32 +457,39 @@ struct NormArgs {
 // QUAD (rotation-free crops of the uint8 variant): the fixed-point column deltas are monotone
 // in x, so a quad whose first and last pixel are interior is interior as a whole -- one range
 // test per quad, and the four pixels' tap loads sit in one basic block.
-#ifndef PC_WARP_COLUMN_MAP
-#define PC_WARP_COLUMN_MAP 0
-#endif
-template <bool NORM, bool QUAD>
-__global__ void __launch_bounds__(kWarpThreads)
-    warp_affine_u8x3_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
-                            const int32_t* __restrict__ src_hw, const double* __restrict__ inv,
-                            void* __restrict__ dst_any, int dst_w, int dst_h, int tiles_per_crop,
-                            FastDiv div_wq, const NormArgs norm) {
-  uint8_t* dst = static_cast<uint8_t*>(dst_any);
-  __shared__ __align__(16) int s_adelta[kWarpMaxDstW];
-  __shared__ __align__(16) int s_bdelta[kWarpMaxDstW];
-  __shared__ int s_x0[kWarp3TileRows];
-  __shared__ int s_y0[kWarp3TileRows];
-  __shared__ int4 s_rowa[kWarp3TileRows];  // rotation-free crops: sy, fy, sx_lo, sx_span per row
-  __shared__ uint32_t s_rowoff[kWarp3TileRows];
-  __shared__ __align__(16) uint32_t s_stage[kWarpThreads / 32][96];
+// Shared memory of the quad kernel below (12.6 KB); the band kernel further down lends it a
+// piece of its band buffer when a tile takes this path.
+struct QuadSmem {
+  int adelta[kWarpMaxDstW];
+  int bdelta[kWarpMaxDstW];
+  int x0[kWarp3TileRows];
+  int y0[kWarp3TileRows];
+  int4 rowa[kWarp3TileRows];  // rotation-free crops: sy, fy, sx_lo, sx_span per row
+  uint32_t rowoff[kWarp3TileRows];
+  uint32_t stage[16][96];     // one 384-byte transpose buffer per warp (<= 16 warps)
+};
 
-  const int64_t crop = blockIdx.x / tiles_per_crop;
-  const int tile = blockIdx.x - (int)(crop * tiles_per_crop);
+// One tile (kWarp3TileRows output rows of one crop) by any number of whole warps.
+template <bool NORM, bool QUAD>
+__device__ __forceinline__ void warp3_quad_tile(
+    QuadSmem& sm, const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
+    const int32_t* __restrict__ src_hw, const double* __restrict__ inv, void* __restrict__ dst_any,
+    int dst_w, int dst_h, int64_t crop, int tile, FastDiv div_wq, const NormArgs& norm) {
+  uint8_t* dst = static_cast<uint8_t*>(dst_any);
+  int* const s_adelta = sm.adelta;
+  int* const s_bdelta = sm.bdelta;
+  int* const s_x0 = sm.x0;
+  int* const s_y0 = sm.y0;
+  int4* const s_rowa = sm.rowa;
+  uint32_t* const s_rowoff = sm.rowoff;
+  const int nthreads = blockDim.x;
+
   const int row0 = tile * kWarp3TileRows;
   const int rows = min(kWarp3TileRows, dst_h - row0);
   const double* m = inv + 6 * crop;
   const double m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5];
 
-  for (int x = threadIdx.x; x < dst_w; x += blockDim.x) {
+  for (int x = threadIdx.x; x < dst_w; x += nthreads) {
     s_adelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m00, (double)x), 1024.0));
     s_bdelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m10, (double)x), 1024.0));
   }
@@ -504,7 +511,7 @@ __global__ void __launch_bounds__(kWarpThreads)
   const int nquads = rows * wq;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* out = dst + ((size_t)crop * dst_h + row0) * dst_w * 3;
-  uint32_t* stage = s_stage[warp];
+  uint32_t* stage = sm.stage[warp];
   // the fixed-point column deltas are monotone in x: the last one being 0 means all are
   const bool axis = s_bdelta[dst_w - 1] == 0;
   const bool rowal = (ws3 & 3u) == 0;
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(kWarpThreads)
     __syncthreads();
   }
 
-  for (int base = warp * 32; base < nquads; base += kWarpThreads) {
+  for (int base = warp * 32; base < nquads; base += nthreads) {
     const int t = base + lane;
     uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     if (t < nquads) {
@@ -628,95 +635,299 @@ __global__ void __launch_bounds__(kWarpThreads)
   }
 }
 
-#if PC_WARP_COLUMN_MAP
-// Experiment for round 2 (off, unmeasured: DESIGN.md section 9).  Crops whose width is a
-// multiple of 32: a lane owns ONE output column and four rows of it, so the 32 lanes of a tap
-// load read 5.7 bytes apart instead of 23 (5.8 instead of 15-17 sectors per load:
-// scripts/warp_sector_model.py) and the per-column X offset is shared by four pixels.  A row's
-// 32 pixels (96 bytes) are packed into 24 words with one shuffle per lane.  Rotated crops
-// (training-time augmentation) take a plain per-pixel loop.  44 registers, 4.5 KB shared memory.
+template <bool NORM, bool QUAD>
 __global__ void __launch_bounds__(kWarpThreads)
-    warp_affine_u8x3_cols_kernel(const uint8_t* __restrict__ src,
-                                 const int64_t* __restrict__ src_off,
-                                 const int32_t* __restrict__ src_hw,
-                                 const double* __restrict__ inv, uint8_t* __restrict__ dst,
-                                 int dst_w, int dst_h, int tiles_per_crop) {
-  __shared__ int s_adelta[kWarpMaxDstW];
-  __shared__ int s_x0[kWarp3TileRows];
-  __shared__ int s_y0[kWarp3TileRows];
-  __shared__ int4 s_rowa[kWarp3TileRows];
-  __shared__ uint32_t s_rowoff[kWarp3TileRows];
+    warp_affine_u8x3_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
+                            const int32_t* __restrict__ src_hw, const double* __restrict__ inv,
+                            void* __restrict__ dst_any, int dst_w, int dst_h, int tiles_per_crop,
+                            FastDiv div_wq, const NormArgs norm) {
+  __shared__ __align__(16) QuadSmem sm;
   const int64_t crop = blockIdx.x / tiles_per_crop;
   const int tile = blockIdx.x - (int)(crop * tiles_per_crop);
-  const int row0 = tile * kWarp3TileRows;
-  const int rows = min(kWarp3TileRows, dst_h - row0);
-  const double* m = inv + 6 * crop;
-  const double m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5];
-  // rint(m10 * x * 1024) is 0 for every column iff it is for the last one (monotone)
-  const bool axis =
-      __double2int_rn(__dmul_rn(__dmul_rn(m10, (double)(dst_w - 1)), 1024.0)) == 0;
-  const int hs = src_hw[2 * crop], ws = src_hw[2 * crop + 1];
-  const uint8_t* img = src + src_off[crop];
-  const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(img) & 3u);
-  const uint8_t* base4 = img - delta;
-  const uint32_t ws3 = (uint32_t)ws * 3u;
-  for (int x = threadIdx.x; x < dst_w; x += blockDim.x)
-    s_adelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m00, (double)x), 1024.0));
-  if (threadIdx.x < rows) {
-    const double y = (double)(row0 + threadIdx.x);
-    s_x0[threadIdx.x] =
-        __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m01, y), m02), 1024.0)) + 16;
-    const int y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m11, y), m12), 1024.0)) + 16;
-    s_y0[threadIdx.x] = y0;
-    const RowCtx rc = make_row(y0 >> 5, hs, ws, ws3, delta);
-    s_rowa[threadIdx.x] = make_int4(rc.sy, rc.fy, rc.sx_lo, (int)rc.sx_span);
-    s_rowoff[threadIdx.x] = rc.off;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* out = dst + ((size_t)crop * dst_h + row0) * dst_w * 3;
-  if (!axis) {  // rotated crop: plain per-pixel path
-    for (int t = threadIdx.x; t < rows * dst_w; t += kWarpThreads) {
-      const int ry = t / dst_w, x = t - ry * dst_w;
-      const int bd = __double2int_rn(__dmul_rn(__dmul_rn(m10, (double)x), 1024.0));
-      const RowCtx rc = make_row((s_y0[ry] + bd) >> 5, hs, ws, ws3, delta);
-      const uint32_t p =
-          warp_pixel3<false>(img, base4, hs, ws, ws3, (s_x0[ry] + s_adelta[x]) >> 5, rc);
-      uint8_t* o = out + (size_t)t * 3;
-      o[0] = (uint8_t)p, o[1] = (uint8_t)(p >> 8), o[2] = (uint8_t)(p >> 16);
-    }
-    return;
-  }
-  const bool rowal = (ws3 & 3u) == 0;
-  const int groups = dst_w >> 5, rgroups = (rows + 3) >> 2;
-  for (int item = warp; item < groups * rgroups; item += kWarpThreads / 32) {
-    const int rq = item / groups, g = item - rq * groups;
-    const int ad = s_adelta[(g << 5) + lane];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ry = 4 * rq + j;
-      if (ry >= rows) break;  // warp-uniform
-      const int4 rw = s_rowa[ry];
-      RowCtx ra;
-      ra.sy = rw.x, ra.fy = rw.y, ra.sx_lo = rw.z, ra.sx_span = (uint32_t)rw.w;
-      ra.off = s_rowoff[ry];
-      const int X = (s_x0[ry] + ad) >> 5;
-      const uint32_t p = rowal ? warp_pixel3<true>(img, base4, hs, ws, ws3, X, ra)
-                               : warp_pixel3<false>(img, base4, hs, ws, ws3, X, ra);
-      // bytes of four neighbouring pixels p0 p1 p2 p3 (24 bits each) as three words:
-      // word k of the group = (p_k >> 8k) | (p_{k+1} << (24 - 8k)), k = 0, 1, 2
-      // (tests/test_warp_identities.py)
-      const uint32_t nxt = __shfl_down_sync(0xffffffffu, p, 1);
-      const int k = lane & 3;
-      if (k < 3) {
-        const uint32_t w = (p >> (8 * k)) | (nxt << (24 - 8 * k));
-        uint8_t* o = out + ((size_t)ry * dst_w + (g << 5)) * 3 + (((lane >> 2) * 3 + k) << 2);
-        asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(o), "r"(w) : "memory");
-      }
+  warp3_quad_tile<NORM, QUAD>(sm, src, src_off, src_hw, inv, dst_any, dst_w, dst_h, crop, tile,
+                              div_wq, norm);
+}
+
+// ---- band kernel: rotation-free 3-channel crops out of shared memory --------------------
+// The evaluation path (rot = 0) and most of the bench.  The quad kernel above gathers its taps
+// from global memory through L1: 81 instructions per pixel (alignment, range tests and address
+// arithmetic per tap), every sector fetched 14 times out of L1, 0.52 of the HBM roofline.
+// Without rotation the source pixels of a tile of output rows are a RECTANGLE of the image, so
+// here
+//   * the rectangle ("band": source rows sy_lo .. sy_hi, columns sx_lo .. sx_hi + 1) is staged
+//     in shared memory by 1-D bulk copies (cp.async.bulk, one per source row, issued by the
+//     lanes of warp 0, completion on an mbarrier): the copies are 16-byte aligned in global
+//     memory, so a row lands at the phase (address mod 16) it has there;
+//   * the parts of the band outside the image are then overwritten with zeros (OpenCV's
+//     constant border), which removes every range test from the inner loop;
+//   * a lane owns ONE output column for the whole tile: the source column, the weight pair
+//     (32 - fx, fx), the word offsets of its three tap words and the two byte-permute selectors
+//     that pair up the channels (r0 r1 g0 g1 | b0 b1) are per-thread constants -- the row
+//     pitch is a multiple of 4 bytes (ws % 4 == 0), so the alignment of a column's 6-byte run
+//     is the same in every row;
+//   * per pixel: 3 + 3 aligned 32-bit shared-memory loads, 4 byte permutes, the same six
+//     dp2a dot products as the quad kernel (the identical integer sum, so the identical
+//     bytes), and the upper row's permuted words are kept when the next output row reuses
+//     them (sy advances by 0 or 1: always when upscaling);
+//   * a warp's 32 pixels of a row (96 bytes) leave as 24 words: one shuffle and one byte
+//     permute per lane (tests/test_warp_identities.py), three lanes of four store.
+// Tiles that do not qualify (rotation, ws % 4 != 0, a mirrored matrix, a band of one output
+// row that does not fit) run the quad path in the same launch, on a piece of the band buffer.
+constexpr int kBandBytes = 36 * 1024;  // 6 CTAs of 192 threads per SM
+constexpr int kBandMaxThreads = 512;   // dst_w <= 512 (one column per thread)
+constexpr int kBandPassRows = 16;      // output rows staged and computed at a time
+constexpr int kBandMaxTileRows = 64;   // output rows per CTA (the host picks 16, 32 or 64)
+
+struct BandRow {
+  uint32_t addr_a;  // shared-memory address of the word holding source pixel (sy, clo) ...
+  uint32_t addr_b;  // ... and (sy + 1, clo): the rows' 16-byte phases differ when ws3 % 16 != 0
+  uint32_t gy;      // 32 - fy
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void bulk_g2s_plain(uint32_t dst_smem, const void* src_gmem,
+                                               uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr));
+  return v;
+}
+
+// zero the bytes [begin, end) of shared memory (byte addresses relative to `base`), one warp
+__device__ __forceinline__ void zero_smem_bytes(uint8_t* base, int begin, int end, int lane) {
+  if (end <= begin) return;
+  const int w0 = begin >> 2, w1 = (end + 3) >> 2;
+  for (int w = w0 + lane; w < w1; w += 32) {
+    const int lo = max(begin - 4 * w, 0), hi = min(end - 4 * w, 4);  // bytes [lo, hi) of word w
+    uint32_t* p = reinterpret_cast<uint32_t*>(base) + w;
+    if (hi - lo == 4) {
+      *p = 0u;
+    } else {
+      const uint32_t keep = ~((0xffffffffu >> (8 * (4 - (hi - lo)))) << (8 * lo));
+      *p &= keep;
     }
   }
 }
-#endif  // PC_WARP_COLUMN_MAP
+
+// the quad path as a real call: its registers then do not count against the band path's
+__device__ __noinline__ void warp3_quad_tile_call(
+    QuadSmem& sm, const uint8_t* src, const int64_t* src_off, const int32_t* src_hw,
+    const double* inv, void* dst, int dst_w, int dst_h, int64_t crop, int tile, FastDiv div_wq) {
+  warp3_quad_tile<false, true>(sm, src, src_off, src_hw, inv, dst, dst_w, dst_h, crop, tile,
+                               div_wq, NormArgs());
+}
+
+// 56 registers: 6 CTAs of 192 threads per SM, as many as the band buffer allows (the band
+// path itself needs fewer; what spills is the call of the quad path)
+__global__ void __maxnreg__(56)
+    warp_affine_u8x3_band_kernel(const uint8_t* __restrict__ src,
+                                 const int64_t* __restrict__ src_off,
+                                 const int32_t* __restrict__ src_hw,
+                                 const double* __restrict__ inv, uint8_t* __restrict__ dst,
+                                 int dst_w, int dst_h, int tile_rows, int tiles_per_crop,
+                                 FastDiv div_wq) {
+  extern __shared__ __align__(128) uint8_t s_band[];  // kBandBytes
+  __shared__ int s_x0[kBandMaxTileRows];
+  __shared__ int s_y0[kBandMaxTileRows];
+  __shared__ __align__(16) BandRow s_row[kBandPassRows];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t crop = blockIdx.x / tiles_per_crop;
+  const int tile = blockIdx.x - (int)(crop * tiles_per_crop);
+  const int row0 = tile * tile_rows;
+  const int rows = min(tile_rows, dst_h - row0);
+  const double* m = inv + 6 * crop;
+  const double m00 = m[0], m10 = m[3];
+  const int hs = src_hw[2 * crop], ws = src_hw[2 * crop + 1];
+  const uint8_t* img = src + src_off[crop];
+  const uint32_t ws3 = (uint32_t)ws * 3u;
+
+  if (tid < rows) {
+    const double m01 = m[1], m02 = m[2], m11 = m[4], m12 = m[5];
+    const double y = (double)(row0 + tid);
+    s_x0[tid] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m01, y), m02), 1024.0)) + 16;
+    s_y0[tid] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m11, y), m12), 1024.0)) + 16;
+  }
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  // this thread's column (blockDim.x == dst_w, a multiple of 32)
+  const int ad = __double2int_rn(__dmul_rn(__dmul_rn(m00, (double)tid), 1024.0));
+  const int ad_last = __double2int_rn(__dmul_rn(__dmul_rn(m00, (double)(dst_w - 1)), 1024.0));
+  const int bd_last = __double2int_rn(__dmul_rn(__dmul_rn(m10, (double)(dst_w - 1)), 1024.0));
+  __syncthreads();
+
+  // ---- does the tile qualify? (block-uniform) --------------------------------------------
+  // Y independent of x (the fixed-point column deltas of Y are monotone: the last one being 0
+  // means all are), X0 the same in every row of the tile, sx and sy non-decreasing.
+  const int X0 = s_x0[0];
+  const bool row_ok = tid == 0 || tid >= rows || (s_x0[tid] == X0 && s_y0[tid] >= s_y0[tid - 1]);
+  bool ok = __syncthreads_and(row_ok) != 0;
+  ok = ok && bd_last == 0 && ad_last >= 0 && (ws3 & 3u) == 0 && hs >= 1 && ws >= 1;
+  const int sx_lo = X0 >> 10, sx_hi = ((X0 + ad_last) >> 10) + 1;  // columns the taps touch
+  const int clo = max(sx_lo, 0), chi = min(sx_hi, ws - 1);         // ... inside the image
+  const int L = ((clo - sx_lo) * 3 + 15) & ~15;  // room for the columns left of the image
+  // row pitch: L, the phase (<= 15), the columns clo .. sx_hi, the tail of the last 16-byte
+  // unit of the copy (<= 15); the three tap words of the last column reach 9 bytes past the
+  // start of its run (covered by the second + 15)
+  const int P = (L + 15 + (sx_hi - clo + 1) * 3 + 15 + 15) & ~15;
+  const int nb_max = kBandBytes / P;  // source rows the buffer holds
+  // nb_max >= 2: one output row needs exactly two source rows, so the passes always advance
+  ok = ok && sx_hi - sx_lo < 8192 && nb_max >= 2;
+  if (!ok) {
+    // the quad path works on tiles of kWarp3TileRows rows
+    QuadSmem& qs = *reinterpret_cast<QuadSmem*>(s_band);
+    for (int r = 0; r < rows; r += kWarp3TileRows) {
+      warp3_quad_tile_call(qs, src, src_off, src_hw, inv, dst, dst_w, dst_h, crop,
+                           (row0 + r) / kWarp3TileRows, div_wq);
+      __syncthreads();
+    }
+    return;
+  }
+
+  // ---- per-thread column constants ---------------------------------------------------------
+  const int X = (X0 + ad) >> 5;
+  const int sx = X >> 5, fx = X & 31;
+  const uint32_t wg = (32u - (uint32_t)fx) | ((uint32_t)fx << 16);
+  const uint32_t wg32 = wg << 5;  // wg * (gy + uy)
+  const uint32_t band0 = smem_u32(s_band);
+  // phase mod 4 of column clo, the same in every row (ws3 % 4 == 0); BandRow.addr_* is the
+  // address of column clo rounded down to a word, so a column's run starts `run` bytes on
+  const uint32_t rho = (uint32_t)((reinterpret_cast<uintptr_t>(img) + (size_t)clo * 3u) & 3u);
+  const int run = (sx - clo) * 3 + (int)rho;  // may be negative (columns left of the image)
+  const uint32_t a = (uint32_t)run & 3u;      // alignment of the run
+  const uint32_t colA = (uint32_t)(run - (int)a);     // word A (B = A + 4)
+  const uint32_t colZ = colA + (a == 3u ? 8u : 0u);   // word C when the run starts at byte 3, else A
+  const uint32_t selA = 0x4130u + 0x1111u * a;               // (A, B) -> r0 r1 g0 g1
+  const uint32_t selB = ((6u + a) & 7u) | ((1u + a) << 4);   // (B, Z) -> b0 b1 . .
+  // output: lane k of a group of four holds pixel k; words 0..2 of the group's 12 bytes
+  const int k4 = lane & 3;
+  const uint32_t selO = k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u);
+  uint8_t* out = dst + ((size_t)crop * dst_h + row0) * dst_w * 3 + (size_t)(tid >> 5) * 96 +
+                 (size_t)(((lane >> 2) * 3 + k4) << 2);
+  const uint32_t out_pitch = (uint32_t)dst_w * 3u;
+  const uint32_t row_tab = smem_u32(s_row);
+
+  uint32_t phase = 0;
+  for (int r_begin = 0; r_begin < rows;) {
+    // ---- the output rows of this pass: as many as the buffer holds source rows for --------
+    const int sy_lo = s_y0[r_begin] >> 10;
+    int r_end = min(r_begin + kBandPassRows, rows);
+    if ((s_y0[r_end - 1] >> 10) + 2 - sy_lo > nb_max) {
+      r_end = r_begin + 1;
+      while ((s_y0[r_end] >> 10) + 2 - sy_lo <= nb_max) ++r_end;  // stops before the probe above
+    }
+    const int sy_hi = (s_y0[r_end - 1] >> 10) + 1;
+    const int nb = sy_hi - sy_lo + 1;
+    const int rlo = max(sy_lo, 0), rhi = min(sy_hi, hs - 1);
+    const bool any = rlo <= rhi && clo <= chi;
+
+    if (tid < r_end - r_begin) {
+      const int Y = s_y0[r_begin + tid] >> 5;
+      const int sy = Y >> 5, fy = Y & 31;
+      // row j = r - sy_lo of the band starts at j * P; its copy starts at L and lands at the
+      // phase (address mod 16) the row has in global memory.  Rows outside the image are all
+      // zeros: any phase with the right alignment mod 4 will do.
+      const uintptr_t g0 = reinterpret_cast<uintptr_t>(img) + (size_t)clo * 3u;
+      const uintptr_t ga = g0 + (size_t)(uint32_t)max(sy, 0) * ws3;
+      const uintptr_t gb = g0 + (size_t)(uint32_t)max(sy + 1, 0) * ws3;
+      BandRow br;
+      br.addr_a = band0 + (uint32_t)((sy - sy_lo) * P + L) + ((uint32_t)ga & 12u);
+      br.addr_b = band0 + (uint32_t)((sy + 1 - sy_lo) * P + L) + ((uint32_t)gb & 12u);
+      br.gy = 32u - (uint32_t)fy;
+      br.pad = 0u;
+      s_row[tid] = br;
+    }
+    // ---- stage the band: one bulk copy per source row, issued by the lanes of warp 0, which
+    //      also waits for them (the other warps wait at the barrier below) ------------------
+    if (tid < 32 && any) {
+      const uint32_t span = (uint32_t)(chi - clo + 1) * 3u;
+      uint32_t bytes = 0;
+      for (int r = rlo + lane; r <= rhi; r += 32) {
+        const uintptr_t g = reinterpret_cast<uintptr_t>(img) + (size_t)r * ws3 + (size_t)clo * 3u;
+        bytes += (uint32_t)(((g & 15u) + span + 15u) & ~15u);
+      }
+      bytes = __reduce_add_sync(0xffffffffu, bytes);
+      if (lane == 0) mbar_arrive_expect_tx(&s_bar, bytes);
+      __syncwarp();
+      for (int r = rlo + lane; r <= rhi; r += 32) {
+        const uintptr_t g = reinterpret_cast<uintptr_t>(img) + (size_t)r * ws3 + (size_t)clo * 3u;
+        const uint32_t n16 = (uint32_t)(((g & 15u) + span + 15u) & ~15u);
+        bulk_g2s_plain(band0 + (uint32_t)((r - sy_lo) * P + L),
+                       reinterpret_cast<const void*>(g & ~(uintptr_t)15), n16, &s_bar);
+      }
+      mbar_wait(&s_bar, phase);
+    }
+    phase ^= any ? 1u : 0u;
+    // ---- zeros outside the image (constant border), one warp per band row ---------------
+    if (sy_lo < 0 || sy_hi > hs - 1 || sx_lo < 0 || sx_hi > ws - 1) {
+      __syncthreads();  // the copies have landed (warp 0 saw the barrier flip)
+      const int nwarps = blockDim.x >> 5;
+      for (int j = tid >> 5; j < nb; j += nwarps) {
+        const int r = sy_lo + j;
+        uint8_t* rowp = s_band + (size_t)j * P;
+        if (r < 0 || r > hs - 1 || !any) {
+          zero_smem_bytes(rowp, 0, P, lane);
+        } else {
+          const uintptr_t g = reinterpret_cast<uintptr_t>(img) + (size_t)r * ws3 + (size_t)clo * 3u;
+          const int first = L + (int)(g & 15u);  // byte of column clo in this row
+          if (sx_lo < 0) zero_smem_bytes(rowp, 0, first, lane);
+          __syncwarp();  // an image narrower than two pixels: both ranges may share a word
+          if (sx_hi > ws - 1) zero_smem_bytes(rowp, first + (chi - clo + 1) * 3, P, lane);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- one column, r_end - r_begin rows ---------------------------------------------------
+    {
+      const int cnt = r_end - r_begin;
+      uint8_t* o = out + (size_t)r_begin * out_pitch;
+#pragma unroll 4
+      for (int i = 0; i < cnt; ++i) {
+        const uint4 rc = lds128(row_tab + 16u * (uint32_t)i);  // addr_a, addr_b, gy
+        const uint32_t A0 = lds32(rc.x + colA), B0 = lds32(rc.x + colA + 4u);
+        const uint32_t Z0 = lds32(rc.x + colZ);
+        const uint32_t A1 = lds32(rc.y + colA), B1 = lds32(rc.y + colA + 4u);
+        const uint32_t Z1 = lds32(rc.y + colZ);
+        const uint32_t arg = __byte_perm(A0, B0, selA), abb = __byte_perm(B0, Z0, selB);
+        const uint32_t brg = __byte_perm(A1, B1, selA), bbb = __byte_perm(B1, Z1, selB);
+        const uint32_t wt = wg * rc.z, wu = wg32 - wt;  // wg * gy, wg * uy
+        const uint32_t c0 = __dp2a_lo(wu, brg, __dp2a_lo(wt, arg, 512u)) >> 10;
+        const uint32_t c1 = __dp2a_hi(wu, brg, __dp2a_hi(wt, arg, 512u)) >> 10;
+        const uint32_t c2 = __dp2a_lo(wu, bbb, __dp2a_lo(wt, abb, 512u)) >> 10;
+        const uint32_t px = __byte_perm(__byte_perm(c0, c1, 0x0040), c2, 0x5410);
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, px, 1);
+        if (k4 < 3) {
+          const uint32_t w = __byte_perm(px, nxt, selO);
+          asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(o), "r"(w) : "memory");
+        }
+        o += out_pitch;
+      }
+    }
+    r_begin = r_end;
+    if (r_begin < rows) {
+      // the next pass overwrites the band and the row table: order this pass's generic-proxy
+      // accesses (reads, zero fill) before the bulk copies of the async proxy
+      fence_proxy_async();
+      __syncthreads();
+    }
+  }
+}
 
 }  // namespace pc
 
@@ -798,14 +1009,23 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
     const int tiles3 = (p->dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
     const int64_t grid3 = n * tiles3;
     PC_REQUIRE(grid3 < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_warp_affine_u8: batch too large");
-#if PC_WARP_COLUMN_MAP
-    if (p->dst_w % 32 == 0) {
-      warp_affine_u8x3_cols_kernel<<<(unsigned)grid3, kWarpThreads, 0, st>>>(
-          d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3);
+    if (p->dst_w % 32 == 0 && p->dst_w <= kBandMaxThreads) {
+      // one thread per output column; rotation-free tiles out of a shared-memory band, the
+      // others through the quad path inside the same kernel
+      // rows per CTA: per-CTA set-up (matrix, column constants) is paid once per tile, so
+      // tiles are as tall as still leaves every SM a few rounds of CTAs
+      int tile_rows = kBandMaxTileRows;
+      const int64_t want = (int64_t)sm_count_cached() * 6 * 3;
+      while (tile_rows > kWarp3TileRows &&
+             n * ((p->dst_h + tile_rows - 1) / tile_rows) < want)
+        tile_rows >>= 1;
+      const int tiles_b = (p->dst_h + tile_rows - 1) / tile_rows;
+      warp_affine_u8x3_band_kernel<<<(unsigned)(n * tiles_b), p->dst_w, kBandBytes, st>>>(
+          d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tile_rows, tiles_b,
+          make_fastdiv((uint32_t)(p->dst_w >> 2)));
       PC_CUDA(cudaGetLastError());
       return PC_OK;
     }
-#endif
     warp_affine_u8x3_kernel<false, true><<<(unsigned)grid3, kWarpThreads, 0, st>>>(
         d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3,
         make_fastdiv((uint32_t)(p->dst_w >> 2)), NormArgs());

@@ -438,6 +438,64 @@ def test_warp_image_corners_and_unaligned_sources(cuda_device, channels):
         assert np.array_equal(out[i], want.reshape(dh, dw, channels)), i
 
 
+@pytest.mark.parametrize("ws,dw,dh", [(52, 64, 40), (64, 32, 16), (40, 96, 50), (320, 192, 256)])
+def test_warp_band_path_edge_cases(cuda_device, ws, dw, dh):
+    """The shared-memory band kernel (3 channels, dst_w % 32 == 0, no rotation, ws % 4 == 0):
+    source rows whose 16-byte phase changes from row to row (ws * 3 % 16 != 0), images at odd
+    byte offsets, crops that hang over every edge or miss the image, up- and down-scaling up
+    to several band passes per tile, and the matrices that must take the quad path instead
+    (mirrored, slightly rotated, a band too large for shared memory)."""
+    dev = cuda_device
+    rng = np.random.RandomState(ws + dw)
+    hs = 37
+    mats = np.array([
+        [[1, 0, 0], [0, 1, 0]],                    # identity: first / last pixel pair
+        [[1, 0, 0.5], [0, 1, 0.5]],
+        [[1, 0, -3.25], [0, 1, 2.75]],             # over the left / bottom edge
+        [[1, 0, 7.0], [0, 1, -5.5]],               # over the right / top edge
+        [[3.7, 0, -11.0], [0, 3.7, -9.0]],         # up-scaling: rows and columns repeat
+        [[0.6, 0, 3.0], [0, 0.6, 2.0]],            # down-scaling by 1.67
+        [[0.21, 0, 1.0], [0, 0.23, 0.5]],          # ... by 4.8 / 4.3 (anisotropic)
+        [[0.02, 0, 0.0], [0, 0.02, 0.0]],          # ... by 50: larger than the image
+        [[1, 0, 500.0], [0, 1, 0]],                # misses the image
+        [[1, 0, 0], [0, 1, -300.0]],
+        [[-1, 0, 40.0], [0, 1, 0]],                # mirrored: quad path
+        [[1, 0.002, 0], [-0.002, 1, 0]],           # a whisper of rotation: quad path
+        [[1.3, 0, -1e-7], [0, 1.3, 1e-7]],
+    ], np.float64)
+    n = len(mats)
+    pad = [(3 * i) % 7 for i in range(n)]          # odd byte offsets inside a shared buffer
+    buf = rng.randint(0, 256, size=n * (hs * ws * 3 + 8), dtype=np.uint8)
+    offs, imgs, pos = [], [], 0
+    for i in range(n):
+        pos += pad[i]
+        offs.append(pos)
+        imgs.append(buf[pos:pos + hs * ws * 3].reshape(hs, ws, 3))
+        pos += hs * ws * 3
+    inv = codec.invert_affine(_t(mats, dev))
+    out = codec.warp_affine(_t(buf, dev), torch.tensor(offs, device=dev),
+                            torch.tensor([[hs, ws]] * n, device=dev, dtype=torch.int32), inv,
+                            (dw, dh), channels=3).cpu().numpy()
+    for i in range(n):
+        want = warp.warp_affine_u8(imgs[i], mats[i], (dw, dh))
+        assert np.array_equal(out[i], want.reshape(dh, dw, 3)), (i, mats[i].tolist())
+
+
+def test_warp_band_path_tiny_and_large_sources(cuda_device):
+    """1- and 2-pixel images (both zero-fill ranges of a band row meet), and a 1080 x 1920
+    source scaled down by 7.5 (one output row per band pass)."""
+    dev = cuda_device
+    rng = np.random.RandomState(5)
+    for hs, ws, m in ((1, 4, [[1, 0, 1.0], [0, 1, 3.0]]), (2, 4, [[4, 0, 8.0], [0, 4, 2.0]]),
+                      (1080, 1920, [[0.1333, 0, -3.0], [0, 0.1333, -4.0]]),
+                      (1080, 1920, [[0.4, 0, -300.0], [0, 0.4, -100.0]])):
+        img = rng.randint(0, 256, size=(1, hs, ws, 3), dtype=np.uint8)
+        mat = np.array([m], np.float64)
+        out = codec.warp_affine_uniform(_t(img, dev), codec.invert_affine(_t(mat, dev)), (256, 144))
+        want = warp.warp_affine_u8(img[0], mat[0], (256, 144))
+        assert np.array_equal(out[0].cpu().numpy(), want), (hs, ws)
+
+
 def test_warp_fused_normalize_chw(cuda_device):
     """N2: warp + Normalize(mean * 255, std * 255) + HWC2CHW in one kernel equals the uint8
     warp followed by the oracle's normalisation, bit for bit (same float32 formula)."""
