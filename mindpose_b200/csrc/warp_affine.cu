@@ -652,37 +652,42 @@ __global__ void __launch_bounds__(kWarpThreads)
 // The evaluation path (rot = 0) and most of the bench.  The quad kernel above gathers its taps
 // from global memory through L1: 81 instructions per pixel (alignment, range tests and address
 // arithmetic per tap), every sector fetched 14 times out of L1, 0.52 of the HBM roofline.
-// Without rotation the source pixels of a tile of output rows are a RECTANGLE of the image, so
+// Without rotation the source pixels of a run of output rows are a RECTANGLE of the image, so
 // here
-//   * the rectangle ("band": source rows sy_lo .. sy_hi, columns sx_lo .. sx_hi + 1) is staged
-//     in shared memory by 1-D bulk copies (cp.async.bulk, one per source row, issued by the
-//     lanes of warp 0, completion on an mbarrier): the copies are 16-byte aligned in global
-//     memory, so a row lands at the phase (address mod 16) it has there;
-//   * the parts of the band outside the image are then overwritten with zeros (OpenCV's
-//     constant border), which removes every range test from the inner loop;
+//   * the rectangle ("band": source rows sy_lo .. sy_hi, columns clo .. chi, clipped to the
+//     image) is staged in shared memory by 1-D bulk copies (cp.async.bulk, one per source row,
+//     issued by the lanes of warp 0, completion on an mbarrier): the copies are 16-byte
+//     aligned in global memory, so a row lands at the phase (address mod 16) it has there;
+//   * OpenCV's constant border costs nothing: a tap outside the image gets WEIGHT 0 (the
+//     column's weight pair is masked once per tile, the row's pair once per pass) and its
+//     address is clamped into the band, so whatever bytes it reads contribute exactly 0 --
+//     no range test and no zero fill anywhere;
 //   * a lane owns ONE output column for the whole tile: the source column, the weight pair
 //     (32 - fx, fx), the word offsets of its three tap words and the two byte-permute selectors
 //     that pair up the channels (r0 r1 g0 g1 | b0 b1) are per-thread constants -- the row
 //     pitch is a multiple of 4 bytes (ws % 4 == 0), so the alignment of a column's 6-byte run
 //     is the same in every row;
-//   * per pixel: 3 + 3 aligned 32-bit shared-memory loads, 4 byte permutes, the same six
-//     dp2a dot products as the quad kernel (the identical integer sum, so the identical
-//     bytes), and the upper row's permuted words are kept when the next output row reuses
-//     them (sy advances by 0 or 1: always when upscaling);
+//   * per pixel: one broadcast load of the row's entry (two row addresses, two weights),
+//     3 + 3 aligned 32-bit shared-memory loads, 4 byte permutes and the same six dp2a dot
+//     products as the quad kernel (the identical integer sum, so the identical bytes);
 //   * a warp's 32 pixels of a row (96 bytes) leave as 24 words: one shuffle and one byte
 //     permute per lane (tests/test_warp_identities.py), three lanes of four store.
 // Tiles that do not qualify (rotation, ws % 4 != 0, a mirrored matrix, a band of one output
 // row that does not fit) run the quad path in the same launch, on a piece of the band buffer.
-constexpr int kBandBytes = 36 * 1024;  // 6 CTAs of 192 threads per SM
+// One band buffer per CTA; the copies of a pass overlap the other five CTAs of the SM.  (Two
+// buffers per CTA, the next pass copied while this one is computed, were measured and lost:
+// 2 x 18 KB 0.469 ms, 2 x 24 KB 0.480 ms against 0.445 ms for 1 x 36 KB -- shorter passes,
+// fewer CTAs; profiles/README.md, r02f.)
+constexpr int kBandBytes = 36 * 1024;
 constexpr int kBandMaxThreads = 512;   // dst_w <= 512 (one column per thread)
 constexpr int kBandPassRows = 16;      // output rows staged and computed at a time
 constexpr int kBandMaxTileRows = 64;   // output rows per CTA (the host picks 16, 32 or 64)
+static_assert(sizeof(QuadSmem) <= (size_t)kBandBytes, "the quad path borrows the band buffers");
 
 struct BandRow {
   uint32_t addr_a;  // shared-memory address of the word holding source pixel (sy, clo) ...
   uint32_t addr_b;  // ... and (sy + 1, clo): the rows' 16-byte phases differ when ws3 % 16 != 0
-  uint32_t gy;      // 32 - fy
-  uint32_t pad;
+  uint32_t gy, uy;  // 32 - fy, fy; 0 for a source row outside the image
 };
 
 __device__ __forceinline__ void bulk_g2s_plain(uint32_t dst_smem, const void* src_gmem,
@@ -705,22 +710,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
-// zero the bytes [begin, end) of shared memory (byte addresses relative to `base`), one warp
-__device__ __forceinline__ void zero_smem_bytes(uint8_t* base, int begin, int end, int lane) {
-  if (end <= begin) return;
-  const int w0 = begin >> 2, w1 = (end + 3) >> 2;
-  for (int w = w0 + lane; w < w1; w += 32) {
-    const int lo = max(begin - 4 * w, 0), hi = min(end - 4 * w, 4);  // bytes [lo, hi) of word w
-    uint32_t* p = reinterpret_cast<uint32_t*>(base) + w;
-    if (hi - lo == 4) {
-      *p = 0u;
-    } else {
-      const uint32_t keep = ~((0xffffffffu >> (8 * (4 - (hi - lo)))) << (8 * lo));
-      *p &= keep;
-    }
-  }
-}
-
 // the quad path as a real call: its registers then do not count against the band path's
 __device__ __noinline__ void warp3_quad_tile_call(
     QuadSmem& sm, const uint8_t* src, const int64_t* src_off, const int32_t* src_hw,
@@ -729,8 +718,8 @@ __device__ __noinline__ void warp3_quad_tile_call(
                                div_wq, NormArgs());
 }
 
-// 56 registers: 6 CTAs of 192 threads per SM, as many as the band buffer allows (the band
-// path itself needs fewer; what spills is the call of the quad path)
+// 56 registers: 6 CTAs of 192 threads per SM, as many as a 36 KB band allows (the band path
+// itself needs fewer; what spills is the call of the quad path)
 __global__ void __maxnreg__(56)
     warp_affine_u8x3_band_kernel(const uint8_t* __restrict__ src,
                                  const int64_t* __restrict__ src_off,
@@ -780,14 +769,16 @@ __global__ void __maxnreg__(56)
   ok = ok && bd_last == 0 && ad_last >= 0 && (ws3 & 3u) == 0 && hs >= 1 && ws >= 1;
   const int sx_lo = X0 >> 10, sx_hi = ((X0 + ad_last) >> 10) + 1;  // columns the taps touch
   const int clo = max(sx_lo, 0), chi = min(sx_hi, ws - 1);         // ... inside the image
-  const int L = ((clo - sx_lo) * 3 + 15) & ~15;  // room for the columns left of the image
-  // row pitch: L, the phase (<= 15), the columns clo .. sx_hi, the tail of the last 16-byte
-  // unit of the copy (<= 15); the three tap words of the last column reach 9 bytes past the
-  // start of its run (covered by the second + 15)
-  const int P = (L + 15 + (sx_hi - clo + 1) * 3 + 15 + 15) & ~15;
+  const bool cols_in = clo <= chi;
+  // Row pitch of the band: 16 bytes in front when there are columns outside the image (a
+  // clamped run may start 3 bytes before column clo), the phase of the row (<= 15), the columns
+  // clo .. chi, the three tap words of the last column (<= 12 bytes from the start of its
+  // run), the tail of the last 16-byte unit of the copy (<= 15).
+  const int L = (sx_lo < 0 || !cols_in) ? 16 : 0;
+  const int P = (L + 15 + (cols_in ? (chi - clo + 1) * 3 : 3) + 12 + 15 + 15) & ~15;
   const int nb_max = kBandBytes / P;  // source rows the buffer holds
   // nb_max >= 2: one output row needs exactly two source rows, so the passes always advance
-  ok = ok && sx_hi - sx_lo < 8192 && nb_max >= 2;
+  ok = ok && nb_max >= 2;
   if (!ok) {
     // the quad path works on tiles of kWarp3TileRows rows
     QuadSmem& qs = *reinterpret_cast<QuadSmem*>(s_band);
@@ -802,14 +793,18 @@ __global__ void __maxnreg__(56)
   // ---- per-thread column constants ---------------------------------------------------------
   const int X = (X0 + ad) >> 5;
   const int sx = X >> 5, fx = X & 31;
-  const uint32_t wg = (32u - (uint32_t)fx) | ((uint32_t)fx << 16);
-  const uint32_t wg32 = wg << 5;  // wg * (gy + uy)
+  // weights of the two taps, 0 for a tap outside the image (constant border 0)
+  const uint32_t wg = ((uint32_t)sx < (uint32_t)ws ? 32u - (uint32_t)fx : 0u) |
+                      ((uint32_t)(sx + 1) < (uint32_t)ws ? (uint32_t)fx << 16 : 0u);
+  // the run is read from a column inside the band, wherever the true column is: a tap that
+  // moved has weight 0 (clo - 1 keeps tap 1 = column clo in place)
+  const int sxc = min(max(sx, clo - 1), max(chi, clo - 1));
   const uint32_t band0 = smem_u32(s_band);
   // phase mod 4 of column clo, the same in every row (ws3 % 4 == 0); BandRow.addr_* is the
   // address of column clo rounded down to a word, so a column's run starts `run` bytes on
   const uint32_t rho = (uint32_t)((reinterpret_cast<uintptr_t>(img) + (size_t)clo * 3u) & 3u);
-  const int run = (sx - clo) * 3 + (int)rho;  // may be negative (columns left of the image)
-  const uint32_t a = (uint32_t)run & 3u;      // alignment of the run
+  const int run = (sxc - clo) * 3 + (int)rho;  // >= -3
+  const uint32_t a = (uint32_t)run & 3u;       // alignment of the run
   const uint32_t colA = (uint32_t)(run - (int)a);     // word A (B = A + 4)
   const uint32_t colZ = colA + (a == 3u ? 8u : 0u);   // word C when the run starts at byte 3, else A
   const uint32_t selA = 0x4130u + 0x1111u * a;               // (A, B) -> r0 r1 g0 g1
@@ -821,40 +816,50 @@ __global__ void __maxnreg__(56)
                  (size_t)(((lane >> 2) * 3 + k4) << 2);
   const uint32_t out_pitch = (uint32_t)dst_w * 3u;
   const uint32_t row_tab = smem_u32(s_row);
+  // fixed-point source rows per output row, for the pass planner (an estimate: the planner
+  // checks the rows it picks)
+  const int y_step = rows > 1 ? max((s_y0[rows - 1] - s_y0[0]) / (rows - 1), 1) : 1;
 
-  uint32_t phase = 0;
-  for (int r_begin = 0; r_begin < rows;) {
-    // ---- the output rows of this pass: as many as the buffer holds source rows for --------
-    const int sy_lo = s_y0[r_begin] >> 10;
-    int r_end = min(r_begin + kBandPassRows, rows);
-    if ((s_y0[r_end - 1] >> 10) + 2 - sy_lo > nb_max) {
-      r_end = r_begin + 1;
-      while ((s_y0[r_end] >> 10) + 2 - sy_lo <= nb_max) ++r_end;  // stops before the probe above
-    }
-    const int sy_hi = (s_y0[r_end - 1] >> 10) + 1;
-    const int nb = sy_hi - sy_lo + 1;
-    const int rlo = max(sy_lo, 0), rhi = min(sy_hi, hs - 1);
-    const bool any = rlo <= rhi && clo <= chi;
-
-    if (tid < r_end - r_begin) {
-      const int Y = s_y0[r_begin + tid] >> 5;
+  struct Pass {
+    int r_begin, r_end, sy_lo, sy_hi;
+    bool any;  // some source pixel of the band lies inside the image
+  };
+  // the output rows of the pass that starts at row r: as many as one buffer holds source
+  // rows for, at most kBandPassRows
+  auto plan = [&](int r) {
+    Pass ps;
+    ps.r_begin = r;
+    ps.sy_lo = s_y0[r] >> 10;
+    int cnt = min(min(((nb_max - 2) << 10) / y_step + 1, kBandPassRows), rows - r);
+    while (cnt > 1 && (s_y0[r + cnt - 1] >> 10) + 2 - ps.sy_lo > nb_max) --cnt;
+    ps.r_end = r + cnt;
+    ps.sy_hi = (s_y0[ps.r_end - 1] >> 10) + 1;
+    ps.any = max(ps.sy_lo, 0) <= min(ps.sy_hi, hs - 1) && cols_in;
+    return ps;
+  };
+  // row table and bulk copies of one pass
+  auto issue = [&](const Pass& ps) {
+    const uint32_t buf = band0;
+    const int rlo = max(ps.sy_lo, 0), rhi = min(ps.sy_hi, hs - 1);
+    if (tid < ps.r_end - ps.r_begin) {
+      const int Y = s_y0[ps.r_begin + tid] >> 5;
       const int sy = Y >> 5, fy = Y & 31;
-      // row j = r - sy_lo of the band starts at j * P; its copy starts at L and lands at the
-      // phase (address mod 16) the row has in global memory.  Rows outside the image are all
-      // zeros: any phase with the right alignment mod 4 will do.
+      // Band row j = r - sy_lo starts at j * P; its copy starts at L and lands at the phase
+      // (address mod 16) the row has in global memory.  A source row outside the image has
+      // weight 0 and reads the nearest row of the band instead.
+      const int ra = ps.any ? min(max(sy, rlo), rhi) : ps.sy_lo;
+      const int rb = ps.any ? min(max(sy + 1, rlo), rhi) : ps.sy_lo;
       const uintptr_t g0 = reinterpret_cast<uintptr_t>(img) + (size_t)clo * 3u;
-      const uintptr_t ga = g0 + (size_t)(uint32_t)max(sy, 0) * ws3;
-      const uintptr_t gb = g0 + (size_t)(uint32_t)max(sy + 1, 0) * ws3;
+      const uintptr_t ga = g0 + (size_t)(uint32_t)max(ra, 0) * ws3;
+      const uintptr_t gb = g0 + (size_t)(uint32_t)max(rb, 0) * ws3;
       BandRow br;
-      br.addr_a = band0 + (uint32_t)((sy - sy_lo) * P + L) + ((uint32_t)ga & 12u);
-      br.addr_b = band0 + (uint32_t)((sy + 1 - sy_lo) * P + L) + ((uint32_t)gb & 12u);
-      br.gy = 32u - (uint32_t)fy;
-      br.pad = 0u;
+      br.addr_a = buf + (uint32_t)((ra - ps.sy_lo) * P + L) + ((uint32_t)ga & 12u);
+      br.addr_b = buf + (uint32_t)((rb - ps.sy_lo) * P + L) + ((uint32_t)gb & 12u);
+      br.gy = (uint32_t)sy < (uint32_t)hs ? 32u - (uint32_t)fy : 0u;
+      br.uy = (uint32_t)(sy + 1) < (uint32_t)hs ? (uint32_t)fy : 0u;
       s_row[tid] = br;
     }
-    // ---- stage the band: one bulk copy per source row, issued by the lanes of warp 0, which
-    //      also waits for them (the other warps wait at the barrier below) ------------------
-    if (tid < 32 && any) {
+    if (tid < 32 && ps.any) {  // one bulk copy per source row, issued by the lanes of warp 0
       const uint32_t span = (uint32_t)(chi - clo + 1) * 3u;
       uint32_t bytes = 0;
       for (int r = rlo + lane; r <= rhi; r += 32) {
@@ -867,67 +872,59 @@ __global__ void __maxnreg__(56)
       for (int r = rlo + lane; r <= rhi; r += 32) {
         const uintptr_t g = reinterpret_cast<uintptr_t>(img) + (size_t)r * ws3 + (size_t)clo * 3u;
         const uint32_t n16 = (uint32_t)(((g & 15u) + span + 15u) & ~15u);
-        bulk_g2s_plain(band0 + (uint32_t)((r - sy_lo) * P + L),
+        bulk_g2s_plain(buf + (uint32_t)((r - ps.sy_lo) * P + L),
                        reinterpret_cast<const void*>(g & ~(uintptr_t)15), n16, &s_bar);
       }
-      mbar_wait(&s_bar, phase);
     }
-    phase ^= any ? 1u : 0u;
-    // ---- zeros outside the image (constant border), one warp per band row ---------------
-    if (sy_lo < 0 || sy_hi > hs - 1 || sx_lo < 0 || sx_hi > ws - 1) {
-      __syncthreads();  // the copies have landed (warp 0 saw the barrier flip)
-      const int nwarps = blockDim.x >> 5;
-      for (int j = tid >> 5; j < nb; j += nwarps) {
-        const int r = sy_lo + j;
-        uint8_t* rowp = s_band + (size_t)j * P;
-        if (r < 0 || r > hs - 1 || !any) {
-          zero_smem_bytes(rowp, 0, P, lane);
-        } else {
-          const uintptr_t g = reinterpret_cast<uintptr_t>(img) + (size_t)r * ws3 + (size_t)clo * 3u;
-          const int first = L + (int)(g & 15u);  // byte of column clo in this row
-          if (sx_lo < 0) zero_smem_bytes(rowp, 0, first, lane);
-          __syncwarp();  // an image narrower than two pixels: both ranges may share a word
-          if (sx_hi > ws - 1) zero_smem_bytes(rowp, first + (chi - clo + 1) * 3, P, lane);
-        }
-      }
+  };
+
+  uint32_t phase = 0u;  // parity of the barrier's next completion
+  Pass cur = plan(0);
+  issue(cur);
+#pragma unroll 1
+  for (;;) {
+    if (cur.any) {
+      if (tid < 32) mbar_wait(&s_bar, phase);  // the other warps wait at the barrier below
+      phase ^= 1u;
     }
     __syncthreads();
 
     // ---- one column, r_end - r_begin rows ---------------------------------------------------
     {
-      const int cnt = r_end - r_begin;
-      uint8_t* o = out + (size_t)r_begin * out_pitch;
+      const int cnt = cur.r_end - cur.r_begin;
+      uint8_t* o = out + (size_t)cur.r_begin * out_pitch;
 #pragma unroll 4
       for (int i = 0; i < cnt; ++i) {
-        const uint4 rc = lds128(row_tab + 16u * (uint32_t)i);  // addr_a, addr_b, gy
+        const uint4 rc = lds128(row_tab + 16u * (uint32_t)i);  // addr_a, addr_b, gy, uy
         const uint32_t A0 = lds32(rc.x + colA), B0 = lds32(rc.x + colA + 4u);
         const uint32_t Z0 = lds32(rc.x + colZ);
         const uint32_t A1 = lds32(rc.y + colA), B1 = lds32(rc.y + colA + 4u);
         const uint32_t Z1 = lds32(rc.y + colZ);
         const uint32_t arg = __byte_perm(A0, B0, selA), abb = __byte_perm(B0, Z0, selB);
         const uint32_t brg = __byte_perm(A1, B1, selA), bbb = __byte_perm(B1, Z1, selB);
-        const uint32_t wt = wg * rc.z, wu = wg32 - wt;  // wg * gy, wg * uy
+        const uint32_t wt = wg * rc.z, wu = wg * rc.w;  // (32 - fx, fx) x (gy, uy)
         const uint32_t c0 = __dp2a_lo(wu, brg, __dp2a_lo(wt, arg, 512u)) >> 10;
         const uint32_t c1 = __dp2a_hi(wu, brg, __dp2a_hi(wt, arg, 512u)) >> 10;
         const uint32_t c2 = __dp2a_lo(wu, bbb, __dp2a_lo(wt, abb, 512u)) >> 10;
         const uint32_t px = __byte_perm(__byte_perm(c0, c1, 0x0040), c2, 0x5410);
-        const uint32_t nxt = __shfl_down_sync(0xffffffffu, px, 1);
+        const uint32_t nxt_px = __shfl_down_sync(0xffffffffu, px, 1);
         if (k4 < 3) {
-          const uint32_t w = __byte_perm(px, nxt, selO);
+          const uint32_t w = __byte_perm(px, nxt_px, selO);
           asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(o), "r"(w) : "memory");
         }
         o += out_pitch;
       }
     }
-    r_begin = r_end;
-    if (r_begin < rows) {
-      // the next pass overwrites the band and the row table: order this pass's generic-proxy
-      // accesses (reads, zero fill) before the bulk copies of the async proxy
-      fence_proxy_async();
-      __syncthreads();
-    }
+    if (cur.r_end >= rows) break;
+    // the next pass overwrites the band and the row table: order this pass's generic-proxy
+    // reads before the bulk copies of the async proxy
+    fence_proxy_async();
+    __syncthreads();
+    cur = plan(cur.r_end);
+    issue(cur);
   }
 }
+
 
 }  // namespace pc
 
@@ -1020,6 +1017,16 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
              n * ((p->dst_h + tile_rows - 1) / tile_rows) < want)
         tile_rows >>= 1;
       const int tiles_b = (p->dst_h + tile_rows - 1) / tile_rows;
+      if (kBandBytes > 47 * 1024) {  // (not the case today) large dynamic shared memory opt-in
+        static bool done[64];
+        int dev = 0;
+        PC_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !done[dev]) {
+          PC_CUDA(cudaFuncSetAttribute(warp_affine_u8x3_band_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kBandBytes));
+          done[dev] = true;
+        }
+      }
       warp_affine_u8x3_band_kernel<<<(unsigned)(n * tiles_b), p->dst_w, kBandBytes, st>>>(
           d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tile_rows, tiles_b,
           make_fastdiv((uint32_t)(p->dst_w >> 2)));

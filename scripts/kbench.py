@@ -146,6 +146,12 @@ def main():
         roi = float(np.mean((x1 - x0) * (y1 - y0) * 3))
         report("warp_affine_u8 480x640 -> 256x192 (dst+ROI)", n, "crops", 147456 + roi, med, mn)
         report("warp_affine_u8 (dst bytes only)", n, "crops", 147456, med, mn)
+        # training-time crops: every crop rotated (the quad path inside the band kernel)
+        rot = torch.from_numpy(rng.uniform(-40, 40, n).astype(np.float32)).to(dev)
+        _, inv_r = codec.affine_matrices(center, scale, rot, [192, 256])
+        fn = lambda: codec.warp_affine(images, off, hw, inv_r, [192, 256], out=out)  # noqa: E731
+        med, mn = timeit(fn, args.iters)
+        report("warp_affine_u8 rotated +-40 deg (dst+ROI of rot 0)", n, "crops", 147456 + roi, med, mn)
         outf = torch.empty(n, 3, 256, 192, device=dev)
         m255 = (np.array([0.485, 0.456, 0.406]) * 255.0).tolist()
         s255 = (np.array([0.229, 0.224, 0.255]) * 255.0).tolist()
