@@ -215,8 +215,10 @@ def make_decode_params(num_joints: int, height: int, width: int, pixel_std: floa
 
 def topdown_decode(heatmap: torch.Tensor, center: torch.Tensor, scale: torch.Tensor,
                    score: torch.Tensor, flipped: Optional[torch.Tensor] = None,
-                   params: Optional["_lib.TopDownDecodeParams"] = None, **kwargs):
-    """heatmap f32 [N,K,H,W] (+ optional flipped pair) -> (all_preds [N,K,3], all_boxes [N,6])."""
+                   params: Optional["_lib.TopDownDecodeParams"] = None,
+                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, **kwargs):
+    """heatmap f32 [N,K,H,W] (+ optional flipped pair) -> (all_preds [N,K,3], all_boxes [N,6]);
+    ``out`` = (preds, boxes) writes into caller-owned contiguous float32 tensors."""
     heatmap = _f32(heatmap, "heatmap")
     if heatmap.dim() != 4:
         raise ValueError("`heatmap` must have shape [N, K, H, W]")
@@ -234,8 +236,16 @@ def topdown_decode(heatmap: torch.Tensor, center: torch.Tensor, scale: torch.Ten
             raise ValueError("`flipped` must have the shape of `heatmap`")
     else:
         flipped = None
-    preds = torch.empty((n, k, 3), dtype=torch.float32, device=heatmap.device)
-    boxes = torch.empty((n, 6), dtype=torch.float32, device=heatmap.device)
+    if out is not None:
+        preds, boxes = out
+        for t, shape in ((preds, (n, k, 3)), (boxes, (n, 6))):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                    and tuple(t.shape) == shape):
+                raise ValueError(f"`out` must hold contiguous float32 CUDA tensors [N,K,3], [N,6]; "
+                                 f"got {tuple(t.shape)} for {shape}")
+    else:
+        preds = torch.empty((n, k, 3), dtype=torch.float32, device=heatmap.device)
+        boxes = torch.empty((n, 6), dtype=torch.float32, device=heatmap.device)
     with torch.cuda.device(heatmap.device):
         _lib.call("pc_topdown_decode", _lib.device_ptr(heatmap), _lib.device_ptr(flipped),
                   _lib.device_ptr(center), _lib.device_ptr(scale), _lib.device_ptr(score),

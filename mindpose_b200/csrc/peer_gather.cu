@@ -10,8 +10,15 @@
 //     replicas), when the allocation has one, or
 //   * the peer-mapped address of the table on each rank (P2P stores over NVLink).
 // The tables are symmetric-memory allocations made by the caller
-// (mindpose_b200/dist.py::PeerGather, torch.distributed._symmetric_memory); a barrier over
-// the same allocation's signal pads orders the ranks afterwards.
+// (mindpose_b200/dist.py::PeerGather, torch.distributed._symmetric_memory).
+//
+// Ordering between ranks, two forms:
+//   * pc_scatter_results: the caller runs a barrier over the allocation's signal pads after
+//     the kernel (one more launch, and every rank waits for the slowest one at once);
+//   * pc_scatter_results_signal + pc_wait_peer_flags: the last CTA of the scatter kernel
+//     publishes the step number in a flag word on every rank (release, system scope) and the
+//     consumer waits for the flags of a step only when it reads that step's table -- one
+//     step later in bench.py, so the wait is off the critical path of the step.
 #include "common.cuh"
 
 namespace pc {
@@ -22,10 +29,17 @@ struct PeerTables {
   float* table[kMaxPeers];
 };
 
+struct PeerFlags {
+  uint32_t* flags[kMaxPeers];  // flags[p]: the flag array (one word per source rank) on rank p
+};
+
+template <bool SIGNAL>
 __global__ void __launch_bounds__(256)
     scatter_results_kernel(const float* __restrict__ preds, const float* __restrict__ boxes,
                            const PeerTables peers, int num_peers, float* multicast,
-                           int64_t row_offset, int kw, int width, int64_t total) {
+                           int64_t row_offset, int kw, int width, int64_t total,
+                           const PeerFlags pf, int num_flag_peers, int my_rank, uint32_t step,
+                           int* __restrict__ counter) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / width;
@@ -40,28 +54,65 @@ __global__ void __launch_bounds__(256)
     }
   }
   // make the remote stores visible system-wide before the kernel retires (the caller's
-  // barrier kernel then signals the peers)
+  // barrier kernel then signals the peers) ...
   __threadfence_system();
+  if (SIGNAL) {
+    // ... or before the last CTA to get here publishes the step on every rank
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int done = atomicAdd(counter, 1);
+      if (done == (int)gridDim.x - 1) {
+        *counter = 0;  // for the next launch (stream order)
+        __threadfence_system();
+        for (int p = 0; p < num_flag_peers; ++p)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[p] + my_rank),
+                       "r"(step)
+                       : "memory");
+      }
+    }
+  }
+}
+
+// One thread per source rank: wait until that rank has published `step` (or a later one) in
+// this rank's flag array.  The awaited kernels run on OTHER GPUs (one rank per GPU).
+__global__ void wait_peer_flags_kernel(const uint32_t* __restrict__ flags, int num_peers,
+                                       uint32_t step) {
+  const int p = threadIdx.x;
+  if (p >= num_peers) return;
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
+    if ((int32_t)(v - step) >= 0) break;
+    __nanosleep(200);
+    if (spins > (1u << 26)) __trap();  // > 13 s: a peer died; fail instead of hanging the GPU
+  }
 }
 
 }  // namespace pc
 
 using namespace pc;
 
-extern "C" int pc_scatter_results(const float* d_preds, const float* d_boxes,
-                                  void* const* h_peer_tables, int32_t num_peers,
-                                  void* d_multicast_table, int64_t row_offset,
-                                  int32_t num_joints, int64_t n, void* stream) {
+static int scatter_launch(const float* d_preds, const float* d_boxes, void* const* h_peer_tables,
+                          int32_t num_peers, void* d_multicast_table, int64_t row_offset,
+                          int32_t num_joints, int64_t n, void* const* h_peer_flags,
+                          int32_t num_flag_peers, int32_t my_rank, uint32_t step,
+                          int32_t* d_counter, void* stream) {
+  const bool signal = h_peer_flags != nullptr;
   PC_REQUIRE(n >= 0 && row_offset >= 0, PC_ERR_INVALID_ARGUMENT,
              "pc_scatter_results: negative n / row_offset");
+  PC_REQUIRE(!signal || (num_flag_peers >= 1 && num_flag_peers <= kMaxPeers && my_rank >= 0 &&
+                         my_rank < num_flag_peers && d_counter),
+             PC_ERR_INVALID_ARGUMENT,
+             "pc_scatter_results_signal: need 1..%d flag arrays, my_rank inside, a counter",
+             kMaxPeers);
   PC_REQUIRE(num_joints >= 1 && num_joints <= PC_MAX_JOINTS, PC_ERR_INVALID_ARGUMENT,
              "pc_scatter_results: num_joints %d outside [1, %d]", num_joints, PC_MAX_JOINTS);
   PC_REQUIRE(d_multicast_table || (num_peers >= 1 && num_peers <= kMaxPeers && h_peer_tables),
              PC_ERR_INVALID_ARGUMENT,
              "pc_scatter_results: need a multicast table or 1..%d peer tables", kMaxPeers);
-  if (n == 0) return PC_OK;
-  PC_REQUIRE(d_preds && d_boxes, PC_ERR_INVALID_ARGUMENT,
+  PC_REQUIRE(n == 0 || (d_preds && d_boxes), PC_ERR_INVALID_ARGUMENT,
              "pc_scatter_results: NULL tensor pointer");
+  if (n == 0 && !signal) return PC_OK;
   PeerTables pt;
   for (int p = 0; p < kMaxPeers; ++p) pt.table[p] = nullptr;
   if (!d_multicast_table)
@@ -70,14 +121,61 @@ extern "C" int pc_scatter_results(const float* d_preds, const float* d_boxes,
                  "pc_scatter_results: peer table %d is NULL", p);
       pt.table[p] = static_cast<float*>(h_peer_tables[p]);
     }
+  PeerFlags pf;
+  for (int p = 0; p < kMaxPeers; ++p) pf.flags[p] = nullptr;
+  if (signal)
+    for (int p = 0; p < num_flag_peers; ++p) {
+      PC_REQUIRE(h_peer_flags[p] != nullptr, PC_ERR_INVALID_ARGUMENT,
+                 "pc_scatter_results_signal: flag array %d is NULL", p);
+      pf.flags[p] = static_cast<uint32_t*>(h_peer_flags[p]);
+    }
   const int kw = num_joints * 3, width = kw + 6;
   const int64_t total = n * width;
   int64_t blocks = (total + 255) / 256;
+  if (blocks < 1) blocks = 1;  // an empty shard still signals
   const int64_t cap = (int64_t)sm_count_cached() * 8;
   if (cap > 0 && blocks > cap) blocks = cap;
-  scatter_results_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      d_preds, d_boxes, pt, d_multicast_table ? 0 : num_peers,
-      static_cast<float*>(d_multicast_table), row_offset, kw, width, total);
+  if (signal)
+    scatter_results_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_preds, d_boxes, pt, d_multicast_table ? 0 : num_peers,
+        static_cast<float*>(d_multicast_table), row_offset, kw, width, total, pf,
+        num_flag_peers, my_rank, step, d_counter);
+  else
+    scatter_results_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_preds, d_boxes, pt, d_multicast_table ? 0 : num_peers,
+        static_cast<float*>(d_multicast_table), row_offset, kw, width, total, pf, 0, 0, 0u,
+        nullptr);
+  PC_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+extern "C" int pc_scatter_results(const float* d_preds, const float* d_boxes,
+                                  void* const* h_peer_tables, int32_t num_peers,
+                                  void* d_multicast_table, int64_t row_offset,
+                                  int32_t num_joints, int64_t n, void* stream) {
+  return scatter_launch(d_preds, d_boxes, h_peer_tables, num_peers, d_multicast_table,
+                        row_offset, num_joints, n, nullptr, 0, 0, 0u, nullptr, stream);
+}
+
+extern "C" int pc_scatter_results_signal(const float* d_preds, const float* d_boxes,
+                                         void* const* h_peer_tables, int32_t num_peers,
+                                         void* d_multicast_table, int64_t row_offset,
+                                         int32_t num_joints, int64_t n,
+                                         void* const* h_peer_flags, int32_t num_flag_peers,
+                                         int32_t my_rank, uint32_t step, int32_t* d_counter,
+                                         void* stream) {
+  PC_REQUIRE(h_peer_flags != nullptr, PC_ERR_INVALID_ARGUMENT,
+             "pc_scatter_results_signal: flag arrays are NULL");
+  return scatter_launch(d_preds, d_boxes, h_peer_tables, num_peers, d_multicast_table,
+                        row_offset, num_joints, n, h_peer_flags, num_flag_peers, my_rank, step,
+                        d_counter, stream);
+}
+
+extern "C" int pc_wait_peer_flags(const uint32_t* d_flags, int32_t num_peers, uint32_t step,
+                                  void* stream) {
+  PC_REQUIRE(d_flags != nullptr && num_peers >= 1 && num_peers <= kMaxPeers,
+             PC_ERR_INVALID_ARGUMENT, "pc_wait_peer_flags: need flags of 1..%d ranks", kMaxPeers);
+  wait_peer_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_flags, num_peers, step);
   PC_CUDA(cudaGetLastError());
   return PC_OK;
 }

@@ -97,17 +97,38 @@ def all_gather_keypoints(preds: torch.Tensor, boxes: torch.Tensor, total: int,
     return pending if async_op else pending.wait()
 
 
+class GatherTicket:
+    """One gather in flight (``PeerGather.gather_async``): this rank's rows are on their way
+    into every rank's table; ``wait()`` orders the caller's current stream after the arrival
+    of EVERY rank's rows of that step and returns the views of the gathered table."""
+
+    def __init__(self, owner, step: int, table: torch.Tensor):
+        self._owner, self.step, self._table = owner, step, table
+
+    def wait(self):
+        self._owner._wait(self.step)
+        return unpack_results(self._table, self._owner.k)
+
+
 class PeerGather:
     """The keypoint all-gather as ONE kernel of direct stores into peer memory
-    (``pc_scatter_results``) plus a barrier, instead of an NCCL collective: every rank's
-    gathered table is a symmetric-memory allocation, and each rank writes its block of rows
-    into all of them -- through the NVSwitch multicast mapping when the allocation has one,
-    else through the peer-mapped addresses over NVLink.
+    (``pc_scatter_results_signal``) instead of an NCCL collective: every rank's gathered table
+    is a symmetric-memory allocation, and each rank writes its block of rows into all of
+    them -- through the NVSwitch multicast mapping when the allocation has one, else through
+    the peer-mapped addresses over NVLink.  The kernel's last CTA then publishes the step
+    number in a flag word on every rank; a rank waits for the flags of a step
+    (``pc_wait_peer_flags``, a one-warp kernel) only when it reads that step's table.
 
-    Two tables alternate, so a rank that is one step ahead never overwrites rows a peer may
-    still be reading (the barrier keeps ranks within one step of each other).  ``gather``
-    returns views of this rank's own table; they stay valid until the step after next.
+    ``gather()`` scatters and waits at once.  ``gather_async()`` returns a ``GatherTicket``;
+    calling ``ticket.wait()`` one step later takes the wait for the slowest rank off the
+    critical path of the step (bench.py does that).  THREE tables alternate: a peer may
+    overwrite the table of step s as soon as it has seen this rank's flag of step s + 2, which
+    this rank only publishes after everything it enqueued before ``gather_async`` of step
+    s + 2 -- so the views a ticket returns are valid until the second ``gather*`` call after
+    the one that made the ticket, for work enqueued on the same stream.
     """
+
+    TABLES = 3
 
     def __init__(self, rows_per_rank: int, num_joints: int, device: torch.device,
                  group: Optional[dist.ProcessGroup] = None):
@@ -124,7 +145,7 @@ class PeerGather:
         self.width = self.k * 3 + 6
         grp = group if group is not None else dist.group.WORLD
         self.tables, self.handles, self._peers, self._mc = [], [], [], []
-        for _ in range(2):
+        for _ in range(self.TABLES):
             t = symm_mem.empty((self.world * self.rows, self.width), dtype=torch.float32,
                                device=device)
             h = symm_mem.rendezvous(t, group=grp)
@@ -135,23 +156,47 @@ class PeerGather:
             mc = int(getattr(h, "multicast_ptr", 0) or 0)
             self._mc.append(mc)
         self.multicast = all(m != 0 for m in self._mc)
-        self._turn = 0
+        # flags[r] on this rank = the last step whose rows rank r has stored here
+        self._flags = symm_mem.empty((max(self.world, 32),), dtype=torch.int32, device=device)
+        self._flags.zero_()
+        fh = symm_mem.rendezvous(self._flags, group=grp)
+        self._flag_handle = fh
+        self._peer_flags = (ctypes.c_void_p * self.world)(*[int(p) for p in fh.buffer_ptrs])
+        self._counter = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        fh.barrier(channel=0)            # nobody signals before everybody has zeroed its flags
+        self._step = 0                   # steps count from 1 (flags start at 0)
+        self._waited = 0
 
-    def gather(self, preds: torch.Tensor, boxes: torch.Tensor):
-        """preds f32 [rows,K,3], boxes f32 [rows,6] of this rank -> (all_preds
-        [world*rows,K,3], all_boxes [world*rows,6]) once every rank's rows have landed."""
+    def gather_async(self, preds: torch.Tensor, boxes: torch.Tensor) -> GatherTicket:
+        """preds f32 [rows,K,3], boxes f32 [rows,6] of this rank: one kernel on the current
+        stream stores them into every rank's table and signals; nothing waits."""
         if preds.shape[0] != self.rows or boxes.shape[0] != self.rows:
             raise ValueError(f"expected {self.rows} rows per rank, got {preds.shape[0]}")
         if not (preds.is_cuda and preds.is_contiguous() and boxes.is_contiguous()):
             raise ValueError("preds / boxes must be contiguous CUDA tensors")
-        i = self._turn
-        self._turn ^= 1
+        self._step += 1
+        i = self._step % self.TABLES
         lib = self._lib
-        lib.call("pc_scatter_results", lib.device_ptr(preds), lib.device_ptr(boxes),
+        lib.call("pc_scatter_results_signal", lib.device_ptr(preds), lib.device_ptr(boxes),
                  self._peers[i], self.world, self._mc[i] if self.multicast else None,
-                 self.rank * self.rows, self.k, self.rows, lib.current_stream())
-        self.handles[i].barrier(channel=0)
-        return unpack_results(self.tables[i], self.k)
+                 self.rank * self.rows, self.k, self.rows, self._peer_flags, self.world,
+                 self.rank, self._step & 0xFFFFFFFF, lib.device_ptr(self._counter),
+                 lib.current_stream())
+        return GatherTicket(self, self._step, self.tables[i])
+
+    def _wait(self, step: int) -> None:
+        if step <= self._waited:         # flags only grow: a later wait covers earlier steps
+            return
+        lib = self._lib
+        lib.call("pc_wait_peer_flags", lib.device_ptr(self._flags), self.world,
+                 step & 0xFFFFFFFF, lib.current_stream())
+        self._waited = step
+
+    def gather(self, preds: torch.Tensor, boxes: torch.Tensor):
+        """-> (all_preds [world*rows,K,3], all_boxes [world*rows,6]) once every rank's rows
+        have landed (scatter + wait on the current stream)."""
+        return self.gather_async(preds, boxes).wait()
 
 
 def make_gatherer(rows_per_rank: int, num_joints: int, device: torch.device,

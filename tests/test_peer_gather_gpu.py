@@ -1,5 +1,7 @@
-"""Peer-memory keypoint gather (pc_scatter_results + symmetric memory) on 2 GPUs against
-the NCCL all-gather.  Skipped on boxes with one GPU."""
+"""Peer-memory keypoint gather (pc_scatter_results_signal + pc_wait_peer_flags over symmetric
+memory) on 2 GPUs against the NCCL all-gather: the blocking form and the deferred form
+(ticket of step t waited for in step t + 1, three alternating tables).  Skipped on boxes with
+one GPU; bench.py verifies the gathered table at every N it runs at."""
 import os
 import socket
 import sys
@@ -31,15 +33,37 @@ def _worker(rank, world, port, rows, k, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         g = pdist.PeerGather(rows, k, dev)
-        for step in range(3):       # both tables, reuse of the first
+
+        def inputs(step):
             idx = torch.arange(rank * rows, (rank + 1) * rows, dtype=torch.float32, device=dev)
             preds = (idx[:, None, None] * 10 + step +
                      torch.arange(k * 3, dtype=torch.float32, device=dev).reshape(1, k, 3))
-            boxes = idx[:, None] * 100 + torch.arange(6, dtype=torch.float32, device=dev)[None]
-            got_p, got_b = g.gather(preds.contiguous(), boxes.contiguous())
+            boxes = idx[:, None] * 100 + step + torch.arange(6, dtype=torch.float32, device=dev)[None]
+            return preds.contiguous(), boxes.contiguous()
+
+        for step in range(4):       # blocking form: all three tables, reuse of the first
+            preds, boxes = inputs(step)
+            got_p, got_b = g.gather(preds, boxes)
             want_p, want_b = pdist.all_gather_keypoints(preds, boxes, world * rows)
             torch.cuda.synchronize()
             assert torch.equal(got_p, want_p) and torch.equal(got_b, want_b), (rank, step)
+        # deferred form: the ticket of step t is waited for after the scatter of step t + 1,
+        # with rank 1 lagging so that rank 0 runs a step ahead
+        prev, prev_want = None, None
+        for step in range(4, 12):
+            if rank == 1:
+                torch.cuda._sleep(3_000_000)
+            preds, boxes = inputs(step)
+            want = pdist.all_gather_keypoints(preds, boxes, world * rows)
+            ticket = g.gather_async(preds, boxes)
+            if prev is not None:
+                got_p, got_b = prev.wait()
+                assert torch.equal(got_p, prev_want[0]) and torch.equal(got_b, prev_want[1]), \
+                    (rank, step)
+            prev, prev_want = ticket, want
+        got_p, got_b = prev.wait()
+        torch.cuda.synchronize()
+        assert torch.equal(got_p, prev_want[0]) and torch.equal(got_b, prev_want[1])
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(g.multicast)]))
     finally:
         dist.destroy_process_group()
