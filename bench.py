@@ -668,9 +668,8 @@ def run_ours(args, wl):
     gatherer = None
     if world > 1 and not args.nccl_gather:
         gatherer = pdist.make_gatherer(n, K, dev)
-    pending = [None]     # ticket of the previous step's gather
 
-    def step(record):
+    def step(record=False):
         if record:
             e0, e1, e2 = ev(), ev(), ev()
             e0.record(stream)
@@ -685,22 +684,17 @@ def run_ours(args, wl):
             marks.append((e0, e1, e2))
         if world > 1:
             if gatherer is not None:
-                # one kernel of peer stores + a flag; the wait for the other ranks' rows of
-                # THIS step is enqueued in the next step, after its scatter
-                ticket = gatherer.gather_async(preds, bxs)
-                if pending[0] is not None:
-                    pending[0].wait()
-                pending[0] = ticket
+                # one kernel of peer stores + a flag; what is waited for here is the arrival
+                # of the PREVIOUS step's rows (this step's are waited for in the next step)
+                gatherer.gather_async(preds, bxs)
+                gatherer.wait_lag(1)
             else:                        # NCCL all-gather
                 pdist.all_gather_keypoints(preds, bxs, world * n)
         return preds, bxs
 
     def drain():
-        if pending[0] is not None:
-            out = pending[0].wait()
-            pending[0] = None
-            return out
-        return None
+        if gatherer is not None:
+            gatherer.wait_lag(0)
 
     def fence():
         if world > 1:
@@ -708,40 +702,75 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     for _ in range(warmup):
-        step(False)
+        step()
     drain()
     fence()
 
     # ---- the gathered table, checked once: every rank holds every rank's rows bit for bit
     gather_verified = None
     if world > 1:
-        preds, bxs = step(False)
-        got = drain() if gatherer is not None else pdist.all_gather_keypoints(preds, bxs, world * n)
-        mine = torch.stack([preds.view(torch.int32).to(torch.int64).sum(),
-                            bxs.view(torch.int32).to(torch.int64).sum()])
+        preds, bxs = step()
+        drain()
+        got = gatherer.table_of_lag(0) if gatherer is not None else \
+            pdist.all_gather_keypoints(preds, bxs, world * n)
+        i64sum = lambda t: t.contiguous().view(torch.int32).to(torch.int64).sum()  # noqa: E731
+        mine = torch.stack([i64sum(preds), i64sum(bxs)])
         owners = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(owners, mine)
         okv = 1
         for r in range(world):
-            blk = torch.stack([got[0][r * n:(r + 1) * n].contiguous().view(torch.int32).to(torch.int64).sum(),
-                               got[1][r * n:(r + 1) * n].contiguous().view(torch.int32).to(torch.int64).sum()])
+            blk = torch.stack([i64sum(got[0][r * n:(r + 1) * n]), i64sum(got[1][r * n:(r + 1) * n])])
             okv &= int(torch.equal(blk, owners[r]))
         okt = torch.tensor([okv], device=dev)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         gather_verified = bool(okt.item())
         fence()
 
+    # ---- the split of a step between its kernels: a few eager steps with events inside
+    for _ in range(12):
+        step(record=True)
+    drain()
+    fence()
+    warp_ms = float(np.median([a.elapsed_time(b) for a, b, _ in marks[2:]]))
+    dec_ms = float(np.median([b.elapsed_time(c) for _, b, c in marks[2:]]))
+
+    # ---- the timed steps: replays of ONE captured CUDA graph of the step (three steps when
+    # the peer gather rotates its three tables), so that the host's launch work -- about as
+    # long as the kernels themselves -- is not what is measured; NCCL gathers run eagerly
+    unroll = pdist.PeerGather.TABLES if gatherer is not None else 1
+    graph, how = None, "eager launches"
+    if not args.no_graph and (world == 1 or gatherer is not None):
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(unroll):
+                    step()
+            how = f"CUDA graph of {unroll} step(s), replayed"
+            if gatherer is not None:
+                gatherer.captured(unroll)  # the capture itself ran nothing
+                graph.replay()             # warm the graph once (and check it runs)
+                gatherer.replayed(unroll)
+            else:
+                graph.replay()
+            drain()
+            fence()
+        except Exception as e:           # capture refused: fall back to eager launches
+            graph, how = None, f"eager launches ({type(e).__name__}: graph capture refused)"
+            torch.cuda.synchronize()
+    q, r = (steps // unroll, steps % unroll) if graph is not None else (0, steps)
     t_start, t_end = ev(), ev()
     with ClockSampler(local_rank) as clocks:
         t_start.record(stream)
-        for _ in range(steps):
-            step(True)
+        for _ in range(q):
+            graph.replay()
+            if gatherer is not None:
+                gatherer.replayed(unroll)
+        for _ in range(r):
+            step()
         drain()
         t_end.record(stream)
         fence()
     total_ms = t_start.elapsed_time(t_end)
-    warp_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in marks]))
-    dec_ms = float(np.mean([b.elapsed_time(c) for _, b, c in marks]))
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -884,6 +913,7 @@ def run_ours(args, wl):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": headline_config(wl, n),
             "kernels_ms": {"warp": warp_ms, "decode": dec_ms},
+            "launch": how,
             # the kernel with the largest share of the timed step, then the other one
             "roofline": dominant,
             "roofline_other": other,
@@ -920,6 +950,8 @@ def main():
     ap.add_argument("--upload", default=None, choices=["full", "roi", "roi_kernel"],
                     help="e2e: how the source images cross PCIe (default: codec.DEFAULT_UPLOAD)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch every timed step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="N > 1: use the NCCL all-gather instead of the peer-memory stores")
     args = ap.parse_args()

@@ -312,22 +312,27 @@ int pc_oks_nms_f64(const double* d_kpts, const double* d_area, double* d_score,
 int pc_scatter_results(const float* d_preds, const float* d_boxes, void* const* h_peer_tables,
                        int32_t num_peers, void* d_multicast_table, int64_t row_offset,
                        int32_t num_joints, int64_t n, void* stream);
-/* The same with the ordering folded in: after its stores the kernel's last CTA writes `step`
- * (release, system scope) into word my_rank of the flag array of every rank --
+/* The same with the ordering folded in: after its stores the kernel's last CTA increments
+ * the step number *d_step (one u32 in this rank's memory, zero-initialised by the caller) and
+ * writes it (release, system scope) into word my_rank of the flag array of every rank --
  * h_peer_flags is a HOST array of num_flag_peers device pointers to u32 [num_flag_peers]
  * arrays in symmetric memory, this rank's own included; d_counter is one zero-initialised
- * i32 in this rank's memory (the kernel leaves it at zero).  A rank reads the gathered table
- * of step s after pc_wait_peer_flags(its own flag array, num_peers, s): one tiny kernel that
- * returns once every source rank has published a step >= s (steps are compared modulo 2^32;
- * a peer that never arrives traps the kernel after about 13 s instead of hanging the GPU).
- * A table may be rewritten by a peer as soon as that peer has seen this rank's flag for a
- * LATER step, so callers alternate three tables when the wait is deferred by one step. */
+ * i32 in this rank's memory (the kernel leaves it at zero).  The step number lives in device
+ * memory so that a captured CUDA graph of the step signals a new number at every replay.
+ * A rank reads the gathered table of its scatter number s after pc_wait_peer_flags(its own
+ * flag array, num_peers, d_step, lag) with lag = (scatters issued so far) - s: one tiny
+ * kernel that returns once every source rank has published a step >= *d_step - lag (compared
+ * modulo 2^32; a peer that never arrives traps the kernel after about 13 s instead of hanging
+ * the GPU).  A table may be rewritten by a peer as soon as that peer has seen this rank's flag
+ * for a LATER step, so callers alternate three tables when the wait is deferred by one step. */
 int pc_scatter_results_signal(const float* d_preds, const float* d_boxes,
                               void* const* h_peer_tables, int32_t num_peers,
                               void* d_multicast_table, int64_t row_offset, int32_t num_joints,
                               int64_t n, void* const* h_peer_flags, int32_t num_flag_peers,
-                              int32_t my_rank, uint32_t step, int32_t* d_counter, void* stream);
-int pc_wait_peer_flags(const uint32_t* d_flags, int32_t num_peers, uint32_t step, void* stream);
+                              int32_t my_rank, uint32_t* d_step, int32_t* d_counter,
+                              void* stream);
+int pc_wait_peer_flags(const uint32_t* d_flags, int32_t num_peers, const uint32_t* d_step,
+                       uint32_t lag, void* stream);
 
 /* ---- host-buffer front end (what the e2e number is measured through) ----
  * Same decode as pc_topdown_decode but every pointer is a HOST pointer.  The

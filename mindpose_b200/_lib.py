@@ -221,8 +221,8 @@ SIGNATURES = {
         c_int, [_P, _P, POINTER(c_void_p), c_int32, _P, c_int64, c_int32, c_int64, _P]),
     "pc_scatter_results_signal": (
         c_int, [_P, _P, POINTER(c_void_p), c_int32, _P, c_int64, c_int32, c_int64,
-                POINTER(c_void_p), c_int32, c_int32, ctypes.c_uint32, _P, _P]),
-    "pc_wait_peer_flags": (c_int, [_P, c_int32, ctypes.c_uint32, _P]),
+                POINTER(c_void_p), c_int32, c_int32, _P, _P, _P]),
+    "pc_wait_peer_flags": (c_int, [_P, c_int32, _P, ctypes.c_uint32, _P]),
     "pc_ctx_create": (c_int, [c_int, c_int64, POINTER(c_void_p)]),
     "pc_ctx_destroy": (c_int, [c_void_p]),
     "pc_ctx_last_transfer_bytes": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),

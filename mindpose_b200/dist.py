@@ -163,6 +163,9 @@ class PeerGather:
         self._flag_handle = fh
         self._peer_flags = (ctypes.c_void_p * self.world)(*[int(p) for p in fh.buffer_ptrs])
         self._counter = torch.zeros(1, dtype=torch.int32, device=device)
+        # the step number the kernels publish lives in device memory (a captured CUDA graph of
+        # a step then signals a new number at every replay); `_step` mirrors it on the host
+        self._dstep = torch.zeros(1, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         fh.barrier(channel=0)            # nobody signals before everybody has zeroed its flags
         self._step = 0                   # steps count from 1 (flags start at 0)
@@ -181,7 +184,7 @@ class PeerGather:
         lib.call("pc_scatter_results_signal", lib.device_ptr(preds), lib.device_ptr(boxes),
                  self._peers[i], self.world, self._mc[i] if self.multicast else None,
                  self.rank * self.rows, self.k, self.rows, self._peer_flags, self.world,
-                 self.rank, self._step & 0xFFFFFFFF, lib.device_ptr(self._counter),
+                 self.rank, lib.device_ptr(self._dstep), lib.device_ptr(self._counter),
                  lib.current_stream())
         return GatherTicket(self, self._step, self.tables[i])
 
@@ -190,8 +193,40 @@ class PeerGather:
             return
         lib = self._lib
         lib.call("pc_wait_peer_flags", lib.device_ptr(self._flags), self.world,
-                 step & 0xFFFFFFFF, lib.current_stream())
+                 lib.device_ptr(self._dstep), self._step - step, lib.current_stream())
         self._waited = step
+
+    def wait_lag(self, lag: int = 0) -> None:
+        """Order the current stream after the arrival of every rank's rows of the scatter
+        issued `lag` scatters ago (0: the latest).  Unlike a ticket this needs no host state
+        per step, so a captured CUDA graph can hold it: "scatter; wait_lag(1)" per step."""
+        if lag < 0:
+            raise ValueError("lag must be >= 0")
+        lib = self._lib
+        lib.call("pc_wait_peer_flags", lib.device_ptr(self._flags), self.world,
+                 lib.device_ptr(self._dstep), int(lag), lib.current_stream())
+        self._waited = max(self._waited, self._step - lag)
+
+    def table_of_lag(self, lag: int = 0):
+        """Views (all_preds, all_boxes) of the table the scatter `lag` scatters ago wrote."""
+        return unpack_results(self.tables[(self._step - lag) % self.TABLES], self.k)
+
+    def captured(self, steps: int) -> None:
+        """`steps` gather steps were just CAPTURED into a CUDA graph (nothing ran on the
+        device): take them back from the host mirror.  Call `replayed(steps)` per replay."""
+        if steps % self.TABLES:
+            raise ValueError(f"a captured graph must hold a multiple of {self.TABLES} gather steps")
+        self._step -= steps
+        self._waited = min(self._waited, self._step)
+
+    def replayed(self, steps: int) -> None:
+        """A captured CUDA graph holding `steps` gather steps (a multiple of TABLES, so that
+        the table rotation closes) was replayed once more: advance the host mirror of the
+        device's step number.  Tickets made during the capture are not valid afterwards."""
+        if steps % self.TABLES:
+            raise ValueError(f"a captured graph must hold a multiple of {self.TABLES} gather steps")
+        self._step += steps
+        self._waited += steps
 
     def gather(self, preds: torch.Tensor, boxes: torch.Tensor):
         """-> (all_preds [world*rows,K,3], all_boxes [world*rows,6]) once every rank's rows

@@ -154,6 +154,51 @@ def test_decode_large_batch_properties(cuda_device, n, h, w, dark, shift_heatmap
     assert torch.equal(p3[..., 0], (idx % w).float()) and torch.equal(p3[..., 1], (idx // w).float())
 
 
+@pytest.mark.parametrize("n,h,w,kw,shift_heatmap", [
+    (4096, 64, 48, dict(dark_udp_refine=True, kernel_size=11), False),   # bench.py headline
+    (4096, 64, 48, dict(shift_coordinate=True), True),                   # BASELINE config 1 recipe
+    (2048, 96, 72, dict(use_udp=True, dark_udp_refine=True, kernel_size=11), False),  # config 3
+])
+def test_decode_bench_sizes_match_oracle_on_a_subset(cuda_device, n, h, w, kw, shift_heatmap):
+    """The bench's own workload (its blob generator, its batch sizes, its decoder settings, so
+    its pipeline depth and consumer-group split): 256 crops spread over the whole batch are
+    compared with the oracle -- maxvals and boxes bit for bit, refined coordinates to 1e-4 px
+    (the unrefined / quarter-shift ones exactly), in heat-map and in image coordinates."""
+    import bench
+
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(21)
+    fidx = synth.flip_index()
+    hm, fl = bench.blob_stack(torch, n, h, w, dev, g, fidx)
+    center = torch.rand(n, 2, device=dev, generator=g) * 400
+    scale = torch.rand(n, 2, device=dev, generator=g) * 2.8 + 0.2
+    score = torch.rand(n, device=dev, generator=g)
+    pick = np.unique(np.concatenate([np.random.RandomState(3).choice(n, 250, replace=False),
+                                     [0, 1, n // 2, n - 2, n - 1, 147, 148, 149]]))
+    okw = dict(shift_coordinate_flag=kw.get("shift_coordinate", False),
+               use_udp=kw.get("use_udp", False),
+               dark_udp_refine_flag=kw.get("dark_udp_refine", False),
+               kernel_size=kw.get("kernel_size", 11))
+    refined = okw["dark_udp_refine_flag"]
+    for to_original in (False, True):
+        dec = mp.create_decoder("topdown_heatmap", to_original=to_original, **kw)
+        p, b = dec.decode_flip_pair(hm, fl, fidx, center, scale, score, shift_heatmap=shift_heatmap)
+        want_p, want_b = topdown_decode.decode_with_flip(
+            hm[pick].cpu().numpy(), fl[pick].cpu().numpy(), fidx, center[pick].cpu().numpy(),
+            scale[pick].cpu().numpy(), score[pick].cpu().numpy(), shift_heatmap=shift_heatmap,
+            to_original=to_original, **okw)
+        got_p, got_b = p[pick].cpu().numpy(), b[pick].cpu().numpy()
+        assert np.array_equal(got_p[..., 2], want_p[..., 2])
+        assert np.array_equal(got_b, want_b)
+        if not refined:
+            assert np.array_equal(got_p, want_p)
+        else:
+            # image coordinates = heat-map coordinates * scale * 200 / size: the tolerance scales
+            tol = COORD_TOL if not to_original else \
+                COORD_TOL * float(scale.max()) * 200.0 / min(h, w)
+            assert np.abs(got_p[..., :2] - want_p[..., :2]).max() <= tol
+
+
 def test_decode_subnormal_and_zero_maps(cuda_device):
     """Flip averaging of values whose halves are subnormal (the kernel compares sums and
     must fall back to exact averages there), all-zero and all-negative planes."""
