@@ -85,6 +85,15 @@ typedef struct pc_affine_params {
 int pc_affine_matrices(const float* d_center, const float* d_scale, const float* d_rot,
                        double* d_fwd, double* d_inv, const pc_affine_params* params,
                        int64_t n, void* stream);
+/* cv2.getAffineTransform(src, dst) op for op, for point triples the CALLER built (float32
+ * [N,3,2] each, as the reference stores them: utils.py:81-96), plus the inverse.  With a
+ * rotation the reference's three points depend on numpy's own sin / cos and on the dtype the
+ * rotation arrives in (float32 from the dataset pipeline, transform.py:66-79); the per-sample
+ * transforms evaluate those few scalars with numpy on the host and hand the points here, so
+ * that rotated crops are bit-exact too (pc_affine_matrices uses the device's sin / cos:
+ * identical at rot = 0, <= 1e-9 relative otherwise). */
+int pc_affine_from_points(const float* d_src_points, const float* d_dst_points, double* d_fwd,
+                          double* d_inv, int64_t n, void* stream);
 /* Invert caller-supplied forward matrices (e.g. from cv2.getAffineTransform). */
 int pc_invert_affine(const double* d_fwd, double* d_inv, int64_t n, void* stream);
 
@@ -190,14 +199,15 @@ int pc_bottomup_encode(const float* d_keypoints, float* d_target, int32_t* d_tag
 
 /* ---- A14-A17: BottomUpHeatMapAEDecoder.construct ------------------------
  * mindpose/models/decoders/bottom_up_decoder.py:67-203.
- * num_stages = 2, with_ae_loss = [True, False], tag_per_joint = True (the
- * HigherHRNet recipe): d_out0 f32 [N, 2K, H0, W0] (heat | tag),
- * d_out1 f32 [N, K, H1, W1] with H1 = 2*H0, W1 = 2*W0;
- * num_stages = 1: d_out0 f32 [N, 2K, H1, W1], d_out1 = NULL.
+ * num_stages = 2, with_ae_loss = [True, False] (the HigherHRNet recipe):
+ * d_out0 f32 [N, C0, H0, W0] (heat | tag) with C0 = 2K (tag_per_joint, a tag plane per joint)
+ * or K + 1 (tag_per_joint = 0: every joint reads the one shared tag plane, the reference's
+ * broadcast at bottom_up_decoder.py:159-160), d_out1 f32 [N, K, H1, W1] with H1 = 2*H0,
+ * W1 = 2*W0;  num_stages = 1: d_out0 f32 [N, C0, H1, W1], d_out1 = NULL.
  * d_mask u8 [N, Hm, Wm] (non-zero = valid).
  * -> d_val_k f32 [N,K,M], d_tag_k f32 [N,K,M,1], d_ind_k f32 [N,K,M,2] (x, y).
  * Optional (may be NULL): d_heatmap_raw f32 [N,K,H1,W1] (aggregated, masked,
- * pre-NMS), d_tagging f32 [N,K,H1,W1,1]. */
+ * pre-NMS), d_tagging f32 [N,K,H1,W1,1] ([N,1,H1,W1,1] with tag_per_joint = 0). */
 typedef struct pc_bottomup_decode_params {
   int32_t num_joints;
   int32_t num_stages;
@@ -209,6 +219,7 @@ typedef struct pc_bottomup_decode_params {
   int32_t shift_coordinate; /* A17, reproduced with the reference's pairing: entry t of the
                              * top M gets the +-0.25 offset of the t-th position in
                              * row-major order (bottom_up_decoder.py:195-201) */
+  int32_t tag_per_joint;    /* 1: a tag plane per joint; 0: one plane shared by all joints */
 } pc_bottomup_decode_params;
 int pc_bottomup_decode(const float* d_out0, const float* d_out1, const uint8_t* d_mask,
                        float* d_val_k, float* d_tag_k, float* d_ind_k, float* d_heatmap_raw,

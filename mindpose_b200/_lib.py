@@ -119,6 +119,7 @@ class BottomUpDecodeParams(Structure):
         ("nms_kernel", c_int32),
         ("max_num", c_int32),
         ("shift_coordinate", c_int32),
+        ("tag_per_joint", c_int32),
     ]
 
 
@@ -193,6 +194,7 @@ SIGNATURES = {
     "pc_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "pc_box_to_center_scale": (c_int, [_P, _P, _P, POINTER(BoxParams), c_int64, _P]),
     "pc_affine_matrices": (c_int, [_P, _P, _P, _P, _P, POINTER(AffineParams), c_int64, _P]),
+    "pc_affine_from_points": (c_int, [_P, _P, _P, _P, c_int64, _P]),
     "pc_invert_affine": (c_int, [_P, _P, c_int64, _P]),
     "pc_warp_affine_u8": (c_int, [_P, _P, _P, _P, _P, POINTER(WarpParams), c_int64, _P]),
     "pc_warp_affine_u8_norm_chw": (

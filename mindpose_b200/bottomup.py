@@ -29,19 +29,25 @@ def decode(decoder, heatmap: List[torch.Tensor], tagging_heatmap: List[torch.Ten
     stages = decoder.num_stages
     if stages not in (1, 2):
         raise ValueError("num_stages must be 1 or 2")
-    if list(decoder.with_ae_loss[:stages]) != ([True, False][:stages]) or not decoder.tag_per_joint:
-        raise ValueError("the CUDA decoder supports with_ae_loss=[True, False], tag_per_joint=True")
+    if list(decoder.with_ae_loss[:stages]) != ([True, False][:stages]):
+        raise ValueError("the CUDA decoder supports with_ae_loss=[True, False] (tags on the "
+                         "first stage only, the HigherHRNet recipe)")
+    per_joint = bool(decoder.tag_per_joint)
+    c0 = 2 * k if per_joint else k + 1   # heat | tag planes of the first-stage output
     if len(heatmap) != stages or len(tagging_heatmap) != 1:
         raise ValueError("expected one heatmap per stage and one tag map")
     # recover the contiguous first-stage output the two views were sliced from; a candidate
     # (the caller's `raw[0]` or the view's base) is only used when both views are provably
     # its channel slices -- same pointer arithmetic, strides, N, H and W
     out0 = raw[0] if raw is not None else heatmap[0]._base
-    if out0 is None or out0.dim() != 4 or out0.shape[1] != 2 * k \
+    if out0 is None or out0.dim() != 4 or out0.shape[1] != c0 \
             or not _same_storage_view(heatmap[0], out0, 0) \
             or not _same_storage_view(tagging_heatmap[0], out0, k):
         # views of something else: pack heat | tag into one contiguous tensor
         out0 = torch.cat([heatmap[0], tagging_heatmap[0]], dim=1).contiguous()
+        if out0.shape[1] != c0:
+            raise ValueError(f"heatmap[0] | tagging_heatmap[0] must hold {c0} channels "
+                             f"(tag_per_joint={per_joint}), got {out0.shape[1]}")
     out1 = None
     if stages == 2:
         # the second stage is one tensor of K channels: the view itself is what is decoded
@@ -78,9 +84,11 @@ def decode(decoder, heatmap: List[torch.Tensor], tagging_heatmap: List[torch.Ten
     raw_map = tag_map = None
     if getattr(decoder, "return_maps", True):
         raw_map = torch.empty((n, k, h1, w1), dtype=torch.float32, device=dev)
-        tag_map = torch.empty((n, k, h1, w1, 1), dtype=torch.float32, device=dev)
+        tag_map = torch.empty((n, k if per_joint else 1, h1, w1, 1), dtype=torch.float32,
+                              device=dev)
     p = _lib.BottomUpDecodeParams(k, stages, h0, w0, h1, w1, mh, mw, int(bool(decoder.use_nms)),
-                                  int(decoder.nms_kernel), m, int(bool(decoder.shift_coordinate)))
+                                  int(decoder.nms_kernel), m, int(bool(decoder.shift_coordinate)),
+                                  int(per_joint))
     with torch.cuda.device(dev):
         _lib.call("pc_bottomup_decode", _lib.device_ptr(out0), _lib.device_ptr(out1),
                   _lib.device_ptr(mask_u8), _lib.device_ptr(val_k), _lib.device_ptr(tag_k),

@@ -64,6 +64,23 @@ def affine_matrices(center: torch.Tensor, scale: torch.Tensor, rot: Optional[tor
     return fwd, inv
 
 
+def affine_from_points(src_points: torch.Tensor, dst_points: torch.Tensor):
+    """``cv2.getAffineTransform`` for caller-built float32 point triples [N,3,2]
+    -> (fwd f64 [N,2,3], inv f64 [N,2,3])."""
+    src_points = _f32(src_points, "src_points").reshape(-1, 3, 2)
+    dst_points = _f32(dst_points, "dst_points").reshape(-1, 3, 2)
+    n = src_points.shape[0]
+    if dst_points.shape[0] != n:
+        raise ValueError("`src_points` and `dst_points` must hold the same number of triples")
+    fwd = torch.empty((n, 2, 3), dtype=torch.float64, device=src_points.device)
+    inv = torch.empty((n, 2, 3), dtype=torch.float64, device=src_points.device)
+    with torch.cuda.device(src_points.device):
+        _lib.call("pc_affine_from_points", _lib.device_ptr(src_points),
+                  _lib.device_ptr(dst_points), _lib.device_ptr(fwd), _lib.device_ptr(inv), n,
+                  _lib.current_stream())
+    return fwd, inv
+
+
 def invert_affine(fwd: torch.Tensor) -> torch.Tensor:
     if not fwd.is_cuda:
         raise ValueError("`fwd` must live on a CUDA device")

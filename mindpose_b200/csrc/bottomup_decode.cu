@@ -17,6 +17,8 @@
 // per-thread maximum, which is a valid lower bound for the M-th largest element.
 #include <math.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace pc {
@@ -39,6 +41,8 @@ struct BuArgs {
   float* heatmap_raw;
   float* tagging;
   int32_t K, stages, h0, w0, h1, w1, mh, mw;
+  int32_t c0;        // channels of out0: 2K (a tag plane per joint) or K + 1 (one shared plane)
+  int32_t tag_step;  // 1, or 0 when every joint reads the same tag plane (tag_per_joint False)
   int32_t use_nms, nms_k, M;
   FastDiv div_w1;
   float sy, sx;    // h0 / h1, w0 / w1 (float32, as the resize computes them)
@@ -84,8 +88,8 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
   int th, tw;
   float tsy, tsx;
   if (a.stages == 2) {
-    heat_lo = a.out0 + ((size_t)n * 2 * a.K + k) * a.h0 * a.w0;
-    tag_src = a.out0 + ((size_t)n * 2 * a.K + a.K + k) * a.h0 * a.w0;
+    heat_lo = a.out0 + ((size_t)n * a.c0 + k) * a.h0 * a.w0;
+    tag_src = a.out0 + ((size_t)n * a.c0 + a.K + k * a.tag_step) * a.h0 * a.w0;
     heat_hi = a.out1 + ((size_t)n * a.K + k) * H * W;
     th = a.h0;
     tw = a.w0;
@@ -93,8 +97,8 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
     tsx = a.sx;
   } else {
     heat_lo = nullptr;
-    heat_hi = a.out0 + ((size_t)n * 2 * a.K + k) * H * W;
-    tag_src = a.out0 + ((size_t)n * 2 * a.K + a.K + k) * H * W;
+    heat_hi = a.out0 + ((size_t)n * a.c0 + k) * H * W;
+    tag_src = a.out0 + ((size_t)n * a.c0 + a.K + k * a.tag_step) * H * W;
     th = H;
     tw = W;
     tsy = 1.f;
@@ -102,7 +106,10 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
   }
   const uint8_t* mask = a.mask + (size_t)n * a.mh * a.mw;
   float* raw_out = a.heatmap_raw ? a.heatmap_raw + ((size_t)n * a.K + k) * H * W : nullptr;
-  float* tag_out = a.tagging ? a.tagging + ((size_t)n * a.K + k) * H * W : nullptr;
+  // tagging_heatmap output: K planes per image, or the one shared plane (written by joint 0)
+  float* tag_out = (a.tagging && (a.tag_step || k == 0))
+                       ? a.tagging + ((size_t)n * (a.tag_step ? a.K : 1) + k * a.tag_step) * H * W
+                       : nullptr;
 
   if (tid == 0) {
     s_thr = -INFINITY;
@@ -771,13 +778,13 @@ __global__ void __launch_bounds__(kFastThreads, (C <= 8) ? 3 : 1)
   int th, tw;
   float tsy, tsx;
   if (TWO_STAGE) {
-    heat_lo = a.out0 + ((size_t)n * 2 * a.K + k) * a.h0 * a.w0;
-    tag_src = a.out0 + ((size_t)n * 2 * a.K + a.K + k) * a.h0 * a.w0;
+    heat_lo = a.out0 + ((size_t)n * a.c0 + k) * a.h0 * a.w0;
+    tag_src = a.out0 + ((size_t)n * a.c0 + a.K + k * a.tag_step) * a.h0 * a.w0;
     heat_hi = a.out1 + ((size_t)n * a.K + k) * H * W;
     th = a.h0, tw = a.w0, tsy = a.sy, tsx = a.sx;
   } else {
-    heat_hi = a.out0 + ((size_t)n * 2 * a.K + k) * H * W;
-    tag_src = a.out0 + ((size_t)n * 2 * a.K + a.K + k) * H * W;
+    heat_hi = a.out0 + ((size_t)n * a.c0 + k) * H * W;
+    tag_src = a.out0 + ((size_t)n * a.c0 + a.K + k * a.tag_step) * H * W;
     th = H, tw = W, tsy = 1.f, tsx = 1.f;
   }
   const uint8_t* mask = a.mask + (size_t)n * a.mh * a.mw;
@@ -1292,8 +1299,8 @@ __global__ void __launch_bounds__(kPairThreads, MINB)
   const int H = a.h1, W = a.w1, M = a.M;
   unsigned char* ring = s_ring + warp * kPairWarp;
 
-  const float* heat_lo = a.out0 + ((size_t)n * 2 * a.K + k) * a.h0 * a.w0;
-  const float* tag_src = a.out0 + ((size_t)n * 2 * a.K + a.K + k) * a.h0 * a.w0;
+  const float* heat_lo = a.out0 + ((size_t)n * a.c0 + k) * a.h0 * a.w0;
+  const float* tag_src = a.out0 + ((size_t)n * a.c0 + a.K + k * a.tag_step) * a.h0 * a.w0;
   const float* heat_hi = a.out1 + ((size_t)n * a.K + k) * H * W;
   const uint8_t* mask = a.mask + (size_t)n * a.mh * a.mw;
   const uint32_t* zrow = zrow_all + (size_t)n * H;
@@ -1467,10 +1474,10 @@ __global__ void __launch_bounds__(128) bottomup_shift_kernel(const BuArgs a, int
   const float* heat_hi;
   const float* heat_lo = nullptr;
   if (a.stages == 2) {
-    heat_lo = a.out0 + ((size_t)n * 2 * a.K + k) * a.h0 * a.w0;
+    heat_lo = a.out0 + ((size_t)n * a.c0 + k) * a.h0 * a.w0;
     heat_hi = a.out1 + ((size_t)n * a.K + k) * H * W;
   } else {
-    heat_hi = a.out0 + ((size_t)n * 2 * a.K + k) * H * W;
+    heat_hi = a.out0 + ((size_t)n * a.c0 + k) * H * W;
   }
   const uint8_t* mask = a.mask + (size_t)n * a.mh * a.mw;
   float* ind = a.ind_k + (size_t)plane * M * 2;
@@ -1504,21 +1511,37 @@ __global__ void __launch_bounds__(128) bottomup_shift_kernel(const BuArgs a, int
 
 using namespace pc;
 
-// The row-flag scratch comes from the device's default stream-ordered pool.  By default the
-// pool hands freed memory back to the driver at every synchronisation, which would turn
-// each call into a driver allocation; keep it (once per device).
-static cudaError_t keep_pool_memory() {
-  static bool done[64] = {};
+// The row-flag scratch comes from a stream-ordered memory pool OWNED BY THE LIBRARY (one per
+// device, created on first use, never destroyed): a pool keeps freed memory only if its
+// release threshold says so, and raising the threshold of the device's DEFAULT pool would
+// change how every other cudaMallocAsync user of the process returns memory to the driver.
+static cudaError_t scratch_pool(cudaMemPool_t* out) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return e;
-  cudaMemPool_t pool;
-  e = cudaDeviceGetDefaultMemPool(&pool, dev);
   if (e != cudaSuccess) return e;
-  uint64_t keep = UINT64_MAX;
-  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-  done[dev] = e == cudaSuccess;
-  return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    uint64_t keep = UINT64_MAX;  // of this pool only: a call must not cost a driver allocation
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) {
+      cudaMemPoolDestroy(pool);
+      return e;
+    }
+    pools[dev] = pool;
+  }
+  *out = pools[dev];
+  return cudaSuccess;
 }
 
 // Launch of the pair kernel as a programmatic dependent of mask_zero_rows_kernel (the
@@ -1605,6 +1628,8 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
   a.use_nms = p->use_nms;
   a.nms_k = p->nms_kernel;
   a.M = p->max_num;
+  a.tag_step = p->tag_per_joint ? 1 : 0;
+  a.c0 = p->tag_per_joint ? 2 * p->num_joints : p->num_joints + 1;
   a.div_w1 = make_fastdiv((uint32_t)p->w1);
   a.sy = p->num_stages == 2 ? (float)p->h0 / (float)p->h1 : 1.f;
   a.sx = p->num_stages == 2 ? (float)p->w0 / (float)p->w1 : 1.f;
@@ -1654,8 +1679,9 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
       // one word per (image, output row): which lanes see a masked pixel (stream-ordered scratch)
       uint32_t* zrow = nullptr;
       const int64_t rows = n * p->h1;
-      PC_CUDA(keep_pool_memory());
-      PC_CUDA(cudaMallocAsync((void**)&zrow, sizeof(uint32_t) * (size_t)rows, st));
+      cudaMemPool_t pool;
+      PC_CUDA(scratch_pool(&pool));
+      PC_CUDA(cudaMallocFromPoolAsync((void**)&zrow, sizeof(uint32_t) * (size_t)rows, pool, st));
       mask_zero_rows_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(
           d_mask, zrow, p->h1, p->w1, p->mask_h, p->mask_w, a.msy, rows);
       const bool all = p->w1 == 256 && p->w0 == 128;
@@ -1686,12 +1712,13 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
     PC_CUDA(cudaGetLastError());
     if (d_tagging) {
       const int th = two ? p->h0 : p->h1, tw = two ? p->w0 : p->w1;
-      const int64_t quads = n * p->num_joints * (int64_t)p->h1 * (p->w1 / 4);
+      const int tag_planes = a.tag_step ? p->num_joints : 1;
+      const int64_t quads = n * tag_planes * (int64_t)p->h1 * (p->w1 / 4);
       int64_t blocks = (quads + 255) / 256;
       const int64_t cap = (int64_t)sm_count_cached() * 16;
       if (blocks > cap) blocks = cap;
       resize_tags_kernel<<<(unsigned)blocks, 256, 0, st>>>(
-          d_out0, d_tagging, p->num_joints, 2 * p->num_joints, p->num_joints, th, tw, p->h1,
+          d_out0, d_tagging, tag_planes, a.c0, p->num_joints, th, tw, p->h1,
           p->w1, two ? a.sy : 1.f, two ? a.sx : 1.f, a.div_w1, quads);
       PC_CUDA(cudaGetLastError());
     }

@@ -54,6 +54,7 @@ struct DecodeArgs {
   int32_t win_floats, row_floats;  // per-warp DARK scratch (0 unless mode == 2)
   uint32_t stage_floats;  // floats per stage (HW or 2*HW)
   int32_t vec_ok;         // W % 4 == 0
+  int32_t bulk_ok;        // planes 16-byte aligned in HBM (H*W % 4 == 0, bases % 16 == 0)
 };
 
 struct DecodeTables {
@@ -261,7 +262,9 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
     topdown_decode_kernel(const DecodeArgs a, const __grid_constant__ DecodeTables tab) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  const size_t stage_bytes_total = (size_t)a.stages * a.stage_floats * sizeof(float);
+  // (rounded up: with H * W % 4 != 0 the stages do not end on a 16-byte boundary)
+  const size_t stage_bytes_total =
+      ((size_t)a.stages * a.stage_floats * sizeof(float) + 15) & ~(size_t)15;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + stage_bytes_total);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* part_bar = empty_bar + kMaxStages;
@@ -299,6 +302,36 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
   if (warp == 0) {
     // ---------------- producer: one thread issues all bulk copies -----------
     // In order, so a parity wait on empty_bar is never more than one phase ahead.
+    if (!a.bulk_ok) {
+      // Planes that are not 16-byte aligned in HBM (H * W % 4 != 0, or an offset base: the
+      // reference takes any H, W -- top_down_decoder.py:96-116) cannot be bulk-copied.  The
+      // producer WARP then copies them itself, element by element, into the same stages and
+      // completes the same barrier by a plain arrival; the consumers do not change.  Slower
+      // (one warp of loads per SM), exact.
+      int s = 0;
+      uint32_t round = 0;
+      for (int64_t j = 0; j < count; ++j) {
+        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        const int64_t item = first + j * gridDim.x;
+        const int64_t n = item / a.K;
+        const int k = (int)(item - n * a.K);
+        float* dst = stage_base + (size_t)s * a.stage_floats;
+        const float* src0 = a.heatmap + item * a.HW;
+        for (int i = lane; i < a.HW; i += 32) dst[i] = __ldg(src0 + i);
+        if (FLIP) {
+          const float* src1 = a.flipped + (n * a.K + tab.flip_index[k]) * a.HW;
+          for (int i = lane; i < a.HW; i += 32) dst[a.HW + i] = __ldg(src1 + i);
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (++s == S) {
+          s = 0;
+          ++round;
+        }
+      }
+      return;
+    }
     if (lane == 0) {
       const uint64_t pol = l2_evict_first_policy();
       int s = 0;
@@ -584,10 +617,11 @@ extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
   PC_REQUIRE(!p->flip_test || d_flipped, PC_ERR_INVALID_ARGUMENT,
              "pc_topdown_decode: flip_test needs the flipped heatmap");
   const int64_t hw = (int64_t)p->height * p->width;
-  PC_REQUIRE(hw % 4 == 0 && ((uintptr_t)d_heatmap % 16 == 0) &&
-                 (!p->flip_test || (uintptr_t)d_flipped % 16 == 0),
-             PC_ERR_UNSUPPORTED,
-             "pc_topdown_decode: planes must be 16-byte aligned (H*W %% 4 == 0, base %% 16 == 0)");
+  PC_REQUIRE(((uintptr_t)d_heatmap % 4 == 0) && (!p->flip_test || (uintptr_t)d_flipped % 4 == 0),
+             PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode: heatmaps must be float32-aligned");
+  // bulk copies need 16-byte aligned planes; any other H, W / base takes the manual copy
+  const bool bulk_ok = hw % 4 == 0 && ((uintptr_t)d_heatmap % 16 == 0) &&
+                       (!p->flip_test || (uintptr_t)d_flipped % 16 == 0);
   PC_REQUIRE((uint64_t)hw * p->width < 0xffffffffull, PC_ERR_UNSUPPORTED,
              "pc_topdown_decode: map %dx%d too large", p->height, p->width);
 
@@ -628,6 +662,7 @@ extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
   a.ks = p->kernel_size;
   a.shift_heatmap = p->flip_test ? p->shift_heatmap : 0;
   a.vec_ok = (a.W % 4 == 0);
+  a.bulk_ok = bulk_ok ? 1 : 0;
   a.divWq = make_fastdiv((uint32_t)(a.vec_ok ? a.W / 4 : 1));
   a.step_xq = a.vec_ok ? 32 % (a.W / 4) : 0;
   a.step_y = a.vec_ok ? 32 / (a.W / 4) : 0;
@@ -658,7 +693,7 @@ extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
                  2 * kMaxStages * kConsumerWarps * sizeof(float) +
                  sizeof(float) * PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL +
                  sizeof(float) * ng * (a.row_floats + a.win_floats);
-    stages = (int)((smem_cap - tail_bytes) / stage_bytes);
+    stages = (int)((smem_cap - tail_bytes - 16) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     const double busy = 4.2 / group + refine;
     if (busy <= stages - 2 || group == kConsumerWarps) break;
@@ -668,7 +703,7 @@ extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
              p->height, p->width, p->flip_test ? " pair" : "");
   a.stages = stages;
   a.group = group;
-  const size_t smem = stages * stage_bytes + tail_bytes;
+  const size_t smem = ((stages * stage_bytes + 15) & ~(size_t)15) + tail_bytes;
 
   const int sms = sm_count_cached();
   PC_REQUIRE(sms > 0, PC_ERR_NO_DEVICE, "pc_topdown_decode: no CUDA device");

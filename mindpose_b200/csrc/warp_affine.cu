@@ -182,6 +182,30 @@ __global__ void affine_matrices_kernel(const float* __restrict__ center,
   }
 }
 
+// cv2.getAffineTransform(src, dst) for caller-built point triples (float32, as the reference
+// stores them: utils.py:81-96), then cv::warpAffine's inversion.
+__global__ void affine_from_points_kernel(const float* __restrict__ src_pts,
+                                          const float* __restrict__ dst_pts,
+                                          double* __restrict__ fwd, double* __restrict__ inv,
+                                          int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double sd[3][2], dd[3][2], m[6];
+  for (int p = 0; p < 3; ++p)
+    for (int c = 0; c < 2; ++c) {
+      sd[p][c] = (double)src_pts[6 * i + 2 * p + c];
+      dd[p][c] = (double)dst_pts[6 * i + 2 * p + c];
+    }
+  solve_three_points(sd, dd, m);
+  if (fwd)
+    for (int c = 0; c < 6; ++c) fwd[6 * i + c] = m[c];
+  if (inv) {
+    double o[6];
+    invert_affine_cv(m, o);
+    for (int c = 0; c < 6; ++c) inv[6 * i + c] = o[c];
+  }
+}
+
 __global__ void invert_affine_kernel(const double* __restrict__ fwd, double* __restrict__ inv,
                                      int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -961,6 +985,18 @@ extern "C" int pc_affine_matrices(const float* d_center, const float* d_scale,
   affine_matrices_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
       d_center, d_scale, d_rot, d_fwd, d_inv, p->image_w, p->image_h, p->pixel_std, p->use_udp,
       n);
+  PC_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+extern "C" int pc_affine_from_points(const float* d_src_points, const float* d_dst_points,
+                                     double* d_fwd, double* d_inv, int64_t n, void* stream) {
+  PC_REQUIRE(n >= 0, PC_ERR_INVALID_ARGUMENT, "pc_affine_from_points: n < 0");
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(d_src_points && d_dst_points && (d_fwd || d_inv), PC_ERR_INVALID_ARGUMENT,
+             "pc_affine_from_points: NULL tensor pointer");
+  affine_from_points_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
+      d_src_points, d_dst_points, d_fwd, d_inv, n);
   PC_CUDA(cudaGetLastError());
   return PC_OK;
 }

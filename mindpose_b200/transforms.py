@@ -118,6 +118,60 @@ class TopDownAffine(TopDownTransform):
         super().__init__(is_train=is_train, config=config)
         self.use_udp = use_udp
 
+    def _host_geometry(self, center, scale, rot):
+        """The rotation-dependent scalars of ONE sample whose geometry lives on the host.
+
+        With a rotation the reference's matrix depends on numpy's own sin / cos and on the
+        dtype the rotation arrives in (a float32 scalar from the dataset pipeline; numpy then
+        rounds the angle, and under NumPy >= 2 the rotated direction, in float32).  Those few
+        scalars are evaluated here with numpy -- in whatever dtypes the caller passed, like the
+        reference does (utils.py:73-96 / :158-190).
+        -> ("points", src f32 [3,2], dst f32 [3,2]) for cv2.getAffineTransform, or
+           ("matrix", m f32 [2,3]) for UDP."""
+        cfg = self._transform_cfg
+        w, h = cfg["image_size"]
+        pixel_std = cfg["pixel_std"]
+        if self.use_udp:
+            theta = np.deg2rad(rot)
+            size_in, size_dst = center * 2.0, np.asarray(cfg["image_size"]) - 1.0
+            size_tgt = scale * pixel_std
+            kx, ky = size_dst[0] / size_tgt[0], size_dst[1] / size_tgt[1]
+            cs, sn = np.cos(theta), np.sin(theta)
+            m = np.zeros((2, 3), dtype=np.float32)
+            m[0, 0], m[0, 1] = cs * kx, -sn * kx
+            m[0, 2] = kx * (-0.5 * size_in[0] * cs + 0.5 * size_in[1] * sn + 0.5 * size_tgt[0])
+            m[1, 0], m[1, 1] = sn * ky, cs * ky
+            m[1, 2] = ky * (-0.5 * size_in[0] * sn - 0.5 * size_in[1] * cs + 0.5 * size_tgt[1])
+            return "matrix", m
+        half_w = (scale * pixel_std)[0] * -0.5
+        angle = np.pi * rot / 180
+        sn, cs = np.sin(angle), np.cos(angle)
+        direction = [0.0 * cs - half_w * sn, 0.0 * sn + half_w * cs]
+        src = np.zeros((3, 2), dtype=np.float32)
+        src[0] = center
+        src[1] = center + direction
+        dst = np.zeros((3, 2), dtype=np.float32)
+        dst[0] = [w * 0.5, h * 0.5]
+        dst[1] = np.array([w * 0.5, h * 0.5]) + np.array([0.0, w * -0.5])
+        for pts in (src, dst):  # third point: (a - b) turned by 90 degrees about b
+            d = pts[0] - pts[1]
+            pts[2] = pts[1] + np.array([-d[1], d[0]], dtype=np.float32)
+        return "points", src, dst
+
+    def _host_matrix(self, center, scale, rot) -> Optional[torch.Tensor]:
+        """Forward matrix f64 [1,2,3] on the device for a ROTATED sample (None at rot == 0,
+        where the device's own matrix is bit-exact): host scalars from `_host_geometry`, the
+        3-point solve (and later the warp and the joints) on the device."""
+        if not np.any(np.asarray(rot) != 0):
+            return None
+        dev = _dev()
+        geo = self._host_geometry(center, scale, rot)
+        if geo[0] == "matrix":
+            return torch.from_numpy(geo[1].astype(np.float64)[None]).to(dev)
+        fwd, _ = codec.affine_from_points(torch.from_numpy(geo[1][None]).to(dev),
+                                          torch.from_numpy(geo[2][None]).to(dev))
+        return fwd
+
     def transform(self, state: Dict[str, Any]) -> Dict[str, Any]:
         dev = _dev()
         image = np.ascontiguousarray(state["image"])
@@ -131,7 +185,8 @@ class TopDownAffine(TopDownTransform):
             kps = torch.from_numpy(
                 np.ascontiguousarray(state["keypoints"], dtype=np.float32)[None]).to(dev)
         img_t = torch.from_numpy(image[None]).to(dev)
-        crop, kps = self.affine_batch(img_t, center, scale, rot, kps)
+        fwd = self._host_matrix(state["center"], state["scale"], state["rotation"])
+        crop, kps = self.affine_batch(img_t, center, scale, rot, kps, matrices=fwd)
         out = dict(image=crop[0].cpu().numpy())
         if kps is not None:
             # the reference mutates state["keypoints"] in place
@@ -140,15 +195,22 @@ class TopDownAffine(TopDownTransform):
         return out
 
     def affine_batch(self, images: torch.Tensor, center, scale, rot=None, keypoints=None,
-                     normalize_mean=None, normalize_std=None):
+                     normalize_mean=None, normalize_std=None, matrices=None):
         """images u8 [N,Hs,Ws,C] (one per crop) -> (crops u8 [N,h,w,C], keypoints).
+
+        ``matrices`` (f64 [N,2,3], CUDA): forward matrices to use instead of the ones the
+        device derives from (center, scale, rot) -- e.g. made by ``codec.affine_from_points``.
 
         With ``normalize_mean`` / ``normalize_std`` (the ``create_pipeline`` arguments, in
         [0, 1] units: data_factory.py:78-79) the pipeline's Normalize + HWC2CHW step is fused
         into the warp and the crops come back as float32 [N,3,h,w]."""
         cfg = self._transform_cfg
-        fwd, inv = codec.affine_matrices(center, scale, rot, cfg["image_size"],
-                                         pixel_std=cfg["pixel_std"], use_udp=self.use_udp)
+        if matrices is not None:
+            fwd = matrices.to(torch.float64).reshape(-1, 2, 3).contiguous()
+            inv = codec.invert_affine(fwd)
+        else:
+            fwd, inv = codec.affine_matrices(center, scale, rot, cfg["image_size"],
+                                             pixel_std=cfg["pixel_std"], use_udp=self.use_udp)
         if normalize_mean is not None:
             n, hs, ws, c = images.shape
             off = torch.arange(n, device=images.device, dtype=torch.int64) * (hs * ws * c)

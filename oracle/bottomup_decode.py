@@ -110,13 +110,15 @@ def nms(heat, k):
     return (heat * (pooled == heat).astype(F32)).astype(F32)
 
 
-def top_k(heat, tags, max_num):
+def top_k(heat, tags, max_num, tag_per_joint=True):
     """-> val_k [N,K,M], tag_k [N,K,M,T], ind_k [N,K,M,2] (x, y), flat indices."""
     n, k, h, w = heat.shape
     flat = heat.reshape(n, k, -1)
     order = np.argsort(-flat, axis=2, kind="stable")[:, :, :max_num]
     val_k = np.take_along_axis(flat, order, axis=2)
     tflat = tags.reshape(n, tags.shape[1], h * w, -1)
+    if not tag_per_joint:   # one tag plane for all joints (bottom_up_decoder.py:159-160)
+        tflat = np.broadcast_to(tflat, (n, k) + tflat.shape[2:])
     tag_k = np.stack(
         [np.take_along_axis(tflat[..., t], order, axis=2) for t in range(tflat.shape[3])], axis=3)
     ind_k = np.stack((order % w, order // w), axis=3).astype(F32)
@@ -141,7 +143,7 @@ def shift_coordinate_quirk(ind_k, heat_raw, order):
 
 
 def decode(model_output, mask, num_joints=17, num_stages=2, with_ae_loss=(True, False),
-           use_nms=False, nms_kernel=5, max_num=30, shift_coordinate=False):
+           use_nms=False, nms_kernel=5, max_num=30, shift_coordinate=False, tag_per_joint=True):
     """``BottomUpHeatMapAEDecoder.construct`` ->
     (val_k, tag_k, ind_k, heatmap_raw, tagging_heatmap)."""
     heat, tag = decouple_output(model_output, num_joints, num_stages, with_ae_loss)
@@ -149,7 +151,7 @@ def decode(model_output, mask, num_joints=17, num_stages=2, with_ae_loss=(True, 
     raw = heatmap.copy()
     if use_nms:
         heatmap = nms(heatmap, nms_kernel)
-    val_k, tag_k, ind_k, order = top_k(heatmap, tagging, max_num)
+    val_k, tag_k, ind_k, order = top_k(heatmap, tagging, max_num, tag_per_joint)
     if shift_coordinate:
         ind_k = shift_coordinate_quirk(ind_k, raw, order)
     return val_k, tag_k, ind_k, raw, tagging

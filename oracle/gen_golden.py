@@ -76,6 +76,46 @@ def gen_affine(ns):
     np.savez_compressed(os.path.join(GOLDEN, "affine_ref.npz"), **out)
 
 
+def gen_affine_rotated(ns):
+    """The reference's own ``TopDownAffine.transform`` (matrix + cv2.warpAffine + joints) on
+    rotated samples, fed the way its dataset pipeline feeds it: float32 arrays and a float32
+    0-d rotation (transform.py:66-79).  -> affine_rot_ref.npz."""
+    rng = np.random.RandomState(23)
+    n, hs, ws = 12, 120, 160
+    image_size = [96, 128]
+    images = rng.randint(0, 256, size=(n, hs, ws, 3), dtype=np.uint8)
+    boxes = np.stack([rng.uniform(0, 60, n), rng.uniform(0, 40, n), rng.uniform(30, 100, n),
+                      rng.uniform(40, 80, n)], axis=1).astype(np.float32)
+    rots = rng.uniform(-60, 60, n).astype(np.float32)
+    rots[0] = 0.0
+    rots[1] = 90.0
+    kps = synth.keypoints(n, 17, [ws, hs], seed=8)
+    out = dict(images=images, boxes=boxes, rots=rots, kps_in=kps,
+               image_size=np.asarray(image_size))
+    for tag, use_udp in (("std", False), ("udp", True)):
+        cfg = _cfg(ns, np.array(image_size), np.array([image_size[0] // 4, image_size[1] // 4]))
+        bt = ns.topdown.TopDownBoxToCenterScale(is_train=False, config=cfg)
+        at = ns.topdown.TopDownAffine(is_train=False, config=cfg, use_udp=use_udp)
+        crops, kout, centers, scales, mats = [], [], [], [], []
+        for i in range(n):
+            c, sc = bt._xywh2cs(*boxes[i])
+            r0 = np.asarray(rots[i])
+            mats.append(ns.utils.get_warp_matrix(r0, c * 2.0, np.array(image_size) - 1.0, sc * 200.0)
+                        if use_udp else
+                        ns.utils.get_affine_transform(c, sc, r0, np.array(image_size), pixel_std=200.0))
+            state = dict(image=images[i], center=np.asarray(c), scale=np.asarray(sc),
+                         rotation=np.asarray(rots[i]), keypoints=kps[i].copy())
+            res = at.transform(state)
+            crops.append(res["image"])
+            kout.append(np.asarray(res["keypoints"]))
+            centers.append(c)
+            scales.append(sc)
+        out.update({f"crops_{tag}": np.stack(crops), f"kps_{tag}": np.stack(kout),
+                    f"mats_{tag}": np.stack(mats).astype(np.float64),
+                    "center": np.stack(centers), "scale": np.stack(scales)})
+    np.savez_compressed(os.path.join(GOLDEN, "affine_rot_ref.npz"), **out)
+
+
 def gen_encode(ns):
     out = {}
     for tag, image_size, heatmap_size, n in (("64x48", [192, 256], [48, 64], 12),
@@ -172,6 +212,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ns = ref_loader.load()
     gen_affine(ns)
+    gen_affine_rotated(ns)
     gen_encode(ns)
     gen_warp(ns)
     gen_decode_restated()

@@ -90,6 +90,32 @@ def test_decode_accepts_batch_sliced_views(cuda_device):
         dec.decode([heat[0], big1[0:3]], tag, mask[sl])        # image counts differ
 
 
+@pytest.mark.parametrize("h0,stages", [(32, 2), (128, 2), (20, 2), (64, 1)])
+def test_decode_shared_tag_plane(cuda_device, h0, stages):
+    """tag_per_joint=False: the first-stage output has K + 1 channels and every joint gathers
+    its tags from the one shared plane (the reference's broadcast, bottom_up_decoder.py:
+    159-160); all three decode kernels (generic, fast, pair scan) by shape."""
+    n, k = 3, 17
+    d = synth.bottomup_outputs(n, k, h0, h0, mask_hw=(4 * h0, 4 * h0), seed=h0 + 1, max_people=5)
+    out0 = np.ascontiguousarray(d["out0"][:, :k + 1])          # heat | ONE tag plane
+    if stages == 1:
+        outs = [out0]
+        kw = dict(num_stages=1, with_ae_loss=(True,))
+    else:
+        outs = [out0, d["out1"]]
+        kw = dict(num_stages=2, with_ae_loss=(True, False))
+    want = bd.decode(outs, d["mask"], use_nms=True, nms_kernel=3, max_num=30,
+                     tag_per_joint=False, **kw)
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3, max_num=30,
+                            tag_per_joint=False, num_stages=kw["num_stages"],
+                            with_ae_loss=list(kw["with_ae_loss"]))
+    got = dec([_t(o, cuda_device) for o in outs], _t(d["mask"], cuda_device))
+    assert got[4].shape == (n, 1, got[3].shape[2], got[3].shape[3], 1)
+    for name, g, w in zip(["val_k", "tag_k", "ind_k", "heatmap_raw", "tagging_heatmap"], got, want):
+        assert g.shape == w.shape, name
+        assert np.array_equal(g.cpu().numpy(), w), name
+
+
 def test_decode_ties_and_flat_maps(cuda_device):
     """Constant / all-zero planes: every pixel survives NMS, top-k = lowest indices."""
     n, k, h0 = 1, 17, 16

@@ -154,3 +154,23 @@ def test_encode_against_live_reference():
             got_t, got_w = fn(kp, cfg["image_size"], cfg["heatmap_size"])
             assert np.array_equal(got_t, ref["target"])
             assert np.array_equal(got_w, ref["target_weight"])
+
+
+def test_host_rotation_geometry_reproduces_the_reference_matrices(golden):
+    """The few rotation scalars the per-sample TopDownAffine evaluates with numpy on the host
+    (float32 rotation in, as from the reference's dataset pipeline) give the reference's own
+    matrices bit for bit: UDP directly, the standard one through cv2.getAffineTransform of the
+    three points (the device solve is that routine op for op)."""
+    cv2 = pytest.importorskip("cv2")
+    import mindpose_b200 as mp
+    from mindpose_b200 import synth
+
+    g = golden("affine_rot_ref.npz")
+    cfg = dict(synth.TOPDOWN_CONFIG, image_size=[96, 128], heatmap_size=[24, 32])
+    for tag, udp in (("std", False), ("udp", True)):
+        at = mp.create_transform("topdown_affine", is_train=False, config=cfg, use_udp=udp)
+        for i in range(len(g["rots"])):
+            geo = at._host_geometry(g["center"][i], g["scale"][i], np.asarray(g["rots"][i]))
+            m = geo[1].astype(np.float64) if geo[0] == "matrix" else \
+                cv2.getAffineTransform(geo[1], geo[2])
+            assert np.array_equal(m, g[f"mats_{tag}"][i]), (tag, i)

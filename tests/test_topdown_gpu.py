@@ -65,6 +65,45 @@ def test_decode_blobs(cuda_device, h, w, flip, shift_heatmap, mode):
         assert np.abs(got_p[..., :2] - want_p[..., :2]).max() <= COORD_TOL
 
 
+@pytest.mark.parametrize("h,w", [(17, 13), (31, 27), (64, 49), (5, 3), (30, 22)])
+@pytest.mark.parametrize("flip,shift_heatmap", [(False, False), (True, True)])
+@pytest.mark.parametrize("mode", ["plain", "shift", "dark"])
+def test_decode_any_map_size(cuda_device, h, w, flip, shift_heatmap, mode):
+    """Map sizes the reference accepts (any H, W: top_down_decoder.py:96-116) whose planes are
+    not 16-byte aligned in HBM (H * W % 4 != 0, or W % 4 != 0): the producer warp copies the
+    planes itself instead of bulk-copying them; same results."""
+    n = 9
+    maps, _ = synth.blob_heatmaps(n, 17, h, w, seed=h + w)
+    flipped = synth.flipped_pair(maps, seed=h)
+    got_p, got_b, want_p, want_b = _decode_case(
+        cuda_device, maps, flipped, n, h, w, seed=3, flip=flip, shift_heatmap=shift_heatmap,
+        shift_coordinate=(mode == "shift"), dark=(mode == "dark"), use_udp=False)
+    assert np.array_equal(got_p[..., 2], want_p[..., 2])
+    assert np.array_equal(got_b, want_b)
+    if mode != "dark":
+        assert np.array_equal(got_p, want_p)
+    else:
+        assert np.abs(got_p[..., :2] - want_p[..., :2]).max() <= COORD_TOL
+
+
+def test_decode_unaligned_base_pointer(cuda_device):
+    """A heat-map view that starts 4 bytes into a buffer (planes not 16-byte aligned although
+    H * W % 4 == 0) takes the manual copy too."""
+    dev = cuda_device
+    n, k, h, w = 5, 17, 64, 48
+    maps, _ = synth.blob_heatmaps(n, k, h, w, seed=4)
+    center, scale, score = synth.crop_geometry(n, seed=4)
+    want_p, want_b = topdown_decode.decode(maps, center, scale, score, shift_coordinate_flag=True)
+    buf = torch.zeros(maps.size + 1, device=dev)
+    view = buf[1:].view(n, k, h, w)
+    view.copy_(_t(maps, dev))
+    assert view.data_ptr() % 16 == 4
+    p = codec.make_decode_params(k, h, w, shift_coordinate=True)
+    got_p, got_b = codec.topdown_decode(view, _t(center, dev), _t(scale, dev), _t(score, dev),
+                                        params=p)
+    assert np.array_equal(got_p.cpu().numpy(), want_p) and np.array_equal(got_b.cpu().numpy(), want_b)
+
+
 @pytest.mark.parametrize("flip", [False, True])
 def test_decode_noise_maps_indices_bit_exact(cuda_device, flip):
     """What the reference's own tests feed (uniform noise): argmax, maxval and the
@@ -388,6 +427,37 @@ def test_geometry_matches_oracle(cuda_device, golden):
                                     _t(g[f"udp_{tag}"].astype(np.float64), dev), True)
         # sgemm accumulation order is the BLAS build's; 2 ulp is the bar, 0 is what we see
         assert np.allclose(k_udp.cpu().numpy(), g[f"kps_udp_{tag}"], rtol=3e-7, atol=1e-5)
+
+
+@pytest.mark.parametrize("use_udp", [False, True])
+def test_rotated_per_sample_transform_matches_reference_golden(cuda_device, golden, use_udp):
+    """(center, scale, rot) -> crop for rot != 0, end to end against the reference's OWN
+    TopDownAffine.transform (its matrix, cv2.warpAffine, its joints) fed float32 rotations as
+    its pipeline does: the per-sample transform evaluates the rotation scalars with numpy on
+    the host and solves / warps on the device -- every crop byte equal.  The batched device
+    path (device sin / cos, matrix within 1e-9) is measured beside it."""
+    g = golden("affine_rot_ref.npz")
+    tag = "udp" if use_udp else "std"
+    cfg = dict(synth.TOPDOWN_CONFIG, image_size=[96, 128], heatmap_size=[24, 32])
+    at = mp.create_transform("topdown_affine", is_train=False, config=cfg, use_udp=use_udp)
+    n = len(g["rots"])
+    for i in range(n):
+        state = dict(image=g["images"][i], center=g["center"][i], scale=g["scale"][i],
+                     rotation=np.asarray(g["rots"][i]), keypoints=g["kps_in"][i].copy())
+        out = at.transform(state)
+        assert np.array_equal(out["image"], g[f"crops_{tag}"][i]), i
+        if use_udp:   # sgemm accumulation order is the BLAS build's (2 ulp bar, as at rot = 0)
+            assert np.allclose(out["keypoints"], g[f"kps_{tag}"][i], rtol=3e-7, atol=1e-5)
+        else:
+            assert np.array_equal(out["keypoints"], g[f"kps_{tag}"][i])
+    # batched path, rotation on the device: how many bytes differ from the reference's crops
+    dev = cuda_device
+    crops, _ = at.affine_batch(_t(g["images"], dev), _t(g["center"], dev), _t(g["scale"], dev),
+                               _t(g["rots"], dev))
+    diff = int((crops.cpu().numpy() != g[f"crops_{tag}"]).sum())
+    print(f"\nbatched rotated crops ({tag}): {diff} of {crops.numel()} bytes differ from the "
+          "reference's (device sin/cos, float64 direction)")
+    assert diff <= crops.numel() // 50   # a matrix a few 1e-9 off moves a few 1/1024-pixel ties
 
 
 def test_warp_matches_cv2_golden(cuda_device, golden):
