@@ -669,6 +669,14 @@ def run_ours(args, wl):
     if world > 1 and not args.nccl_gather:
         gatherer = pdist.make_gatherer(n, K, dev)
 
+    # The scatter of step t and the wait for step t - 1 run on a SIDE stream, next to the
+    # parameter kernels and the crop warp of step t + 1; the main stream joins before the next
+    # decode, which overwrites the results the scatter reads.  (--fused-gather instead lets the
+    # decode kernel store into every rank's table itself: one kernel, measured 11 us per step
+    # slower at N = 8, because its stores are 4 bytes each.)
+    side = torch.cuda.Stream(device=dev) if gatherer is not None else None
+    joins = [None]     # event: the side stream has finished the previous step's gather work
+
     def step(record=False):
         if record:
             e0, e1, e2 = ev(), ev(), ev()
@@ -678,21 +686,36 @@ def run_ours(args, wl):
         codec.warp_affine(images, off, src_hw, inv, cfg["image_size"], out=crops)
         if record:
             e1.record(stream)
-        preds, bxs = codec.topdown_decode(heat, center, scale, score, flipped=flip, params=dparams)
+        cur = torch.cuda.current_stream()   # (the capture stream while a graph is recorded)
+        if joins[0] is not None:
+            cur.wait_event(joins[0])
+            joins[0] = None
+        preds, bxs = codec.topdown_decode(heat, center, scale, score, flipped=flip, params=dparams,
+                                          gather=gatherer if args.fused_gather else None)
         if record:
             e2.record(stream)
             marks.append((e0, e1, e2))
         if world > 1:
-            if gatherer is not None:
-                # one kernel of peer stores + a flag; what is waited for here is the arrival
-                # of the PREVIOUS step's rows (this step's are waited for in the next step)
-                gatherer.gather_async(preds, bxs)
-                gatherer.wait_lag(1)
-            else:                        # NCCL all-gather
+            if gatherer is None:         # NCCL all-gather
                 pdist.all_gather_keypoints(preds, bxs, world * n)
+            elif args.fused_gather:
+                gatherer.wait_lag(1)
+            else:
+                done = torch.cuda.Event()
+                done.record(cur)
+                side.wait_event(done)
+                with torch.cuda.stream(side):
+                    gatherer.gather_async(preds, bxs)   # one kernel of peer stores + a flag
+                    # the arrival of the PREVIOUS step's rows (this step's: in the next step)
+                    gatherer.wait_lag(1)
+                    joins[0] = torch.cuda.Event()
+                    joins[0].record(side)
         return preds, bxs
 
     def drain():
+        if joins[0] is not None:
+            torch.cuda.current_stream().wait_event(joins[0])
+            joins[0] = None
         if gatherer is not None:
             gatherer.wait_lag(0)
 
@@ -745,6 +768,9 @@ def run_ours(args, wl):
             with torch.cuda.graph(graph):
                 for _ in range(unroll):
                     step()
+                if joins[0] is not None:      # a capture must end with every fork joined
+                    torch.cuda.current_stream().wait_event(joins[0])
+                    joins[0] = None
             how = f"CUDA graph of {unroll} step(s), replayed"
             if gatherer is not None:
                 gatherer.captured(unroll)  # the capture itself ran nothing
@@ -759,18 +785,41 @@ def run_ours(args, wl):
             torch.cuda.synchronize()
     q, r = (steps // unroll, steps % unroll) if graph is not None else (0, steps)
     t_start, t_end = ev(), ev()
-    with ClockSampler(local_rank) as clocks:
+    dbg = []
+    with ClockSampler(local_rank) as clocks:   # (its thread starts before the ranks line up)
+        fence()
+        # One untimed unit lines the ranks up ON THE DEVICE: every step waits for every rank's
+        # previous one, so after it the ranks are within a step of each other  (The host
+        # leaves the barrier above up to 2 ms apart on an 8-GPU box, measured; a region of
+        # 20 x 0.7 ms would otherwise time that skew, not the steps.)
+        if graph is not None:
+            graph.replay()
+            if gatherer is not None:
+                gatherer.replayed(unroll)
+        else:
+            step()
+        drain()   # ... and within microseconds once each has seen every rank's last rows
         t_start.record(stream)
         for _ in range(q):
             graph.replay()
             if gatherer is not None:
                 gatherer.replayed(unroll)
+            if args.debug_steps:
+                dbg.append(ev())
+                dbg[-1].record(stream)
         for _ in range(r):
             step()
+            if args.debug_steps:
+                dbg.append(ev())
+                dbg[-1].record(stream)
         drain()
         t_end.record(stream)
         fence()
     total_ms = t_start.elapsed_time(t_end)
+    if args.debug_steps:
+        marks_ms = [t_start.elapsed_time(e) for e in dbg] + [total_ms]
+        print(f"rank {rank}: cumulative ms after each launch unit {[round(m, 3) for m in marks_ms]}",
+              file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -905,7 +954,7 @@ def run_ours(args, wl):
             v, _, per_step = cpu_reference_run(wl, max(cores * 16, 256), 2, 1, cores)
             cpu = {"value": v, "unit": "crops/s", "cores": cores, "kind": "port",
                    "sample": f"{per_step} crops per step x 2 steps (cv2 warp + numpy decode)"}
-        launches = 4 + (2 if gatherer is not None else 0)
+        launches = 4 + ((1 if args.fused_gather else 2) if gatherer is not None else 0)
         line = {
             "metric": "person-crops/sec encode+decode", "value": value, "unit": "crops/s",
             "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -921,9 +970,10 @@ def run_ours(args, wl):
             "e2e": e2e,
             "gpu_launches": launches * steps,
             "gather": (None if world == 1 else
-                       ("peer stores (multicast) + flags, wait deferred by one step"
-                        if gatherer is not None and gatherer.multicast
-                        else "peer stores + flags, wait deferred by one step"
+                       (("decode kernel stores into every rank's table" if args.fused_gather
+                         else "scatter kernel of peer stores on a side stream") +
+                        (" (NVSwitch multicast)" if gatherer.multicast else " (peer pointers)") +
+                        " + flags, wait deferred by one step"
                         if gatherer is not None else "nccl all_gather")),
             "gather_verified": gather_verified,
             "parity": "numpy/cv2/scipy half bit-exact vs goldens made by the unmodified "
@@ -950,8 +1000,14 @@ def main():
     ap.add_argument("--upload", default=None, choices=["full", "roi", "roi_kernel"],
                     help="e2e: how the source images cross PCIe (default: codec.DEFAULT_UPLOAD)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-steps", action="store_true",
+                    help="print, per rank, the device time after every replay / eager step")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every timed step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--fused-gather", action="store_true",
+                    help="N > 1: let the decode kernel store its results into every rank's "
+                         "table itself (pc_topdown_decode_gather) instead of a scatter kernel "
+                         "on a side stream")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="N > 1: use the NCCL all-gather instead of the peer-memory stores")
     args = ap.parse_args()

@@ -345,6 +345,28 @@ int pc_scatter_results_signal(const float* d_preds, const float* d_boxes,
 int pc_wait_peer_flags(const uint32_t* d_flags, int32_t num_peers, const uint32_t* d_step,
                        uint32_t lag, void* stream);
 
+/* The decode and the all-gather as ONE kernel: pc_topdown_decode whose result stores ALSO go,
+ * value by value as they are produced, into rows [row_offset, row_offset + n) of the gathered
+ * table of every rank (multicast or peer-mapped, as in pc_scatter_results), and whose last
+ * warp publishes the step like pc_scatter_results_signal does.  No scatter kernel, no second
+ * pass over the results; the exchange overlaps the decode.  All fields as in
+ * pc_scatter_results_signal.  d_all_preds / d_all_boxes still receive the local results. */
+typedef struct pc_gather_target {
+  void* const* h_peer_tables; /* HOST array of num_peers device pointers (NULL with multicast) */
+  int32_t num_peers;
+  void* d_multicast_table;    /* or NULL */
+  int64_t row_offset;
+  void* const* h_peer_flags;  /* HOST array of num_flag_peers device pointers */
+  int32_t num_flag_peers, my_rank;
+  uint32_t* d_step;
+  int32_t* d_counter;
+} pc_gather_target;
+int pc_topdown_decode_gather(const float* d_heatmap, const float* d_flipped,
+                             const float* d_center, const float* d_scale, const float* d_score,
+                             float* d_all_preds, float* d_all_boxes,
+                             const pc_topdown_decode_params* params, int64_t n,
+                             const pc_gather_target* gather, void* stream);
+
 /* ---- host-buffer front end (what the e2e number is measured through) ----
  * Same decode as pc_topdown_decode but every pointer is a HOST pointer.  The
  * context owns device scratch and two streams; crops are streamed through in

@@ -170,6 +170,20 @@ class OksNmsParams(Structure):
     ]
 
 
+class GatherTarget(Structure):
+    _fields_ = [
+        ("h_peer_tables", POINTER(c_void_p)),
+        ("num_peers", c_int32),
+        ("d_multicast_table", c_void_p),
+        ("row_offset", c_int64),
+        ("h_peer_flags", POINTER(c_void_p)),
+        ("num_flag_peers", c_int32),
+        ("my_rank", c_int32),
+        ("d_step", c_void_p),
+        ("d_counter", c_void_p),
+    ]
+
+
 class AffineHostParams(Structure):
     _fields_ = [
         ("src_h", c_int32),
@@ -225,6 +239,9 @@ SIGNATURES = {
         c_int, [_P, _P, POINTER(c_void_p), c_int32, _P, c_int64, c_int32, c_int64,
                 POINTER(c_void_p), c_int32, c_int32, _P, _P, _P]),
     "pc_wait_peer_flags": (c_int, [_P, c_int32, _P, ctypes.c_uint32, _P]),
+    "pc_topdown_decode_gather": (
+        c_int, [_P, _P, _P, _P, _P, _P, _P, POINTER(TopDownDecodeParams), c_int64,
+                POINTER(GatherTarget), _P]),
     "pc_ctx_create": (c_int, [c_int, c_int64, POINTER(c_void_p)]),
     "pc_ctx_destroy": (c_int, [c_void_p]),
     "pc_ctx_last_transfer_bytes": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),

@@ -233,9 +233,15 @@ def make_decode_params(num_joints: int, height: int, width: int, pixel_std: floa
 def topdown_decode(heatmap: torch.Tensor, center: torch.Tensor, scale: torch.Tensor,
                    score: torch.Tensor, flipped: Optional[torch.Tensor] = None,
                    params: Optional["_lib.TopDownDecodeParams"] = None,
-                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, **kwargs):
+                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, gather=None,
+                   **kwargs):
     """heatmap f32 [N,K,H,W] (+ optional flipped pair) -> (all_preds [N,K,3], all_boxes [N,6]);
-    ``out`` = (preds, boxes) writes into caller-owned contiguous float32 tensors."""
+    ``out`` = (preds, boxes) writes into caller-owned contiguous float32 tensors.
+
+    ``gather`` (a ``dist.PeerGather``): the decode kernel also stores every result into the
+    gathered table of every rank and signals the step (``pc_topdown_decode_gather``: decode and
+    all-gather as one kernel); wait for the other ranks' rows with ``gather.wait_lag`` /
+    the ticket ``gather.last_ticket()``."""
     heatmap = _f32(heatmap, "heatmap")
     if heatmap.dim() != 4:
         raise ValueError("`heatmap` must have shape [N, K, H, W]")
@@ -264,10 +270,17 @@ def topdown_decode(heatmap: torch.Tensor, center: torch.Tensor, scale: torch.Ten
         preds = torch.empty((n, k, 3), dtype=torch.float32, device=heatmap.device)
         boxes = torch.empty((n, 6), dtype=torch.float32, device=heatmap.device)
     with torch.cuda.device(heatmap.device):
-        _lib.call("pc_topdown_decode", _lib.device_ptr(heatmap), _lib.device_ptr(flipped),
-                  _lib.device_ptr(center), _lib.device_ptr(scale), _lib.device_ptr(score),
-                  _lib.device_ptr(preds), _lib.device_ptr(boxes), ctypes.byref(params), n,
-                  _lib.current_stream())
+        if gather is not None:
+            target = gather.next_target(n, k)      # bumps the gather's step
+            _lib.call("pc_topdown_decode_gather", _lib.device_ptr(heatmap),
+                      _lib.device_ptr(flipped), _lib.device_ptr(center), _lib.device_ptr(scale),
+                      _lib.device_ptr(score), _lib.device_ptr(preds), _lib.device_ptr(boxes),
+                      ctypes.byref(params), n, ctypes.byref(target), _lib.current_stream())
+        else:
+            _lib.call("pc_topdown_decode", _lib.device_ptr(heatmap), _lib.device_ptr(flipped),
+                      _lib.device_ptr(center), _lib.device_ptr(scale), _lib.device_ptr(score),
+                      _lib.device_ptr(preds), _lib.device_ptr(boxes), ctypes.byref(params), n,
+                      _lib.current_stream())
     return preds, boxes
 
 

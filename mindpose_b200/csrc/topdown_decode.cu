@@ -30,6 +30,8 @@ constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;  // + the producer war
 constexpr int kMaxStages = 12;
 constexpr int kDarkSamples = 7;
 
+constexpr int kGatherMaxPeers = 16;
+
 struct DecodeArgs {
   const float* heatmap;
   const float* flipped;
@@ -55,6 +57,16 @@ struct DecodeArgs {
   uint32_t stage_floats;  // floats per stage (HW or 2*HW)
   int32_t vec_ok;         // W % 4 == 0
   int32_t bulk_ok;        // planes 16-byte aligned in HBM (H*W % 4 == 0, bases % 16 == 0)
+  // ---- fused all-gather of the results (pc_topdown_decode_gather; g_on = 0 otherwise) ----
+  // Every result is ALSO stored into row g_row0 + crop of the gathered table [total, 3K + 6]
+  // of every rank: through the NVSwitch multicast mapping (g_mc) or the peer-mapped tables.
+  int32_t g_on, g_peers, g_nflags, g_rank;
+  int64_t g_row0;
+  float* g_mc;
+  float* g_peer[kGatherMaxPeers];
+  uint32_t* g_flags[kGatherMaxPeers];  // flag array (one word per source rank) on each rank
+  uint32_t* g_step;                    // this rank's step number (device memory)
+  int32_t* g_counter;                  // CTAs that have finished (zero between launches)
 };
 
 struct DecodeTables {
@@ -257,6 +269,16 @@ __device__ __forceinline__ float2 dark_offset(const float* hm, const float* fm, 
   return o;
 }
 
+// one float into element i of the gathered table of every rank
+__device__ __forceinline__ void gather_store(const DecodeArgs& a, int64_t i, float v) {
+  if (a.g_mc) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.g_mc + i), "f"(v)
+                 : "memory");
+  } else {
+    for (int p = 0; p < a.g_peers; ++p) a.g_peer[p][i] = v;
+  }
+}
+
 template <bool FLIP>
 __global__ void __launch_bounds__(kDecodeThreads, 1)
     topdown_decode_kernel(const DecodeArgs a, const __grid_constant__ DecodeTables tab) {
@@ -275,11 +297,15 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
   float* s_rows = s_kernel + PC_MAX_DARK_KERNEL * PC_MAX_DARK_KERNEL;  // [groups][7][17]
   float* s_win = s_rows + (kConsumerWarps / a.group) * a.row_floats;  // [groups][(ks+2)^2]
 
+  __shared__ int s_warps_done_v;
+  int* const s_warps_done = &s_warps_done_v;
+
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = a.stages;
 
   if (threadIdx.x == 0) {
+    s_warps_done_v = 0;
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -559,14 +585,51 @@ __global__ void __launch_bounds__(kDecodeThreads, 1)
       o[0] = rx;
       o[1] = ry;
       o[2] = bv;
+      const float area = __fmul_rn(s_w, s_h);
       if (k == 0) {
         float* b = a.all_boxes + n * 6;
         b[0] = cx;
         b[1] = cy;
         b[2] = sw;
         b[3] = sh;
-        b[4] = __fmul_rn(s_w, s_h);
+        b[4] = area;
         b[5] = sc;
+      }
+      if (a.g_on) {  // the same values straight into every rank's gathered table
+        const int64_t row = (a.g_row0 + n) * (int64_t)(a.K * 3 + 6);
+        gather_store(a, row + k * 3, rx);
+        gather_store(a, row + k * 3 + 1, ry);
+        gather_store(a, row + k * 3 + 2, bv);
+        if (k == 0) {
+          const int64_t b0 = row + a.K * 3;
+          gather_store(a, b0, cx);
+          gather_store(a, b0 + 1, cy);
+          gather_store(a, b0 + 2, sw);
+          gather_store(a, b0 + 3, sh);
+          gather_store(a, b0 + 4, area);
+          gather_store(a, b0 + 5, sc);
+        }
+      }
+    }
+  }
+  if (a.g_on) {
+    // The remote stores of this warp are made visible system-wide, then the last warp of
+    // the last CTA publishes the step number on every rank (release, system scope): the
+    // consumers wait for it with pc_wait_peer_flags.  One fence per warp (by the lane that
+    // stored), the counters only count.
+    if (lane == 0) {
+      __threadfence_system();
+      if (atomicAdd(s_warps_done, 1) == kConsumerWarps - 1) {
+        if (atomicAdd(a.g_counter, 1) == (int)gridDim.x - 1) {
+          *a.g_counter = 0;  // for the next launch (stream order)
+          const uint32_t step = *a.g_step + 1u;
+          *a.g_step = step;
+          __threadfence_system();
+          for (int p = 0; p < a.g_nflags; ++p)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.g_flags[p] + a.g_rank),
+                         "r"(step)
+                         : "memory");
+        }
       }
     }
   }
@@ -594,10 +657,10 @@ static void build_dark_kernel(int ks, float* out) {
 
 using namespace pc;
 
-extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
-                                 const float* d_center, const float* d_scale,
-                                 const float* d_score, float* d_all_preds, float* d_all_boxes,
-                                 const pc_topdown_decode_params* p, int64_t n, void* stream) {
+static int decode_launch(const float* d_heatmap, const float* d_flipped, const float* d_center,
+                         const float* d_scale, const float* d_score, float* d_all_preds,
+                         float* d_all_boxes, const pc_topdown_decode_params* p, int64_t n,
+                         const pc_gather_target* g, void* stream) {
   PC_REQUIRE(p != nullptr, PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode: params is NULL");
   PC_REQUIRE(n >= 0, PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode: n = %lld < 0", (long long)n);
   PC_REQUIRE(p->num_joints >= 1 && p->num_joints <= PC_MAX_JOINTS, PC_ERR_INVALID_ARGUMENT,
@@ -611,6 +674,20 @@ extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
                    (p->kernel_size & 1),
                PC_ERR_UNSUPPORTED, "pc_topdown_decode: kernel_size %d must be odd and <= %d",
                p->kernel_size, PC_MAX_DARK_KERNEL);
+  if (g) {
+    PC_REQUIRE(n >= 1, PC_ERR_INVALID_ARGUMENT,
+               "pc_topdown_decode_gather: a rank without crops must still signal -- use "
+               "pc_scatter_results_signal with n = 0");
+    PC_REQUIRE(g->row_offset >= 0 && g->d_step && g->d_counter && g->h_peer_flags &&
+                   g->num_flag_peers >= 1 && g->num_flag_peers <= kGatherMaxPeers &&
+                   g->my_rank >= 0 && g->my_rank < g->num_flag_peers,
+               PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode_gather: bad flags / step / counter");
+    PC_REQUIRE(g->d_multicast_table || (g->h_peer_tables && g->num_peers >= 1 &&
+                                        g->num_peers <= kGatherMaxPeers),
+               PC_ERR_INVALID_ARGUMENT,
+               "pc_topdown_decode_gather: need a multicast table or 1..%d peer tables",
+               kGatherMaxPeers);
+  }
   if (n == 0) return PC_OK;
   PC_REQUIRE(d_heatmap && d_center && d_scale && d_score && d_all_preds && d_all_boxes,
              PC_ERR_INVALID_ARGUMENT, "pc_topdown_decode: NULL tensor pointer");
@@ -663,6 +740,37 @@ extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
   a.shift_heatmap = p->flip_test ? p->shift_heatmap : 0;
   a.vec_ok = (a.W % 4 == 0);
   a.bulk_ok = bulk_ok ? 1 : 0;
+  a.g_on = g ? 1 : 0;
+  a.g_peers = a.g_nflags = a.g_rank = 0;
+  a.g_row0 = 0;
+  a.g_mc = nullptr;
+  a.g_step = nullptr;
+  a.g_counter = nullptr;
+  for (int i = 0; i < kGatherMaxPeers; ++i) {
+    a.g_peer[i] = nullptr;
+    a.g_flags[i] = nullptr;
+  }
+  if (g) {
+    a.g_row0 = g->row_offset;
+    a.g_mc = static_cast<float*>(g->d_multicast_table);
+    if (!a.g_mc) {
+      a.g_peers = g->num_peers;
+      for (int i = 0; i < g->num_peers; ++i) {
+        PC_REQUIRE(g->h_peer_tables[i] != nullptr, PC_ERR_INVALID_ARGUMENT,
+                   "pc_topdown_decode_gather: peer table %d is NULL", i);
+        a.g_peer[i] = static_cast<float*>(g->h_peer_tables[i]);
+      }
+    }
+    a.g_nflags = g->num_flag_peers;
+    a.g_rank = g->my_rank;
+    for (int i = 0; i < g->num_flag_peers; ++i) {
+      PC_REQUIRE(g->h_peer_flags[i] != nullptr, PC_ERR_INVALID_ARGUMENT,
+                 "pc_topdown_decode_gather: flag array %d is NULL", i);
+      a.g_flags[i] = static_cast<uint32_t*>(g->h_peer_flags[i]);
+    }
+    a.g_step = g->d_step;
+    a.g_counter = g->d_counter;
+  }
   a.divWq = make_fastdiv((uint32_t)(a.vec_ok ? a.W / 4 : 1));
   a.step_xq = a.vec_ok ? 32 % (a.W / 4) : 0;
   a.step_y = a.vec_ok ? 32 / (a.W / 4) : 0;
@@ -720,4 +828,24 @@ extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
   }
   PC_CUDA(cudaGetLastError());
   return PC_OK;
+}
+
+extern "C" int pc_topdown_decode(const float* d_heatmap, const float* d_flipped,
+                                 const float* d_center, const float* d_scale,
+                                 const float* d_score, float* d_all_preds, float* d_all_boxes,
+                                 const pc_topdown_decode_params* p, int64_t n, void* stream) {
+  return decode_launch(d_heatmap, d_flipped, d_center, d_scale, d_score, d_all_preds,
+                       d_all_boxes, p, n, nullptr, stream);
+}
+
+extern "C" int pc_topdown_decode_gather(const float* d_heatmap, const float* d_flipped,
+                                        const float* d_center, const float* d_scale,
+                                        const float* d_score, float* d_all_preds,
+                                        float* d_all_boxes, const pc_topdown_decode_params* p,
+                                        int64_t n, const pc_gather_target* gather,
+                                        void* stream) {
+  PC_REQUIRE(gather != nullptr, PC_ERR_INVALID_ARGUMENT,
+             "pc_topdown_decode_gather: gather target is NULL");
+  return decode_launch(d_heatmap, d_flipped, d_center, d_scale, d_score, d_all_preds,
+                       d_all_boxes, p, n, gather, stream);
 }

@@ -188,6 +188,31 @@ class PeerGather:
                  lib.current_stream())
         return GatherTicket(self, self._step, self.tables[i])
 
+    def next_target(self, rows: int, num_joints: int):
+        """The ``pc_gather_target`` of the NEXT step, for a producer kernel that stores its
+        results into the gathered tables itself (``codec.topdown_decode(..., gather=self)``:
+        decode and all-gather as one kernel).  Counts as this step's scatter."""
+        if rows != self.rows or num_joints != self.k:
+            raise ValueError(f"this gather holds {self.rows} rows of {self.k} joints per rank")
+        self._step += 1
+        i = self._step % self.TABLES
+        lib = self._lib
+        t = lib.GatherTarget()
+        t.h_peer_tables = self._peers[i]
+        t.num_peers = self.world
+        t.d_multicast_table = self._mc[i] if self.multicast else None
+        t.row_offset = self.rank * self.rows
+        t.h_peer_flags = self._peer_flags
+        t.num_flag_peers = self.world
+        t.my_rank = self.rank
+        t.d_step = lib.device_ptr(self._dstep)
+        t.d_counter = lib.device_ptr(self._counter)
+        return t
+
+    def last_ticket(self) -> GatherTicket:
+        """Ticket of the latest scatter (made by ``gather_async`` or by a fused producer)."""
+        return GatherTicket(self, self._step, self.tables[self._step % self.TABLES])
+
     def _wait(self, step: int) -> None:
         if step <= self._waited:         # flags only grow: a later wait covers earlier steps
             return

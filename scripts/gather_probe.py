@@ -66,6 +66,50 @@ res["deferred_gather_us"] = timed(deferred) * 1e3
 prev[0].wait()
 res["nccl_all_gather_us"] = timed(lambda: pdist.all_gather_keypoints(preds, boxes, world * n)) * 1e3
 res["multicast"] = g.multicast
+
+
+def graphed(label, body, reps=30):
+    """device time per step of `body` (scatter [+ wait]) from a captured graph of `reps` steps"""
+    torch.cuda.synchronize()
+    dist.barrier()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for _ in range(reps):
+            body()
+    g.captured(reps)
+    gr.replay()
+    g.replayed(reps)
+    g.wait_lag(0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(5):
+        gr.replay()
+        g.replayed(reps)
+    g.wait_lag(0)
+    b.record(stream)
+    b.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / (5 * reps)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res[label] = float(t) * 1e3
+
+
+def body_deferred():
+    g.gather_async(preds, boxes)
+    g.wait_lag(1)
+
+
+def body_blocking():
+    g.gather_async(preds, boxes)
+    g.wait_lag(0)
+
+
+graphed("graph_deferred_us", body_deferred)
+graphed("graph_blocking_us", body_blocking)
+g.multicast = False
+graphed("graph_deferred_peer_ptr_us", body_deferred)
+g.multicast = res["multicast"]
 # without multicast (peer pointers)
 g.multicast = False
 res["scatter_signal_peer_ptr_us"] = timed(scatter_only) * 1e3

@@ -64,6 +64,29 @@ def _worker(rank, world, port, rows, k, out_dir):
         got_p, got_b = prev.wait()
         torch.cuda.synchronize()
         assert torch.equal(got_p, prev_want[0]) and torch.equal(got_b, prev_want[1])
+
+        # decode and all-gather as ONE kernel (pc_topdown_decode_gather): the decode kernel
+        # stores its results into every rank's table itself
+        import mindpose_b200 as mp
+        from mindpose_b200 import codec, synth
+
+        gen = torch.Generator(device=dev).manual_seed(100 + rank)
+        hm = torch.rand(rows, k, 64, 48, device=dev, generator=gen)
+        fl = torch.rand(rows, k, 64, 48, device=dev, generator=gen)
+        center = torch.rand(rows, 2, device=dev, generator=gen) * 400
+        scale = torch.rand(rows, 2, device=dev, generator=gen) * 2.8 + 0.2
+        score = torch.rand(rows, device=dev, generator=gen)
+        dec = mp.create_decoder("topdown_heatmap", dark_udp_refine=True)
+        p = dec._params(k, 64, 48, flip_index=synth.flip_index(), shift_heatmap=False)
+        for _ in range(4):
+            preds, boxes = codec.topdown_decode(hm, center, scale, score, flipped=fl, params=p,
+                                                gather=g)
+            got_p, got_b = g.last_ticket().wait()
+            plain_p, plain_b = codec.topdown_decode(hm, center, scale, score, flipped=fl, params=p)
+            want_p, want_b = pdist.all_gather_keypoints(plain_p, plain_b, world * rows)
+            torch.cuda.synchronize()
+            assert torch.equal(preds, plain_p) and torch.equal(boxes, plain_b)
+            assert torch.equal(got_p, want_p) and torch.equal(got_b, want_b)
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(g.multicast)]))
     finally:
         dist.destroy_process_group()
