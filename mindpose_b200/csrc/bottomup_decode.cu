@@ -17,8 +17,6 @@
 // per-thread maximum, which is a valid lower bound for the M-th largest element.
 #include <math.h>
 
-#include <mutex>
-
 #include "common.cuh"
 
 namespace pc {
@@ -1510,39 +1508,6 @@ __global__ void __launch_bounds__(128) bottomup_shift_kernel(const BuArgs a, int
 }  // namespace pc
 
 using namespace pc;
-
-// The row-flag scratch comes from a stream-ordered memory pool OWNED BY THE LIBRARY (one per
-// device, created on first use, never destroyed): a pool keeps freed memory only if its
-// release threshold says so, and raising the threshold of the device's DEFAULT pool would
-// change how every other cudaMallocAsync user of the process returns memory to the driver.
-static cudaError_t scratch_pool(cudaMemPool_t* out) {
-  static std::mutex mu;
-  static cudaMemPool_t pools[64] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  std::lock_guard<std::mutex> lock(mu);
-  if (!pools[dev]) {
-    cudaMemPoolProps props = {};
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = dev;
-    cudaMemPool_t pool;
-    e = cudaMemPoolCreate(&pool, &props);
-    if (e != cudaSuccess) return e;
-    uint64_t keep = UINT64_MAX;  // of this pool only: a call must not cost a driver allocation
-    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    if (e != cudaSuccess) {
-      cudaMemPoolDestroy(pool);
-      return e;
-    }
-    pools[dev] = pool;
-  }
-  *out = pools[dev];
-  return cudaSuccess;
-}
 
 // Launch of the pair kernel as a programmatic dependent of mask_zero_rows_kernel (the
 // previous launch on the stream): its CTAs may become resident and run their prologue

@@ -17,6 +17,9 @@ namespace pc {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int sm_count_cached();  // SM count of the current device (148 on B200)
+// Stream-ordered memory pool OWNED BY THE LIBRARY (one per device, created on first use, never
+// destroyed) for the small scratch some ops need: cudaMallocFromPoolAsync / cudaFreeAsync.
+cudaError_t scratch_pool(cudaMemPool_t* out);
 
 #define PC_REQUIRE(cond, code, ...)  \
   do {                               \

@@ -43,6 +43,38 @@ int sm_count_cached() {
   return counts[dev];
 }
 
+// A pool keeps freed memory only if its release threshold says so, and raising the threshold
+// of the device's DEFAULT pool would change how every other cudaMallocAsync user of the
+// process returns memory to the driver: the library has its own.
+cudaError_t scratch_pool(cudaMemPool_t* out) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    uint64_t keep = UINT64_MAX;  // of this pool only: a call must not cost a driver allocation
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) {
+      cudaMemPoolDestroy(pool);
+      return e;
+    }
+    pools[dev] = pool;
+  }
+  *out = pools[dev];
+  return cudaSuccess;
+}
+
 }  // namespace pc
 
 using namespace pc;

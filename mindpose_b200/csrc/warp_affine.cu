@@ -703,11 +703,14 @@ __global__ void __launch_bounds__(kWarpThreads)
 // 2 x 18 KB 0.469 ms, 2 x 24 KB 0.480 ms against 0.445 ms for 1 x 36 KB -- shorter passes,
 // fewer CTAs; profiles/README.md, r02f.)
 constexpr int kBandBytes = 36 * 1024;
+// (Measured and not kept, profiles/README.md r02s: 44 KB bands / 5 CTAs 0.569 ms, 128-row
+// tiles 0.514 ms, unroll 2 / 8 0.484 / 0.478 ms, and skipping the loads of a source row the
+// previous output row already fetched 0.480 ms -- its uniform branches cost more than the
+// loads they save -- against 0.445 ms for this form.)
+constexpr int kBandUnroll = 4;
 constexpr int kBandMaxThreads = 512;   // dst_w <= 512 (one column per thread)
 constexpr int kBandPassRows = 16;      // output rows staged and computed at a time
 constexpr int kBandMaxTileRows = 64;   // output rows per CTA (the host picks 16, 32 or 64)
-static_assert(sizeof(QuadSmem) <= (size_t)kBandBytes, "the quad path borrows the band buffers");
-
 struct BandRow {
   uint32_t addr_a;  // shared-memory address of the word holding source pixel (sy, clo) ...
   uint32_t addr_b;  // ... and (sy + 1, clo): the rows' 16-byte phases differ when ws3 % 16 != 0
@@ -734,23 +737,16 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
-// the quad path as a real call: its registers then do not count against the band path's
-__device__ __noinline__ void warp3_quad_tile_call(
-    QuadSmem& sm, const uint8_t* src, const int64_t* src_off, const int32_t* src_hw,
-    const double* inv, void* dst, int dst_w, int dst_h, int64_t crop, int tile, FastDiv div_wq) {
-  warp3_quad_tile<false, true>(sm, src, src_off, src_hw, inv, dst, dst_w, dst_h, crop, tile,
-                               div_wq, NormArgs());
-}
-
-// 56 registers: 6 CTAs of 192 threads per SM, as many as a 36 KB band allows (the band path
-// itself needs fewer; what spills is the call of the quad path)
-__global__ void __maxnreg__(56)
+// 48 registers: 6 CTAs of 192 threads per SM, as many as a 36 KB band allows.
+// todo: [0] = number of entries, [1 ...] = the 16-row tiles (crop * tiles16 + tile) this kernel
+// leaves to the quad kernel.
+__global__ void __maxnreg__(48)
     warp_affine_u8x3_band_kernel(const uint8_t* __restrict__ src,
                                  const int64_t* __restrict__ src_off,
                                  const int32_t* __restrict__ src_hw,
                                  const double* __restrict__ inv, uint8_t* __restrict__ dst,
                                  int dst_w, int dst_h, int tile_rows, int tiles_per_crop,
-                                 FastDiv div_wq) {
+                                 int* __restrict__ todo) {
   extern __shared__ __align__(128) uint8_t s_band[];  // kBandBytes
   __shared__ int s_x0[kBandMaxTileRows];
   __shared__ int s_y0[kBandMaxTileRows];
@@ -804,12 +800,14 @@ __global__ void __maxnreg__(56)
   // nb_max >= 2: one output row needs exactly two source rows, so the passes always advance
   ok = ok && nb_max >= 2;
   if (!ok) {
-    // the quad path works on tiles of kWarp3TileRows rows
-    QuadSmem& qs = *reinterpret_cast<QuadSmem*>(s_band);
-    for (int r = 0; r < rows; r += kWarp3TileRows) {
-      warp3_quad_tile_call(qs, src, src_off, src_hw, inv, dst, dst_w, dst_h, crop,
-                           (row0 + r) / kWarp3TileRows, div_wq);
-      __syncthreads();
+    // Rotation, ws % 4 != 0, a mirrored matrix, a band that does not fit: the tile goes to the
+    // quad kernel (its 16-row tiles), launched right after this kernel over the list.
+    if (tid == 0) {
+      const int tiles16 = (dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
+      const int first = row0 / kWarp3TileRows;  // tile_rows is a multiple of kWarp3TileRows
+      const int cnt = (rows + kWarp3TileRows - 1) / kWarp3TileRows;
+      const int at = atomicAdd(todo, cnt);
+      for (int i = 0; i < cnt; ++i) todo[1 + at + i] = (int)crop * tiles16 + first + i;
     }
     return;
   }
@@ -917,7 +915,7 @@ __global__ void __maxnreg__(56)
     {
       const int cnt = cur.r_end - cur.r_begin;
       uint8_t* o = out + (size_t)cur.r_begin * out_pitch;
-#pragma unroll 4
+#pragma unroll kBandUnroll
       for (int i = 0; i < cnt; ++i) {
         const uint4 rc = lds128(row_tab + 16u * (uint32_t)i);  // addr_a, addr_b, gy, uy
         const uint32_t A0 = lds32(rc.x + colA), B0 = lds32(rc.x + colA + 4u);
@@ -949,6 +947,25 @@ __global__ void __maxnreg__(56)
   }
 }
 
+// The tiles the band kernel left: the quad kernel over a list, with a fixed grid (the list is
+// empty on the evaluation path, and the launch then costs a few microseconds).
+__global__ void __launch_bounds__(kWarpThreads, 5)
+    warp_affine_u8x3_list_kernel(const uint8_t* __restrict__ src,
+                                 const int64_t* __restrict__ src_off,
+                                 const int32_t* __restrict__ src_hw,
+                                 const double* __restrict__ inv, void* __restrict__ dst, int dst_w,
+                                 int dst_h, FastDiv div_wq, const int* __restrict__ todo) {
+  __shared__ __align__(16) QuadSmem sm;
+  const int count = todo[0];
+  const int tiles16 = (dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    const int t = todo[1 + i];
+    const int crop = t / tiles16;
+    warp3_quad_tile<false, true>(sm, src, src_off, src_hw, inv, dst, dst_w, dst_h, crop,
+                                 t - crop * tiles16, div_wq, NormArgs());
+    __syncthreads();  // the tile's tables are rebuilt for the next one
+  }
+}
 
 }  // namespace pc
 
@@ -1042,31 +1059,41 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
     const int tiles3 = (p->dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
     const int64_t grid3 = n * tiles3;
     PC_REQUIRE(grid3 < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_warp_affine_u8: batch too large");
-    if (p->dst_w % 32 == 0 && p->dst_w <= kBandMaxThreads) {
-      // one thread per output column; rotation-free tiles out of a shared-memory band, the
-      // others through the quad path inside the same kernel
+    if (p->dst_w % 32 == 0 && p->dst_w <= kBandMaxThreads && n * (int64_t)tiles3 < 0x3fffffffLL) {
+      // One thread per output column; rotation-free tiles out of a shared-memory band.  Tiles
+      // that do not qualify are listed in stream-ordered scratch (the library's own pool) and
+      // done by the quad kernel right after.
       // rows per CTA: per-CTA set-up (matrix, column constants) is paid once per tile, so
       // tiles are as tall as still leaves every SM a few rounds of CTAs
       int tile_rows = kBandMaxTileRows;
-      const int64_t want = (int64_t)sm_count_cached() * 6 * 3;
+      const int64_t want = (int64_t)sm_count_cached() * 6 * 3;  // three rounds of CTAs
       while (tile_rows > kWarp3TileRows &&
              n * ((p->dst_h + tile_rows - 1) / tile_rows) < want)
         tile_rows >>= 1;
       const int tiles_b = (p->dst_h + tile_rows - 1) / tile_rows;
-      if (kBandBytes > 47 * 1024) {  // (not the case today) large dynamic shared memory opt-in
-        static bool done[64];
-        int dev = 0;
-        PC_CUDA(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && !done[dev]) {
-          PC_CUDA(cudaFuncSetAttribute(warp_affine_u8x3_band_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kBandBytes));
-          done[dev] = true;
-        }
+      cudaMemPool_t pool;
+      PC_CUDA(scratch_pool(&pool));
+      int* todo = nullptr;
+      PC_CUDA(cudaMallocFromPoolAsync((void**)&todo, sizeof(int) * (size_t)(1 + n * tiles3), pool,
+                                      st));
+      cudaError_t le = cudaMemsetAsync(todo, 0, sizeof(int), st);
+      if (le == cudaSuccess) {
+        warp_affine_u8x3_band_kernel<<<(unsigned)(n * tiles_b), p->dst_w, kBandBytes, st>>>(
+            d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tile_rows, tiles_b,
+            todo);
+        le = cudaGetLastError();
       }
-      warp_affine_u8x3_band_kernel<<<(unsigned)(n * tiles_b), p->dst_w, kBandBytes, st>>>(
-          d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tile_rows, tiles_b,
-          make_fastdiv((uint32_t)(p->dst_w >> 2)));
-      PC_CUDA(cudaGetLastError());
+      if (le == cudaSuccess) {
+        int64_t lgrid = (int64_t)sm_count_cached() * 5;  // <= 51 registers x 256 threads: 5 CTAs per SM
+        if (lgrid > n * tiles3) lgrid = n * tiles3;
+        warp_affine_u8x3_list_kernel<<<(unsigned)lgrid, kWarpThreads, 0, st>>>(
+            d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h,
+            make_fastdiv((uint32_t)(p->dst_w >> 2)), todo);
+        le = cudaGetLastError();
+      }
+      const cudaError_t fe = cudaFreeAsync(todo, st);  // on every path
+      PC_CUDA(le);
+      PC_CUDA(fe);
       return PC_OK;
     }
     warp_affine_u8x3_kernel<false, true><<<(unsigned)grid3, kWarpThreads, 0, st>>>(
