@@ -949,7 +949,7 @@ __global__ void __maxnreg__(48)
 
 // The tiles the band kernel left: the quad kernel over a list, with a fixed grid (the list is
 // empty on the evaluation path, and the launch then costs a few microseconds).
-__global__ void __launch_bounds__(kWarpThreads, 5)
+__global__ void __launch_bounds__(kWarpThreads)
     warp_affine_u8x3_list_kernel(const uint8_t* __restrict__ src,
                                  const int64_t* __restrict__ src_off,
                                  const int32_t* __restrict__ src_hw,
@@ -1084,7 +1084,8 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
         le = cudaGetLastError();
       }
       if (le == cudaSuccess) {
-        int64_t lgrid = (int64_t)sm_count_cached() * 5;  // <= 51 registers x 256 threads: 5 CTAs per SM
+        int64_t lgrid = (int64_t)sm_count_cached() * 4;  // 64 registers x 256 threads: 4 CTAs per SM
+        // (capped at 48 registers for 5 CTAs per SM: rotated crops 1.52 instead of 1.49 ms)
         if (lgrid > n * tiles3) lgrid = n * tiles3;
         warp_affine_u8x3_list_kernel<<<(unsigned)lgrid, kWarpThreads, 0, st>>>(
             d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h,
