@@ -38,6 +38,20 @@ def test_our_arm_line_has_the_contract_keys():
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
     for key in ("sm_mhz", "sm_max_mhz", "reasons"):
         assert key in d["clocks"], key
+    # round 2: the link rate measured beside e2e, how the steps were launched, and every other
+    # BASELINE config device-timed in the same line
+    assert e["link_gbs"]["h2d"]["min_rank_gbs"] > 0 and 0 < e["link_frac"] <= 1.05
+    assert "launch" in d and "kernels_ms" in d
+    cfgs = d["configs"]
+    assert set(cfgs) == {"config1_simplebaseline_b64", "config3_udp_384_b2048",
+                         "config4_higherhrnet_b64", "config5_sweep_1m"}
+    for name, c in cfgs.items():
+        for key in ("workload", "units_per_step", "unit", "ms_per_step", "value", "kernels", "l2"):
+            assert key in c, (name, key)
+        assert abs(c["value"] - c["units_per_step"] / (c["ms_per_step"] * 1e-3)) < 1e-6 * c["value"]
+    assert cfgs["config5_sweep_1m"]["units_per_step"] == 1_000_000
+    assert cfgs["config5_sweep_1m"]["scaling"] == "strong"
+    assert "cpu_match_by_tag" in cfgs["config4_higherhrnet_b64"]
 
 
 def test_reference_arm_line_has_the_contract_keys():
@@ -50,7 +64,8 @@ def test_reference_arm_line_has_the_contract_keys():
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
     ours = _latest("r*_bench.json")
     assert d["metric"] == ours["metric"] and d["unit"] == ours["unit"]
-    assert d["config"]["workload"] == ours["config"]["workload"]
+    assert d["config"] == ours["config"]          # the same object in both arms
+    assert d["warmup"] >= 3
 
 
 def test_reference_arm_runs_on_rank_0_only():
