@@ -103,7 +103,14 @@ int pc_invert_affine(const double* d_fwd, double* d_inv, int64_t n, void* stream
  * Crop i reads the dense HWC image at d_src + d_src_offset[i] (bytes) of size
  * d_src_hw[i] = (rows, cols); several crops may share one source image.
  * d_inv f64 [N,6] from pc_affine_matrices / pc_invert_affine.
- * d_dst u8 [N, dst_h, dst_w, C]. */
+ * d_dst u8 [N, dst_h, dst_w, C].
+ * Memory the call touches besides its arguments: the aligned 32-bit words (quad kernel) or
+ * 16-byte units (band kernel: its bulk copies are 16-byte aligned) that contain the first and
+ * the last byte of a source row may be read up to 15 bytes beyond the row; d_src must therefore
+ * lie in an allocation whose start and size are multiples of 16 bytes (every CUDA allocator's
+ * are), and those bytes are never used.  3-channel crops of a width that is a multiple of 32
+ * take a list of (1 + n * ceil(dst_h / 16)) ints from the library's stream-ordered pool on
+ * `stream` for the duration of the call (capturable into a CUDA graph). */
 typedef struct pc_warp_params {
   int32_t dst_w, dst_h, channels;
 } pc_warp_params;

@@ -15,6 +15,10 @@ for k,v in (d.get('configs') or {}).items(): print(k, v['ms_per_step'], v['value
 "; tail -3 $out/${tag}_bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 3 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
 echo "bench ref exit $?"; cut -c1-300 $out/${tag}_bench_reference.json
+for sec in decode encode warp bottomup bu_encode refine nms; do
+  timeout 240 python scripts/kbench.py --iters 10 --only $sec,group >> $out/${tag}_kbench.log 2>&1 || echo "kbench $sec failed rc=$?" >> $out/${tag}_kbench.log
+done
+grep -v "exact-pass" $out/${tag}_kbench.log
 if [ "$2" = "ncu" ]; then
   CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-configs"
   timeout 300 $CMD > $out/${tag}_plain.log 2>&1 &&
@@ -26,6 +30,6 @@ if [ "$2" = "ncu" ]; then
       -k regex:topdown_decode_kernel -s 3 -c 1 -f -o $out/${tag}_decode $CMD > $out/${tag}_ncu2.log 2>&1
   echo "ncu decode exit $?"
   timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:warp_affine_u8x3 -s 3 -c 1 -f -o $out/${tag}_warp $CMD > $out/${tag}_ncu3.log 2>&1
+      -k regex:warp_affine_u8x3_band -s 3 -c 1 -f -o $out/${tag}_warp $CMD > $out/${tag}_ncu3.log 2>&1
   echo "ncu warp exit $?"
 fi
