@@ -24,3 +24,6 @@ PY
 }
 run peer "$@"
 run nccl --nccl-gather --no-e2e --no-configs "$@"
+if [ "$UPLOAD_AB" = "1" ]; then   # e2e with the copy-engine upload of the rectangles instead of the fetch kernel
+  run e2e_roi --upload roi --no-configs --no-cpu-baseline "$@"
+fi
