@@ -469,7 +469,22 @@ __device__ __forceinline__ uint32_t warp_pixel3(const uint8_t* __restrict__ img,
 
 struct NormArgs {
   float mean[3], std[3];
+  // 1 / std and whether x * rcp corrected by one residual step equals the IEEE quotient for
+  // every value this channel can take (checked on the host for all 256: norm_fast_ok)
+  float rcp[3];
+  int32_t fast;
 };
+
+// (pixel - mean) / std, correctly rounded: the division itself, or -- when the host has
+// verified it for all 256 pixel values of the channel -- q0 = x * (1 / std) plus one exact
+// residual step (three instructions instead of the nine of an IEEE division).
+__device__ __forceinline__ float norm_value(uint32_t px, float mean, float std, float rcp,
+                                            bool fast) {
+  const float x = __fsub_rn((float)px, mean);
+  if (!fast) return __fdiv_rn(x, std);
+  const float q0 = __fmul_rn(x, rcp);
+  return __fmaf_rn(__fmaf_rn(-q0, std, x), rcp, q0);
+}
 
 // NORM = false: uint8 HWC crops; dst_w % 16 == 0 and dst 16-byte aligned, so every warp's
 //   32 quads are 384 contiguous, 16-byte aligned output bytes.
@@ -740,13 +755,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // 48 registers: 6 CTAs of 192 threads per SM, as many as a 36 KB band allows.
 // todo: [0] = number of entries, [1 ...] = the 16-row tiles (crop * tiles16 + tile) this kernel
 // leaves to the quad kernel.
+// NORM: the float32 CHW variant (row N2, see the quad kernel): (pixel - mean[c]) / std[c] to
+// three planes, a warp's 32 pixels of a row as one 128-byte store per channel.
+template <bool NORM>
 __global__ void __maxnreg__(48)
     warp_affine_u8x3_band_kernel(const uint8_t* __restrict__ src,
                                  const int64_t* __restrict__ src_off,
                                  const int32_t* __restrict__ src_hw,
-                                 const double* __restrict__ inv, uint8_t* __restrict__ dst,
+                                 const double* __restrict__ inv, void* __restrict__ dst_any,
                                  int dst_w, int dst_h, int tile_rows, int tiles_per_crop,
-                                 int* __restrict__ todo) {
+                                 int* __restrict__ todo, const NormArgs norm) {
+  uint8_t* const dst = static_cast<uint8_t*>(dst_any);
   extern __shared__ __align__(128) uint8_t s_band[];  // kBandBytes
   __shared__ int s_x0[kBandMaxTileRows];
   __shared__ int s_y0[kBandMaxTileRows];
@@ -837,6 +856,9 @@ __global__ void __maxnreg__(48)
   uint8_t* out = dst + ((size_t)crop * dst_h + row0) * dst_w * 3 + (size_t)(tid >> 5) * 96 +
                  (size_t)(((lane >> 2) * 3 + k4) << 2);
   const uint32_t out_pitch = (uint32_t)dst_w * 3u;
+  // NORM: this column of channel 0's plane; the planes are dst_h * dst_w floats apart
+  float* fout = static_cast<float*>(dst_any) + ((size_t)crop * 3 * dst_h + row0) * dst_w + tid;
+  const size_t fplane = (size_t)dst_h * dst_w;
   const uint32_t row_tab = smem_u32(s_row);
   // fixed-point source rows per output row, for the pass planner (an estimate: the planner
   // checks the rows it picks)
@@ -928,6 +950,17 @@ __global__ void __maxnreg__(48)
         const uint32_t c0 = __dp2a_lo(wu, brg, __dp2a_lo(wt, arg, 512u)) >> 10;
         const uint32_t c1 = __dp2a_hi(wu, brg, __dp2a_hi(wt, arg, 512u)) >> 10;
         const uint32_t c2 = __dp2a_lo(wu, bbb, __dp2a_lo(wt, abb, 512u)) >> 10;
+        if (NORM) {
+          float* f = fout + (size_t)(cur.r_begin + i) * dst_w;
+          const bool fast = norm.fast != 0;  // uniform
+          const float v0 = norm_value(c0, norm.mean[0], norm.std[0], norm.rcp[0], fast);
+          const float v1 = norm_value(c1, norm.mean[1], norm.std[1], norm.rcp[1], fast);
+          const float v2 = norm_value(c2, norm.mean[2], norm.std[2], norm.rcp[2], fast);
+          asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(f), "f"(v0) : "memory");
+          asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(f + fplane), "f"(v1) : "memory");
+          asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(f + 2 * fplane), "f"(v2) : "memory");
+          continue;
+        }
         const uint32_t px = __byte_perm(__byte_perm(c0, c1, 0x0040), c2, 0x5410);
         const uint32_t nxt_px = __shfl_down_sync(0xffffffffu, px, 1);
         if (k4 < 3) {
@@ -949,20 +982,22 @@ __global__ void __maxnreg__(48)
 
 // The tiles the band kernel left: the quad kernel over a list, with a fixed grid (the list is
 // empty on the evaluation path, and the launch then costs a few microseconds).
+template <bool NORM>
 __global__ void __launch_bounds__(kWarpThreads)
     warp_affine_u8x3_list_kernel(const uint8_t* __restrict__ src,
                                  const int64_t* __restrict__ src_off,
                                  const int32_t* __restrict__ src_hw,
                                  const double* __restrict__ inv, void* __restrict__ dst, int dst_w,
-                                 int dst_h, FastDiv div_wq, const int* __restrict__ todo) {
+                                 int dst_h, FastDiv div_wq, const int* __restrict__ todo,
+                                 const NormArgs norm) {
   __shared__ __align__(16) QuadSmem sm;
   const int count = todo[0];
   const int tiles16 = (dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
   for (int i = blockIdx.x; i < count; i += gridDim.x) {
     const int t = todo[1 + i];
     const int crop = t / tiles16;
-    warp3_quad_tile<false, true>(sm, src, src_off, src_hw, inv, dst, dst_w, dst_h, crop,
-                                 t - crop * tiles16, div_wq, NormArgs());
+    warp3_quad_tile<NORM, !NORM>(sm, src, src_off, src_hw, inv, dst, dst_w, dst_h, crop,
+                                 t - crop * tiles16, div_wq, norm);
     __syncthreads();  // the tile's tables are rebuilt for the next one
   }
 }
@@ -1041,6 +1076,76 @@ extern "C" int pc_affine_joints(float* d_keypoints, const double* d_fwd, int32_t
   return PC_OK;
 }
 
+// Does q0 = x * (1 / std) corrected by one residual step give the IEEE quotient x / std for all
+// 256 pixel values of every channel?  (It does for the ImageNet statistics; any other mean /
+// std is checked the same way and falls back to the division when one value differs.)
+static bool norm_fast_ok(NormArgs* na) {
+  bool ok = true;
+  for (int c = 0; c < 3; ++c) {
+    const float std = na->std[c], mean = na->mean[c];
+    const float rcp = 1.0f / std;
+    na->rcp[c] = rcp;
+    for (int v = 0; v < 256 && ok; ++v) {
+      const float x = (float)v - mean;
+      const float q0 = x * rcp;
+      const float q = fmaf(fmaf(-q0, std, x), rcp, q0);
+      const float want = x / std;
+      ok = memcmp(&q, &want, sizeof(float)) == 0;
+    }
+  }
+  return ok;
+}
+
+// The band kernel takes 3-channel crops of a width that is a multiple of 32 (one thread per
+// output column, whole warps) up to 512.
+static bool band_path_takes(int dst_w, int dst_h, int64_t n) {
+  const int tiles16 = (dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
+  return dst_w % 32 == 0 && dst_w <= kBandMaxThreads && n * (int64_t)tiles16 < 0x3fffffffLL;
+}
+
+// Rotation-free tiles out of a shared-memory band; tiles that do not qualify are listed in
+// stream-ordered scratch (the library's own pool) and done by the quad kernel right after.
+template <bool NORM>
+static int launch_band_path(const uint8_t* d_src, const int64_t* d_src_offset,
+                            const int32_t* d_src_hw, const double* d_inv, void* d_dst, int dst_w,
+                            int dst_h, int64_t n, const NormArgs& na, cudaStream_t st) {
+  const int tiles16 = (dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
+  // rows per CTA: per-CTA set-up (matrix, column constants) is paid once per tile, so tiles
+  // are as tall as still leaves every SM a few rounds of CTAs
+  int tile_rows = kBandMaxTileRows;
+  const int64_t want = (int64_t)sm_count_cached() * 6 * 3;  // three rounds of CTAs
+  while (tile_rows > kWarp3TileRows && n * ((dst_h + tile_rows - 1) / tile_rows) < want)
+    tile_rows >>= 1;
+  const int tiles_b = (dst_h + tile_rows - 1) / tile_rows;
+  cudaMemPool_t pool;
+  PC_CUDA(scratch_pool(&pool));
+  int* todo = nullptr;
+  PC_CUDA(cudaMallocFromPoolAsync((void**)&todo, sizeof(int) * (size_t)(1 + n * tiles16), pool, st));
+  cudaError_t le = cudaMemsetAsync(todo, 0, sizeof(int), st);
+  if (le == cudaSuccess) {
+    warp_affine_u8x3_band_kernel<NORM><<<(unsigned)(n * tiles_b), dst_w, kBandBytes, st>>>(
+        d_src, d_src_offset, d_src_hw, d_inv, d_dst, dst_w, dst_h, tile_rows, tiles_b, todo, na);
+    le = cudaGetLastError();
+  }
+  if (le == cudaSuccess) {
+    int64_t lgrid = (int64_t)sm_count_cached() * 4;  // 64 registers x 256 threads: 4 CTAs per SM
+    // (capped at 48 registers for 5 CTAs per SM: rotated crops 1.52 instead of 1.49 ms)
+    if (lgrid > n * tiles16) lgrid = n * tiles16;
+    // (A programmatic dependent launch would hide this launch under the band kernel's tail --
+    // 3 us on the evaluation path -- but the quad path lives on L1 hits, and CTAs that become
+    // resident next to six 36 KB bands run with the SM's shared-memory carve-out: rotated
+    // crops 3.45 ms instead of 1.48, measured.)
+    warp_affine_u8x3_list_kernel<NORM><<<(unsigned)lgrid, kWarpThreads, 0, st>>>(
+        d_src, d_src_offset, d_src_hw, d_inv, d_dst, dst_w, dst_h,
+        make_fastdiv((uint32_t)(dst_w >> 2)), todo, na);
+    le = cudaGetLastError();
+  }
+  const cudaError_t fe = cudaFreeAsync(todo, st);  // on every path
+  PC_CUDA(le);
+  PC_CUDA(fe);
+  return PC_OK;
+}
+
 extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offset,
                                  const int32_t* d_src_hw, const double* d_inv, uint8_t* d_dst,
                                  const pc_warp_params* p, int64_t n, void* stream) {
@@ -1059,48 +1164,9 @@ extern "C" int pc_warp_affine_u8(const uint8_t* d_src, const int64_t* d_src_offs
     const int tiles3 = (p->dst_h + kWarp3TileRows - 1) / kWarp3TileRows;
     const int64_t grid3 = n * tiles3;
     PC_REQUIRE(grid3 < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_warp_affine_u8: batch too large");
-    if (p->dst_w % 32 == 0 && p->dst_w <= kBandMaxThreads && n * (int64_t)tiles3 < 0x3fffffffLL) {
-      // One thread per output column; rotation-free tiles out of a shared-memory band.  Tiles
-      // that do not qualify are listed in stream-ordered scratch (the library's own pool) and
-      // done by the quad kernel right after.
-      // rows per CTA: per-CTA set-up (matrix, column constants) is paid once per tile, so
-      // tiles are as tall as still leaves every SM a few rounds of CTAs
-      int tile_rows = kBandMaxTileRows;
-      const int64_t want = (int64_t)sm_count_cached() * 6 * 3;  // three rounds of CTAs
-      while (tile_rows > kWarp3TileRows &&
-             n * ((p->dst_h + tile_rows - 1) / tile_rows) < want)
-        tile_rows >>= 1;
-      const int tiles_b = (p->dst_h + tile_rows - 1) / tile_rows;
-      cudaMemPool_t pool;
-      PC_CUDA(scratch_pool(&pool));
-      int* todo = nullptr;
-      PC_CUDA(cudaMallocFromPoolAsync((void**)&todo, sizeof(int) * (size_t)(1 + n * tiles3), pool,
-                                      st));
-      cudaError_t le = cudaMemsetAsync(todo, 0, sizeof(int), st);
-      if (le == cudaSuccess) {
-        warp_affine_u8x3_band_kernel<<<(unsigned)(n * tiles_b), p->dst_w, kBandBytes, st>>>(
-            d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tile_rows, tiles_b,
-            todo);
-        le = cudaGetLastError();
-      }
-      if (le == cudaSuccess) {
-        int64_t lgrid = (int64_t)sm_count_cached() * 4;  // 64 registers x 256 threads: 4 CTAs per SM
-        // (capped at 48 registers for 5 CTAs per SM: rotated crops 1.52 instead of 1.49 ms)
-        if (lgrid > n * tiles3) lgrid = n * tiles3;
-        // (A programmatic dependent launch would hide this launch under the band kernel's tail
-        // -- 3 us on the evaluation path -- but the quad path lives on L1 hits, and CTAs that
-        // become resident next to six 36 KB bands run with the SM's shared-memory carve-out:
-        // rotated crops 3.45 ms instead of 1.48, measured.)
-        warp_affine_u8x3_list_kernel<<<(unsigned)lgrid, kWarpThreads, 0, st>>>(
-            d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h,
-            make_fastdiv((uint32_t)(p->dst_w >> 2)), todo);
-        le = cudaGetLastError();
-      }
-      const cudaError_t fe = cudaFreeAsync(todo, st);  // on every path
-      PC_CUDA(le);
-      PC_CUDA(fe);
-      return PC_OK;
-    }
+    if (band_path_takes(p->dst_w, p->dst_h, n))
+      return launch_band_path<false>(d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w,
+                                     p->dst_h, n, NormArgs(), st);
     warp_affine_u8x3_kernel<false, true><<<(unsigned)grid3, kWarpThreads, 0, st>>>(
         d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3,
         make_fastdiv((uint32_t)(p->dst_w >> 2)), NormArgs());
@@ -1155,6 +1221,10 @@ extern "C" int pc_warp_affine_u8_norm_chw(const uint8_t* d_src, const int64_t* d
     na.mean[c] = p->mean[c];
     na.std[c] = p->std[c];
   }
+  na.fast = norm_fast_ok(&na) ? 1 : 0;
+  if (band_path_takes(p->dst_w, p->dst_h, n))
+    return launch_band_path<true>(d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h,
+                                  n, na, (cudaStream_t)stream);
   warp_affine_u8x3_kernel<true, false><<<(unsigned)grid3, kWarpThreads, 0, (cudaStream_t)stream>>>(
       d_src, d_src_offset, d_src_hw, d_inv, d_dst, p->dst_w, p->dst_h, tiles3,
       make_fastdiv((uint32_t)(p->dst_w >> 2)), na);

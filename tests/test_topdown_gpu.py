@@ -632,6 +632,15 @@ def test_warp_fused_normalize_chw(cuda_device):
     for i in range(n):
         want = warp.normalize_chw(crops_u8[i].cpu().numpy(), m255, s255)
         assert np.array_equal(fused[i].cpu().numpy(), want), i
+    # other statistics (the library checks on the host, for all 256 pixel values of a channel,
+    # whether its 3-instruction quotient equals the IEEE division, and divides otherwise)
+    for mean2, std2 in (([0.3, 0.1, 0.7], [0.11, 0.37, 0.013]), ([0.0, 0.5, 1.0], [1.0, 0.333, 3.0])):
+        m2, s2 = (np.array(mean2) * 255.0).tolist(), (np.array(std2) * 255.0).tolist()
+        fused2, _ = at.affine_batch(_t(images, dev), c, s, rot, normalize_mean=mean2,
+                                    normalize_std=std2)
+        for i in range(n):
+            want = warp.normalize_chw(crops_u8[i].cpu().numpy(), m2, s2)
+            assert np.array_equal(fused2[i].cpu().numpy(), want), (mean2, i)
     with pytest.raises(ValueError):
         codec.warp_affine_normalized(_t(images, dev), torch.zeros(n, device=dev),
                                      torch.zeros(n, 2, device=dev), torch.zeros(n, 2, 3, device=dev),
