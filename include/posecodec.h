@@ -47,7 +47,8 @@ typedef enum pc_status {
 
 #define PC_MAX_JOINTS 64
 #define PC_MAX_DARK_KERNEL 17 /* kernel_size <= 17 (sigma = 3 recipe) */
-#define PC_MAX_GROUPS 128     /* people per image the grouping kernel can hold */
+#define PC_MAX_GROUPS 128     /* default people-per-image capacity of the grouping kernels
+                               * (pc_group_params.max_groups raises it) */
 #define PC_MAX_SCALES 4       /* heat-map resolutions of the bottom-up target encoder */
 #define PC_NMS_MAX_PEOPLE 1024 /* people per image pc_oks_nms can hold */
 
@@ -242,34 +243,40 @@ int pc_bottomup_decode_stats(int64_t* exact_pass_planes, int reset);
  * mindpose/utils/match.py:14-116, engine/inferencer/bottomup_inferencer.py:
  * 153-156 and data/transform/utils.py:235-274.
  * d_val_k [N,K,M], d_tag_k [N,K,M,1], d_ind_k [N,K,M,2] ->
- * d_ans f32 [N, PC_MAX_GROUPS, K, 4] (x, y, val, tag; insertion order),
- * d_num_groups i32 [N], d_scores f32 [N, PC_MAX_GROUPS].
- * d_num_groups[i] = -1 flags an image whose group count exceeded PC_MAX_GROUPS. */
+ * d_ans f32 [N, G, K, 4] (x, y, val, tag; insertion order), d_num_groups i32 [N],
+ * d_scores f32 [N, G], with G = max_groups (0 = PC_MAX_GROUPS) the people an image can hold.
+ * The reference is unbounded (match.py:63-113); at most num_joints * max_num groups can form
+ * (every detection its own), so max_groups = num_joints * max_num never overflows (510 for
+ * the HigherHRNet recipe; the shared memory of the kernel bounds G at about 900 for K = 17).
+ * d_num_groups[i] = -1 flags an image whose group count exceeded G: call again with more. */
 typedef struct pc_group_params {
   int32_t num_joints, max_num;
   float vis_thr, tag_thr;
   int32_t ignore_too_much, use_rounded_norm;
   int32_t joint_order[PC_MAX_JOINTS];
+  int32_t max_groups; /* G; 0 = PC_MAX_GROUPS */
 } pc_group_params;
 int pc_group_by_tag(const float* d_val_k, const float* d_tag_k, const float* d_ind_k,
                     float* d_ans, int32_t* d_num_groups, float* d_scores,
                     const pc_group_params* params, int64_t n, void* stream);
-/* Back-projection of grouped people, in place on d_ans (utils.py:235-274).
- * d_center, d_scale f64 [N,2]; d_heatmap_wh f64 [N,2] (= image_shape / downsample_scale). */
+/* Back-projection of grouped people, in place on d_ans f32 [N, G, K, 4] (utils.py:235-274).
+ * d_center, d_scale f64 [N,2]; d_heatmap_wh f64 [N,2] (= image_shape / downsample_scale);
+ * max_groups = G as in pc_group_params (0 = PC_MAX_GROUPS). */
 int pc_transform_keypoints(float* d_ans, const int32_t* d_num_groups, const double* d_center,
                            const double* d_scale, const double* d_heatmap_wh, float pixel_std,
-                           int32_t num_joints, int64_t n, void* stream);
+                           int32_t num_joints, int32_t max_groups, int64_t n, void* stream);
 
 /* ---- N3: BottomUpHeatMapAEInferencer._refine_missing --------------------
  * mindpose/engine/inferencer/bottomup_inferencer.py:189-249, for every person of
  * every image.  Runs on the grouped people in heat-map coordinates, i.e. after
  * pc_group_by_tag and before pc_transform_keypoints (bottomup_inferencer.py:158-166).
  * d_heatmap f32 [N,K,H,W] and d_tagging f32 [N,K,H,W,1] are the heatmap_raw /
- * tagging_heatmap outputs of pc_bottomup_decode; d_ans f32 [N, PC_MAX_GROUPS, K, 4]
+ * tagging_heatmap outputs of pc_bottomup_decode; d_ans f32 [N, G, K, 4]
  * is updated in place (x, y, val of joints with val == 0); d_mean_tag f32
- * [N, PC_MAX_GROUPS] is caller-provided scratch. */
+ * [N, G] is caller-provided scratch; G = max_groups (0 = PC_MAX_GROUPS). */
 typedef struct pc_refine_params {
   int32_t num_joints, height, width;
+  int32_t max_groups;
 } pc_refine_params;
 int pc_refine_missing(const float* d_heatmap, const float* d_tagging, float* d_ans,
                       const int32_t* d_num_groups, float* d_mean_tag,

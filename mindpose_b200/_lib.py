@@ -132,6 +132,7 @@ class GroupParams(Structure):
         ("ignore_too_much", c_int32),
         ("use_rounded_norm", c_int32),
         ("joint_order", c_int32 * PC_MAX_JOINTS),
+        ("max_groups", c_int32),
     ]
 
 
@@ -149,7 +150,8 @@ class BottomUpEncodeParams(Structure):
 
 
 class RefineParams(Structure):
-    _fields_ = [("num_joints", c_int32), ("height", c_int32), ("width", c_int32)]
+    _fields_ = [("num_joints", c_int32), ("height", c_int32), ("width", c_int32),
+                ("max_groups", c_int32)]
 
 
 class OksNmsParams(Structure):
@@ -228,7 +230,7 @@ SIGNATURES = {
     "pc_group_by_tag": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(GroupParams), c_int64, _P]),
     "pc_transform_keypoints": (
         c_int,
-        [_P, _P, _P, _P, _P, c_float, c_int32, c_int64, _P],
+        [_P, _P, _P, _P, _P, c_float, c_int32, c_int32, c_int64, _P],
     ),
     "pc_refine_missing": (c_int, [_P, _P, _P, _P, _P, POINTER(RefineParams), c_int64, _P]),
     "pc_oks_nms": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(OksNmsParams), c_int64, _P]),

@@ -107,12 +107,14 @@ def decode_stats(reset: bool = False) -> int:
 
 def group_by_tag(val_k: torch.Tensor, tag_k: torch.Tensor, ind_k: torch.Tensor,
                  joint_order: Sequence[int], vis_thr: float = 0.1, tag_thr: float = 1.0,
-                 ignore_too_much: bool = False, use_rounded_norm: bool = True):
+                 ignore_too_much: bool = False, use_rounded_norm: bool = True,
+                 max_groups: Optional[int] = None):
     """Batched ``match_by_tag`` + instance score.
 
-    -> (ans f32 [N, PC_MAX_GROUPS, K, 4], num_groups i32 [N], scores f32 [N, PC_MAX_GROUPS]);
-    image i has ``num_groups[i]`` people in ``ans[i, :num_groups[i]]`` (insertion order);
-    -1 flags more people than PC_MAX_GROUPS."""
+    -> (ans f32 [N, G, K, 4], num_groups i32 [N], scores f32 [N, G]) with G = ``max_groups``
+    (default PC_MAX_GROUPS = 128); image i has ``num_groups[i]`` people in
+    ``ans[i, :num_groups[i]]`` (insertion order); -1 flags more people than G.  The reference
+    is unbounded; ``max_groups = K * M`` (every detection its own group) can never overflow."""
     for t in (val_k, tag_k, ind_k):
         if not (t.is_cuda and t.dtype == torch.float32):
             raise ValueError("val_k / tag_k / ind_k must be float32 CUDA tensors")
@@ -121,7 +123,9 @@ def group_by_tag(val_k: torch.Tensor, tag_k: torch.Tensor, ind_k: torch.Tensor,
         raise ValueError("the CUDA grouping supports one tag channel (tag_k [N,K,M,1])")
     val_k, tag_k, ind_k = val_k.contiguous(), tag_k.contiguous(), ind_k.contiguous()
     dev = val_k.device
-    g = _lib.PC_MAX_GROUPS
+    g = _lib.PC_MAX_GROUPS if max_groups is None else int(max_groups)
+    if g < 1:
+        raise ValueError("`max_groups` must be >= 1")
     ans = torch.empty((n, g, k, 4), dtype=torch.float32, device=dev)
     num = torch.empty((n,), dtype=torch.int32, device=dev)
     scores = torch.zeros((n, g), dtype=torch.float32, device=dev)
@@ -129,6 +133,7 @@ def group_by_tag(val_k: torch.Tensor, tag_k: torch.Tensor, ind_k: torch.Tensor,
     p.num_joints, p.max_num = k, m
     p.vis_thr, p.tag_thr = float(vis_thr), float(tag_thr)
     p.ignore_too_much, p.use_rounded_norm = int(bool(ignore_too_much)), int(bool(use_rounded_norm))
+    p.max_groups = g
     order = list(joint_order)
     if len(order) != k:
         raise ValueError("`joint_order` must list every joint once")
@@ -151,12 +156,12 @@ def transform_keypoints(ans: torch.Tensor, num_groups: torch.Tensor, center, sca
         return torch.as_tensor(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x),
                                dtype=torch.float64).reshape(-1, 2).to(dev).contiguous()
 
-    n, _, k, _ = ans.shape
+    n, g, k, _ = ans.shape
     c, s, hw = f64(center), f64(scale), f64(heatmap_wh)
     with torch.cuda.device(dev):
         _lib.call("pc_transform_keypoints", _lib.device_ptr(ans), _lib.device_ptr(num_groups),
                   _lib.device_ptr(c), _lib.device_ptr(s), _lib.device_ptr(hw), float(pixel_std),
-                  k, n, _lib.current_stream())
+                  k, g, n, _lib.current_stream())
     return ans
 
 
@@ -199,7 +204,7 @@ def encode_targets(keypoints: torch.Tensor, heatmap_sizes, sigma: float = 2.0, m
 def refine_missing(heatmap: torch.Tensor, tagging_heatmap: torch.Tensor, ans: torch.Tensor,
                    num_groups: torch.Tensor) -> torch.Tensor:
     """Batched ``_refine_missing`` (bottomup_inferencer.py:189-249), in place on ``ans``
-    [N, PC_MAX_GROUPS, K, 4] (heat-map coordinates).  heatmap [N,K,H,W] / tagging_heatmap
+    [N, G, K, 4] (heat-map coordinates; G as ``group_by_tag`` made it).  heatmap [N,K,H,W] / tagging_heatmap
     [N,K,H,W,1] are the decoder's ``heatmap_raw`` / ``tagging_heatmap`` outputs."""
     for t in (heatmap, tagging_heatmap, ans):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
@@ -207,11 +212,12 @@ def refine_missing(heatmap: torch.Tensor, tagging_heatmap: torch.Tensor, ans: to
     n, k, h, w = heatmap.shape
     if tagging_heatmap.shape != (n, k, h, w, 1):
         raise ValueError("the CUDA refinement supports one tag channel (tagging_heatmap [N,K,H,W,1])")
-    if ans.shape != (n, _lib.PC_MAX_GROUPS, k, 4):
-        raise ValueError("`ans` must be the [N, PC_MAX_GROUPS, K, 4] output of group_by_tag")
+    if ans.dim() != 4 or ans.shape[0] != n or ans.shape[2:] != (k, 4):
+        raise ValueError("`ans` must be the [N, G, K, 4] output of group_by_tag")
+    g = ans.shape[1]
     num_groups = num_groups.to(torch.int32).contiguous()
-    scratch = torch.empty((n, _lib.PC_MAX_GROUPS), dtype=torch.float32, device=ans.device)
-    p = _lib.RefineParams(k, h, w)
+    scratch = torch.empty((n, g), dtype=torch.float32, device=ans.device)
+    p = _lib.RefineParams(k, h, w, g)
     with torch.cuda.device(ans.device):
         _lib.call("pc_refine_missing", _lib.device_ptr(heatmap), _lib.device_ptr(tagging_heatmap),
                   _lib.device_ptr(ans), _lib.device_ptr(num_groups), _lib.device_ptr(scratch),

@@ -19,7 +19,7 @@
 
 namespace pc {
 
-constexpr int kG = PC_MAX_GROUPS;
+// (the group capacity G of an image is a run-time argument: pc_group_params.max_groups)
 constexpr int kMaxDet = 32;
 
 struct GroupArgs {
@@ -30,6 +30,7 @@ struct GroupArgs {
   int32_t* num_groups;
   float* scores;
   int32_t K, M;
+  int32_t G;  // people an image can hold (capacity of ans / scores per image)
   float vis_thr, tag_thr;
   int32_t ignore_too_much, use_rounded_norm;
 };
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(32)
     group_by_tag_kernel(const GroupArgs a, const __grid_constant__ GroupTables tab) {
   extern __shared__ __align__(16) unsigned char g_smem[];
   const int lane = threadIdx.x;
-  const int K = a.K, M = a.M;
+  const int K = a.K, M = a.M, kG = a.G;
   // ---- shared-memory carve-up
   double* s_v = reinterpret_cast<double*>(g_smem);
   double* s_short = s_v + kG;
@@ -337,7 +338,7 @@ __global__ void transform_keypoints_kernel(float* __restrict__ ans,
                                            const double* __restrict__ center,
                                            const double* __restrict__ scale,
                                            const double* __restrict__ hm_wh, double pixel_std,
-                                           int K) {
+                                           int K, int kG) {
   const int64_t img = blockIdx.x;
   const int p = num_groups[img];
   if (p <= 0) return;
@@ -369,6 +370,7 @@ extern "C" int pc_group_by_tag(const float* d_val_k, const float* d_tag_k, const
              "pc_group_by_tag: num_joints %d outside [1, %d]", p->num_joints, PC_MAX_JOINTS);
   PC_REQUIRE(p->max_num >= 1 && p->max_num <= kMaxDet, PC_ERR_UNSUPPORTED,
              "pc_group_by_tag: max_num %d outside [1, %d]", p->max_num, kMaxDet);
+  PC_REQUIRE(p->max_groups >= 0, PC_ERR_INVALID_ARGUMENT, "pc_group_by_tag: max_groups < 0");
   GroupTables tab;
   memset(&tab, 0, sizeof(tab));
   uint64_t seen = 0;
@@ -396,9 +398,13 @@ extern "C" int pc_group_by_tag(const float* d_val_k, const float* d_tag_k, const
   a.tag_thr = p->tag_thr;
   a.ignore_too_much = p->ignore_too_much;
   a.use_rounded_norm = p->use_rounded_norm;
+  const int kG = p->max_groups > 0 ? p->max_groups : PC_MAX_GROUPS;
+  a.G = kG;
   const size_t smem = sizeof(double) * (2 * kG + kMaxDet) +
                       sizeof(float) * (2 * kG + kMaxDet * kG + (size_t)kG * a.K + 4 * kMaxDet) +
                       sizeof(int) * (5 * kG + 2 * kMaxDet);
+  PC_REQUIRE(smem <= 227 * 1024, PC_ERR_UNSUPPORTED,
+             "pc_group_by_tag: max_groups %d needs %zu bytes of shared memory (> 227 KB)", kG, smem);
   if (smem > 48 * 1024)
     PC_CUDA(cudaFuncSetAttribute(group_by_tag_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -410,14 +416,16 @@ extern "C" int pc_group_by_tag(const float* d_val_k, const float* d_tag_k, const
 extern "C" int pc_transform_keypoints(float* d_ans, const int32_t* d_num_groups,
                                       const double* d_center, const double* d_scale,
                                       const double* d_heatmap_wh, float pixel_std,
-                                      int32_t num_joints, int64_t n, void* stream) {
-  PC_REQUIRE(n >= 0 && num_joints >= 1 && num_joints <= PC_MAX_JOINTS, PC_ERR_INVALID_ARGUMENT,
-             "pc_transform_keypoints: bad n / num_joints");
+                                      int32_t num_joints, int32_t max_groups, int64_t n,
+                                      void* stream) {
+  PC_REQUIRE(n >= 0 && num_joints >= 1 && num_joints <= PC_MAX_JOINTS && max_groups >= 0,
+             PC_ERR_INVALID_ARGUMENT, "pc_transform_keypoints: bad n / num_joints / max_groups");
   if (n == 0) return PC_OK;
   PC_REQUIRE(d_ans && d_num_groups && d_center && d_scale && d_heatmap_wh,
              PC_ERR_INVALID_ARGUMENT, "pc_transform_keypoints: NULL tensor pointer");
   transform_keypoints_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(
-      d_ans, d_num_groups, d_center, d_scale, d_heatmap_wh, (double)pixel_std, num_joints);
+      d_ans, d_num_groups, d_center, d_scale, d_heatmap_wh, (double)pixel_std, num_joints,
+      max_groups > 0 ? max_groups : PC_MAX_GROUPS);
   PC_CUDA(cudaGetLastError());
   return PC_OK;
 }

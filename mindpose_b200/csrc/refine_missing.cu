@@ -41,11 +41,11 @@ __device__ float np_sum_f32_local(const float* a, int n) {
 __global__ void refine_mean_tag_kernel(const float* __restrict__ tagging,
                                        const float* __restrict__ ans,
                                        const int32_t* __restrict__ num_groups,
-                                       float* __restrict__ mean_tag, int K, int H, int W) {
-  const int n = blockIdx.x, p = threadIdx.x;
+                                       float* __restrict__ mean_tag, int K, int H, int W, int G) {
+  const int n = blockIdx.x, p = blockIdx.y * blockDim.x + threadIdx.x;
   const int np_ = num_groups[n];
-  if (p >= np_ || p >= PC_MAX_GROUPS) return;
-  const float* person = ans + ((size_t)n * PC_MAX_GROUPS + p) * K * 4;
+  if (p >= np_ || p >= G) return;
+  const float* person = ans + ((size_t)n * G + p) * K * 4;
   float tags[PC_MAX_JOINTS];
   int nv = 0;
   for (int k = 0; k < K; ++k) {
@@ -57,7 +57,7 @@ __global__ void refine_mean_tag_kernel(const float* __restrict__ tagging,
       tags[nv++] = __ldg(tagging + (((size_t)n * K + k) * H + y) * W + x);
     }
   }
-  mean_tag[(size_t)n * PC_MAX_GROUPS + p] = __fdiv_rn(np_sum_f32_local(tags, nv), (float)nv);
+  mean_tag[(size_t)n * G + p] = __fdiv_rn(np_sum_f32_local(tags, nv), (float)nv);
 }
 
 __device__ __forceinline__ void score_px(float heat, float tag, int idx, const float (&mt)[kRefChunk],
@@ -83,14 +83,15 @@ __device__ __forceinline__ void score_px(float heat, float tag, int idx, const f
 __global__ void __launch_bounds__(kRefThreads)
     refine_missing_kernel(const float* __restrict__ heatmap, const float* __restrict__ tagging,
                           float* __restrict__ ans, const int32_t* __restrict__ num_groups,
-                          const float* __restrict__ mean_tag, int K, int H, int W, int vec_ok) {
+                          const float* __restrict__ mean_tag, int K, int H, int W, int vec_ok,
+                          int G) {
   __shared__ float s_v[kRefThreads / 32][kRefChunk];
   __shared__ int s_i[kRefThreads / 32][kRefChunk];
   const int n = blockIdx.x / K, k = blockIdx.x - n * K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int np_ = num_groups[n];
   if (np_ <= 0) return;
-  np_ = min(np_, PC_MAX_GROUPS);
+  np_ = min(np_, G);
   const int HW = H * W;
   const float* heat = heatmap + ((size_t)n * K + k) * HW;
   const float* tagp = tagging + ((size_t)n * K + k) * HW;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kRefThreads)
 #pragma unroll
     for (int c = 0; c < kRefChunk; ++c) {
       // people past the end get a NaN mean: never better than -inf
-      mt[c] = p0 + c < np_ ? __ldg(mean_tag + (size_t)n * PC_MAX_GROUPS + p0 + c)
+      mt[c] = p0 + c < np_ ? __ldg(mean_tag + (size_t)n * G + p0 + c)
                            : __int_as_float(0x7fc00000);
       bv[c] = -INFINITY;
       bi[c] = 0x7fffffff;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kRefThreads)
       fx = __fadd_rn(fx, px ? 0.25f : -0.25f);
       fy = __fadd_rn(fy, py ? 0.25f : -0.25f);
       const float val = heat[y * W + x];
-      float* row = ans + (((size_t)n * PC_MAX_GROUPS + p0 + tid) * K + k) * 4;
+      float* row = ans + (((size_t)n * G + p0 + tid) * K + k) * 4;
       if (val > 0.f && row[2] == 0.f) {
         row[0] = fx;
         row[1] = fy;
@@ -177,20 +178,22 @@ extern "C" int pc_refine_missing(const float* d_heatmap, const float* d_tagging,
              "pc_refine_missing: num_joints %d outside [1, %d]", p->num_joints, PC_MAX_JOINTS);
   PC_REQUIRE(p->height >= 1 && p->width >= 1 && (int64_t)p->height * p->width < (1 << 30),
              PC_ERR_INVALID_ARGUMENT, "pc_refine_missing: bad map size");
+  PC_REQUIRE(p->max_groups >= 0, PC_ERR_INVALID_ARGUMENT, "pc_refine_missing: max_groups < 0");
   if (n == 0) return PC_OK;
   PC_REQUIRE(d_heatmap && d_tagging && d_ans && d_num_groups && d_mean_tag,
              PC_ERR_INVALID_ARGUMENT, "pc_refine_missing: NULL tensor pointer");
   PC_REQUIRE(n * p->num_joints < 0x7fffffffLL, PC_ERR_UNSUPPORTED,
              "pc_refine_missing: batch too large");
   cudaStream_t st = (cudaStream_t)stream;
-  refine_mean_tag_kernel<<<(unsigned)n, PC_MAX_GROUPS, 0, st>>>(
-      d_tagging, d_ans, d_num_groups, d_mean_tag, p->num_joints, p->height, p->width);
+  const int G = p->max_groups > 0 ? p->max_groups : PC_MAX_GROUPS;
+  refine_mean_tag_kernel<<<dim3((unsigned)n, (unsigned)((G + 127) / 128)), 128, 0, st>>>(
+      d_tagging, d_ans, d_num_groups, d_mean_tag, p->num_joints, p->height, p->width, G);
   PC_CUDA(cudaGetLastError());
   const int vec_ok = ((int64_t)p->height * p->width) % 4 == 0 &&
                      ((uintptr_t)d_heatmap % 16 == 0) && ((uintptr_t)d_tagging % 16 == 0);
   refine_missing_kernel<<<(unsigned)(n * p->num_joints), kRefThreads, 0, st>>>(
       d_heatmap, d_tagging, d_ans, d_num_groups, d_mean_tag, p->num_joints, p->height, p->width,
-      vec_ok);
+      vec_ok, G);
   PC_CUDA(cudaGetLastError());
   return PC_OK;
 }

@@ -167,10 +167,15 @@ class BottomUpHeatMapAEInferencer(Inferencer):
         cfg = self._inference_cfg
         for data in dataset:
             val_k, tag_k, ind_k, raw, tagging = self.decoder(self.net(data["image"]), data["mask"])
-            ans, num, scores = bottomup.group_by_tag(
-                val_k, tag_k, ind_k, joint_order=cfg["joint_order"], vis_thr=cfg["vis_thr"],
-                tag_thr=cfg["tag_thr"], ignore_too_much=cfg["ignore_too_much"],
-                use_rounded_norm=cfg["use_rounded_norm"])
+            gkw = dict(joint_order=cfg["joint_order"], vis_thr=cfg["vis_thr"],
+                       tag_thr=cfg["tag_thr"], ignore_too_much=cfg["ignore_too_much"],
+                       use_rounded_norm=cfg["use_rounded_norm"])
+            ans, num, scores = bottomup.group_by_tag(val_k, tag_k, ind_k, **gkw)
+            if bool((num < 0).any()):
+                # more than the default 128 people in some image (the reference is unbounded,
+                # match.py:63-113): once more with room for every detection as its own group
+                ans, num, scores = bottomup.group_by_tag(
+                    val_k, tag_k, ind_k, max_groups=val_k.shape[1] * val_k.shape[2], **gkw)
             if cfg["refine_missing_joint"]:  # after the scores, as the reference (:153-166)
                 if raw is None or tagging is None:
                     raise ValueError("refine_missing_joint needs the decoder's heatmap outputs "
@@ -183,8 +188,8 @@ class BottomUpHeatMapAEInferencer(Inferencer):
             ans_h, num_h, scores_h = ans.cpu().numpy(), num.cpu().numpy(), scores.cpu().numpy()
             for i, path in enumerate(data["image_file"]):
                 p = int(num_h[i])
-                if p < 0:
-                    raise RuntimeError("more people than PC_MAX_GROUPS in one image")
+                if p < 0:   # cannot happen with K * M groups of room
+                    raise RuntimeError("group_by_tag overflowed its group capacity")
                 outputs.append(dict(pred=ans_h[i, :p], score=scores_h[i, :p].tolist(),
                                     image_path=path))
         return outputs

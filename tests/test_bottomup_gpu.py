@@ -302,6 +302,41 @@ def test_grouping_empty_and_collisions(cuda_device):
     assert ans[1, 0, 0].tolist() == [3.0, 4.0, np.float32(0.8), 5.0]
 
 
+def test_grouping_more_than_128_people(cuda_device):
+    """The reference's grouping is unbounded (match.py:63-113); here the capacity is a runtime
+    parameter: 128 by default (num_groups = -1 flags the overflow), K * M can never overflow."""
+    k, m = 17, 30
+    rng = np.random.RandomState(5)
+    val = rng.uniform(0.2, 1.0, (2, k, m)).astype(np.float32)
+    ind = rng.randint(0, 128, (2, k, m, 2)).astype(np.float32)
+    tag = np.zeros((2, k, m, 1), np.float32)
+    # image 0: every detection far from every other one -> K * M people of one joint each;
+    # image 1: even and odd joints in two disjoint tag ranges -> 2 * M people
+    tag[0, :, :, 0] = (np.arange(k * m, dtype=np.float32) * 7.0).reshape(k, m)
+    tag[1, :, :, 0] = np.arange(m, dtype=np.float32)[None] * 5.0 + \
+        (np.arange(k)[:, None] % 2) * 1000.0 + rng.uniform(-0.3, 0.3, (k, m))
+    args = [_t(x, cuda_device) for x in (val, tag, ind)]
+    ans, num, _ = bottomup.group_by_tag(*args, synth.COCO_JOINT_ORDER)
+    assert num.tolist() == [-1, 60]
+    ans, num, scores = bottomup.group_by_tag(*args, synth.COCO_JOINT_ORDER, max_groups=k * m)
+    assert ans.shape == (2, k * m, k, 4) and num.tolist() == [k * m, 60]
+    ans, scores = ans.cpu().numpy(), scores.cpu().numpy()
+    for i in range(2):
+        want = grouping.match_by_tag(val[i], tag[i], ind[i], synth.COCO_JOINT_ORDER)
+        assert np.array_equal(ans[i, :want.shape[0]], want), i
+        assert scores[i, :want.shape[0]].tolist() == [float(x) for x in grouping.instance_scores(want)]
+    # back-projection and refinement follow the capacity of `ans`
+    center, scale = np.array([[64.0, 64.0]] * 2), np.array([[1.0, 1.0]] * 2)
+    hw = np.array([[128.0, 128.0]] * 2)
+    dev_ans, dev_num = _t(ans, cuda_device), _t(np.array([k * m, 60], np.int32), cuda_device)
+    want = grouping.transform_keypoints([ans[0], ans[1, :60]], center, scale, hw)
+    bottomup.transform_keypoints(dev_ans, dev_num, center, scale, hw)
+    assert np.array_equal(dev_ans[0].cpu().numpy(), want[0])
+    assert np.array_equal(dev_ans[1, :60].cpu().numpy(), want[1])
+    with pytest.raises(ValueError, match="shared memory"):
+        bottomup.group_by_tag(*args, synth.COCO_JOINT_ORDER, max_groups=2000)
+
+
 def test_transform_keypoints_matches_oracle(cuda_device):
     val, tag, ind = grouping_inputs(7, 6, mode="people")
     ans, num, _ = bottomup.group_by_tag(_t(val, cuda_device), _t(tag, cuda_device),
@@ -352,6 +387,40 @@ def test_bottomup_inferencer_end_to_end(cuda_device, refine):
     for rec, w, sc in zip(records, want, scores):
         assert np.array_equal(rec["pred"], w)
         assert rec["score"] == sc
+
+
+def test_bottomup_inferencer_more_than_128_people(cuda_device):
+    """Tags spread over a wide range: nearly every detection is its own person (> 128); the
+    inferencer groups again with room for K * M people instead of failing."""
+    from oracle import refine_missing as rm
+
+    rng = np.random.RandomState(3)
+    n, k, h = 1, 17, 32
+    out0 = np.concatenate([rng.uniform(0, 1, (n, k, h, h)),
+                           rng.uniform(-500, 500, (n, k, h, h))], 1).astype(np.float32)
+    out1 = rng.uniform(0, 1, (n, k, 2 * h, 2 * h)).astype(np.float32)
+    mask = np.ones((n, 4 * h, 4 * h), np.uint8)
+    dev = cuda_device
+    cfg = dict(has_heatmap_output=True, hflip_tta=False, joint_order=synth.COCO_JOINT_ORDER,
+               vis_thr=0.1, ignore_too_much=False, use_rounded_norm=True, tag_thr=1.0,
+               pixel_std=200.0, downsample_scale=2, refine_missing_joint=True,
+               flip_pairs=synth.COCO_FLIP_PAIRS)
+    dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3)
+    inf = mp.create_inferencer(lambda image: [_t(out0, dev), _t(out1, dev)],
+                               "bottomup_heatmap_ae", config=cfg, decoder=dec)
+    center, scale = np.array([[64.0, 64.0]]), np.array([[0.64, 0.64]])
+    shape = np.array([[128.0, 128.0]])
+    records = inf([dict(image=None, mask=_t(mask, dev), center=center, scale=scale,
+                        image_shape=shape, image_file=["a.jpg"])])
+    val_k, tag_k, ind_k, raw, tagging = bd.decode([out0, out1], mask, use_nms=True, nms_kernel=3,
+                                                  max_num=30)
+    people = grouping.match_by_tag(val_k[0], tag_k[0], ind_k[0], synth.COCO_JOINT_ORDER)
+    assert people.shape[0] > 128
+    scores = [y[:, 2].mean() for y in people]
+    people = np.stack([rm.refine_missing(raw[0], tagging[0], kp) for kp in people])
+    want = grouping.transform_keypoints([people], center, scale, shape / 2, pixel_std=200.0)
+    assert np.array_equal(records[0]["pred"], want[0])
+    assert records[0]["score"] == scores
 
 
 # ------------------------------------------------------------------ N1: bottom-up encode
