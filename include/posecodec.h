@@ -49,6 +49,8 @@ typedef enum pc_status {
 #define PC_MAX_DARK_KERNEL 17 /* kernel_size <= 17 (sigma = 3 recipe) */
 #define PC_MAX_GROUPS 128     /* default people-per-image capacity of the grouping kernels
                                * (pc_group_params.max_groups raises it) */
+#define PC_MAX_DETECTIONS 64  /* max_num of the bottom-up decode / grouping (the reference's
+                               * configs use 30; 33..64 takes the generic decode kernel) */
 #define PC_MAX_SCALES 4       /* heat-map resolutions of the bottom-up target encoder */
 #define PC_NMS_MAX_PEOPLE 1024 /* people per image pc_oks_nms can hold */
 
@@ -223,7 +225,7 @@ typedef struct pc_bottomup_decode_params {
   int32_t h1, w1; /* output / highest-resolution map size */
   int32_t mask_h, mask_w;
   int32_t use_nms, nms_kernel;
-  int32_t max_num;          /* M <= 32 */
+  int32_t max_num;          /* M <= PC_MAX_DETECTIONS (33..64: generic kernel) */
   int32_t shift_coordinate; /* A17, reproduced with the reference's pairing: entry t of the
                              * top M gets the +-0.25 offset of the t-th position in
                              * row-major order (bottom_up_decoder.py:195-201) */

@@ -26,6 +26,7 @@ PC_MAX_JOINTS = 64
 PC_NMS_MAX_PEOPLE = 1024
 PC_MAX_DARK_KERNEL = 17
 PC_MAX_GROUPS = 128
+PC_MAX_DETECTIONS = 64
 PC_MAX_SCALES = 4
 
 PC_OK = 0

@@ -105,6 +105,15 @@ def decode_stats(reset: bool = False) -> int:
     return int(v.value)
 
 
+def max_group_capacity(num_joints: int, max_num: int) -> int:
+    """The largest ``max_groups`` ``group_by_tag`` accepts: what 227 KB of shared memory holds
+    (csrc/grouping.cu: 44 + 4 * (D + K) bytes per group, D = 32 or 64 detections per joint),
+    and never more than K * max_num -- every detection a person of its own."""
+    d = 32 if max_num <= 32 else 64
+    room = (227 * 1024 - 32 * d) // (44 + 4 * (d + num_joints))
+    return min(num_joints * max_num, room)
+
+
 def group_by_tag(val_k: torch.Tensor, tag_k: torch.Tensor, ind_k: torch.Tensor,
                  joint_order: Sequence[int], vis_thr: float = 0.1, tag_thr: float = 1.0,
                  ignore_too_much: bool = False, use_rounded_norm: bool = True,

@@ -114,9 +114,9 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
     s_full = 0;
     s_ncand = 0;
   }
-  // top-M list: lane i of warp 0 holds rank i
-  float top_v = -INFINITY;
-  int top_i = 0x7fffffff;
+  // top-M list (M <= 64): lane i of warp 0 holds ranks i and i + 32
+  float top_v[2] = {-INFINITY, -INFINITY};
+  int top_i[2] = {0x7fffffff, 0x7fffffff};
   int top_count = 0;
 
   const int lo = a.use_nms ? (a.nms_k - 1) / 2 : 0;
@@ -225,22 +225,32 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
       for (int c = 0; c < nc; ++c) {
         const float v = s_cval[c];
         const int idx = s_cidx[c];
-        const bool mine_beats = lane < top_count && beats(top_v, top_i, v, idx);
-        const int p = __popc(__ballot_sync(0xffffffffu, mine_beats));
+        const bool b0 = lane < top_count && beats(top_v[0], top_i[0], v, idx);
+        const bool b1 = lane + 32 < top_count && beats(top_v[1], top_i[1], v, idx);
+        const int p = __popc(__ballot_sync(0xffffffffu, b0)) + __popc(__ballot_sync(0xffffffffu, b1));
         if (p < M) {
-          const float uv = __shfl_up_sync(0xffffffffu, top_v, 1);
-          const int ui = __shfl_up_sync(0xffffffffu, top_i, 1);
-          if (lane > p) {
-            top_v = uv;
-            top_i = ui;
-          } else if (lane == p) {
-            top_v = v;
-            top_i = idx;
+          // shift ranks p.. up by one (rank 31 carries into rank 32) and insert at p
+          const float cv = __shfl_sync(0xffffffffu, top_v[0], 31);
+          const int ci = __shfl_sync(0xffffffffu, top_i[0], 31);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            float uv = __shfl_up_sync(0xffffffffu, top_v[s], 1);
+            int ui = __shfl_up_sync(0xffffffffu, top_i[s], 1);
+            if (s == 1 && lane == 0) uv = cv, ui = ci;
+            const int r = lane + 32 * s;
+            if (r > p) {
+              top_v[s] = uv;
+              top_i[s] = ui;
+            } else if (r == p) {
+              top_v[s] = v;
+              top_i[s] = idx;
+            }
           }
           top_count = min(top_count + 1, M);
         }
       }
-      const float last = __shfl_sync(0xffffffffu, top_v, M - 1);
+      const float last = M <= 32 ? __shfl_sync(0xffffffffu, top_v[0], (M - 1) & 31)
+                                 : __shfl_sync(0xffffffffu, top_v[1], (M - 1) & 31);
       if (lane == 0) {
         s_full = top_count == M;
         s_thr = top_count == M ? last : -INFINITY;
@@ -251,14 +261,19 @@ __global__ void __launch_bounds__(kBuThreads) bottomup_decode_kernel(const BuArg
   }
 
   // ---- 5. results: value, (x, y), tag through the resized tag plane
-  if (warp == 0 && lane < M) {
-    const size_t o = ((size_t)n * a.K + k) * M + lane;
-    const int y = (int)fdiv((uint32_t)top_i, a.div_w1);
-    const int x = top_i - y * W;
-    a.val_k[o] = top_v;
-    a.ind_k[2 * o] = (float)x;
-    a.ind_k[2 * o + 1] = (float)y;
-    a.tag_k[o] = bilinear_legacy(tag_src, th, tw, tsy, tsx, y, x);
+  if (warp == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int r = lane + 32 * s;
+      if (r >= M) continue;
+      const size_t o = ((size_t)n * a.K + k) * M + r;
+      const int y = (int)fdiv((uint32_t)top_i[s], a.div_w1);
+      const int x = top_i[s] - y * W;
+      a.val_k[o] = top_v[s];
+      a.ind_k[2 * o] = (float)x;
+      a.ind_k[2 * o + 1] = (float)y;
+      a.tag_k[o] = bilinear_legacy(tag_src, th, tw, tsy, tsx, y, x);
+    }
   }
 }
 
@@ -1463,7 +1478,7 @@ __device__ __forceinline__ float sign_of_diff(float hi, float lo) {
 }
 
 __global__ void __launch_bounds__(128) bottomup_shift_kernel(const BuArgs a, int planes) {
-  __shared__ float s_ox[4][32], s_oy[4][32];
+  __shared__ float s_ox[4][64], s_oy[4][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int plane = blockIdx.x * 4 + warp;
   if (plane >= planes) return;
@@ -1479,29 +1494,45 @@ __global__ void __launch_bounds__(128) bottomup_shift_kernel(const BuArgs a, int
   }
   const uint8_t* mask = a.mask + (size_t)n * a.mh * a.mw;
   float* ind = a.ind_k + (size_t)plane * M * 2;
-  int flat = 0x7fffffff;
-  float ox = 0.f, oy = 0.f;
-  if (lane < M) {
-    const int x = (int)ind[2 * lane], y = (int)ind[2 * lane + 1];
-    flat = y * W + x;
-    if (x >= 1 && x <= W - 2)
-      ox = sign_of_diff(bu_raw_at(a, heat_hi, heat_lo, mask, y, x + 1),
-                        bu_raw_at(a, heat_hi, heat_lo, mask, y, x - 1));
-    if (y >= 1 && y <= H - 2)
-      oy = sign_of_diff(bu_raw_at(a, heat_hi, heat_lo, mask, y + 1, x),
-                        bu_raw_at(a, heat_hi, heat_lo, mask, y - 1, x));
+  // entries t = lane and lane + 32 (M <= 64)
+  int flat[2] = {0x7fffffff, 0x7fffffff};
+  float ox[2] = {0.f, 0.f}, oy[2] = {0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int t = lane + 32 * s;
+    if (t < M) {
+      const int x = (int)ind[2 * t], y = (int)ind[2 * t + 1];
+      flat[s] = y * W + x;
+      if (x >= 1 && x <= W - 2)
+        ox[s] = sign_of_diff(bu_raw_at(a, heat_hi, heat_lo, mask, y, x + 1),
+                             bu_raw_at(a, heat_hi, heat_lo, mask, y, x - 1));
+      if (y >= 1 && y <= H - 2)
+        oy[s] = sign_of_diff(bu_raw_at(a, heat_hi, heat_lo, mask, y + 1, x),
+                             bu_raw_at(a, heat_hi, heat_lo, mask, y - 1, x));
+    }
   }
-  // spatial rank of this entry among the M positions (they are distinct)
-  int rank = 0;
-  for (int j = 0; j < M; ++j) rank += __shfl_sync(0xffffffffu, flat, j) < flat ? 1 : 0;
-  if (lane < M) {
-    s_ox[warp][rank] = ox;
-    s_oy[warp][rank] = oy;
+  // spatial rank of each entry among the M positions (they are distinct)
+  int rank[2] = {0, 0};
+  for (int j = 0; j < M; ++j) {
+    const int fj = j < 32 ? __shfl_sync(0xffffffffu, flat[0], j)
+                          : __shfl_sync(0xffffffffu, flat[1], j - 32);
+    rank[0] += fj < flat[0] ? 1 : 0;
+    rank[1] += fj < flat[1] ? 1 : 0;
   }
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+    if (lane + 32 * s < M) {
+      s_ox[warp][rank[s]] = ox[s];
+      s_oy[warp][rank[s]] = oy[s];
+    }
   __syncwarp();
-  if (lane < M) {
-    ind[2 * lane] = __fadd_rn(ind[2 * lane], __fmul_rn(s_ox[warp][lane], 0.25f));
-    ind[2 * lane + 1] = __fadd_rn(ind[2 * lane + 1], __fmul_rn(s_oy[warp][lane], 0.25f));
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int t = lane + 32 * s;
+    if (t < M) {
+      ind[2 * t] = __fadd_rn(ind[2 * t], __fmul_rn(s_ox[warp][t], 0.25f));
+      ind[2 * t + 1] = __fadd_rn(ind[2 * t + 1], __fmul_rn(s_oy[warp][t], 0.25f));
+    }
   }
 }
 
@@ -1558,8 +1589,8 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
              "pc_bottomup_decode: bad stage-0 size");
   PC_REQUIRE(p->mask_h >= 1 && p->mask_w >= 1, PC_ERR_INVALID_ARGUMENT,
              "pc_bottomup_decode: bad mask size");
-  PC_REQUIRE(p->max_num >= 1 && p->max_num <= 32, PC_ERR_UNSUPPORTED,
-             "pc_bottomup_decode: max_num %d outside [1, 32]", p->max_num);
+  PC_REQUIRE(p->max_num >= 1 && p->max_num <= PC_MAX_DETECTIONS, PC_ERR_UNSUPPORTED,
+             "pc_bottomup_decode: max_num %d outside [1, %d]", p->max_num, PC_MAX_DETECTIONS);
   PC_REQUIRE((int64_t)p->h1 * p->w1 >= p->max_num, PC_ERR_INVALID_ARGUMENT,
              "pc_bottomup_decode: map smaller than max_num");
   PC_REQUIRE(!p->use_nms || (p->nms_kernel >= 1 && p->nms_kernel <= kBuMaxNms),
@@ -1616,7 +1647,8 @@ extern "C" int pc_bottomup_decode(const float* d_out0, const float* d_out1,
   const bool aligned = ((uintptr_t)d_out0 % 16 == 0) && (!two || (uintptr_t)d_out1 % 16 == 0) &&
                        (!d_heatmap_raw || (uintptr_t)d_heatmap_raw % 16 == 0) &&
                        (!two || (p->w0 % 4 == 0));
-  if (nms_ok && half && C != 0 && aligned) {
+  // (the fast kernels rank with one 32-lane ballot: max_num 33..64 takes the generic kernel)
+  if (nms_ok && half && C != 0 && aligned && p->max_num <= 32) {
     const bool mask2x = p->mask_w == 2 * p->w1 && (uintptr_t)d_mask % 16 == 0;
     BuArgs b = a;
     if (p->use_nms && p->nms_kernel == 1) b.use_nms = 0;  // a 1x1 pool keeps every value

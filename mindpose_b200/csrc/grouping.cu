@@ -20,7 +20,8 @@
 namespace pc {
 
 // (the group capacity G of an image is a run-time argument: pc_group_params.max_groups)
-constexpr int kMaxDet = 32;
+// detections per joint: shared memory is carved for 32, or for 64 when max_num > 32
+constexpr int kMaxDetCap = PC_MAX_DETECTIONS;
 
 struct GroupArgs {
   const float* val_k;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(32)
   extern __shared__ __align__(16) unsigned char g_smem[];
   const int lane = threadIdx.x;
   const int K = a.K, M = a.M, kG = a.G;
+  const int kMaxDet = M <= 32 ? 32 : kMaxDetCap;
   // ---- shared-memory carve-up
   double* s_v = reinterpret_cast<double*>(g_smem);
   double* s_short = s_v + kG;
@@ -246,26 +248,30 @@ __global__ void __launch_bounds__(32)
   for (int step = 0; step < K && !overflow; ++step) {
     const int idx = tab.joint_order[step];
     // ---- detections of this joint with val > vis_thr, compacted in rank order
-    float dv = 0.f, dt = 0.f, dx = 0.f, dy = 0.f;
-    bool keep = false;
-    if (lane < M) {
-      dv = __ldg(val + idx * M + lane);
-      dt = __ldg(tag + idx * M + lane);
-      dx = __ldg(ind + (idx * M + lane) * 2);
-      dy = __ldg(ind + (idx * M + lane) * 2 + 1);
-      keep = dv > a.vis_thr;
-    }
-    const unsigned km = __ballot_sync(0xffffffffu, keep);
-    const int na = __popc(km);
-    if (na == 0) continue;
+    int na = 0;
     __syncwarp();
-    if (keep) {
-      const int d = __popc(km & ((1u << lane) - 1));
-      s_det[d] = dx;
-      s_det[kMaxDet + d] = dy;
-      s_det[2 * kMaxDet + d] = dv;
-      s_det[3 * kMaxDet + d] = dt;
+    for (int m0 = 0; m0 < M; m0 += 32) {
+      const int m = m0 + lane;
+      float dv = 0.f, dt = 0.f, dx = 0.f, dy = 0.f;
+      bool keep = false;
+      if (m < M) {
+        dv = __ldg(val + idx * M + m);
+        dt = __ldg(tag + idx * M + m);
+        dx = __ldg(ind + (idx * M + m) * 2);
+        dy = __ldg(ind + (idx * M + m) * 2 + 1);
+        keep = dv > a.vis_thr;
+      }
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int d = na + __popc(km & ((1u << lane) - 1));
+        s_det[d] = dx;
+        s_det[kMaxDet + d] = dy;
+        s_det[2 * kMaxDet + d] = dv;
+        s_det[3 * kMaxDet + d] = dt;
+      }
+      na += __popc(km);
     }
+    if (na == 0) continue;
     __syncwarp();
 
     if (step == 0 || ngroups == 0) {
@@ -368,8 +374,8 @@ extern "C" int pc_group_by_tag(const float* d_val_k, const float* d_tag_k, const
   PC_REQUIRE(n >= 0, PC_ERR_INVALID_ARGUMENT, "pc_group_by_tag: n < 0");
   PC_REQUIRE(p->num_joints >= 1 && p->num_joints <= PC_MAX_JOINTS, PC_ERR_INVALID_ARGUMENT,
              "pc_group_by_tag: num_joints %d outside [1, %d]", p->num_joints, PC_MAX_JOINTS);
-  PC_REQUIRE(p->max_num >= 1 && p->max_num <= kMaxDet, PC_ERR_UNSUPPORTED,
-             "pc_group_by_tag: max_num %d outside [1, %d]", p->max_num, kMaxDet);
+  PC_REQUIRE(p->max_num >= 1 && p->max_num <= kMaxDetCap, PC_ERR_UNSUPPORTED,
+             "pc_group_by_tag: max_num %d outside [1, %d]", p->max_num, kMaxDetCap);
   PC_REQUIRE(p->max_groups >= 0, PC_ERR_INVALID_ARGUMENT, "pc_group_by_tag: max_groups < 0");
   GroupTables tab;
   memset(&tab, 0, sizeof(tab));
@@ -400,6 +406,7 @@ extern "C" int pc_group_by_tag(const float* d_val_k, const float* d_tag_k, const
   a.use_rounded_norm = p->use_rounded_norm;
   const int kG = p->max_groups > 0 ? p->max_groups : PC_MAX_GROUPS;
   a.G = kG;
+  const int kMaxDet = p->max_num <= 32 ? 32 : kMaxDetCap;
   const size_t smem = sizeof(double) * (2 * kG + kMaxDet) +
                       sizeof(float) * (2 * kG + kMaxDet * kG + (size_t)kG * a.K + 4 * kMaxDet) +
                       sizeof(int) * (5 * kG + 2 * kMaxDet);

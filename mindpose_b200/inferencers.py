@@ -174,8 +174,10 @@ class BottomUpHeatMapAEInferencer(Inferencer):
             if bool((num < 0).any()):
                 # more than the default 128 people in some image (the reference is unbounded,
                 # match.py:63-113): once more with room for every detection as its own group
-                ans, num, scores = bottomup.group_by_tag(
-                    val_k, tag_k, ind_k, max_groups=val_k.shape[1] * val_k.shape[2], **gkw)
+                # (or what shared memory holds, when max_num > 32)
+                room = bottomup.max_group_capacity(val_k.shape[1], val_k.shape[2])
+                ans, num, scores = bottomup.group_by_tag(val_k, tag_k, ind_k, max_groups=room,
+                                                         **gkw)
             if cfg["refine_missing_joint"]:  # after the scores, as the reference (:153-166)
                 if raw is None or tagging is None:
                     raise ValueError("refine_missing_joint needs the decoder's heatmap outputs "
@@ -189,7 +191,7 @@ class BottomUpHeatMapAEInferencer(Inferencer):
             for i, path in enumerate(data["image_file"]):
                 p = int(num_h[i])
                 if p < 0:   # cannot happen with K * M groups of room
-                    raise RuntimeError("group_by_tag overflowed its group capacity")
+                    raise RuntimeError("more people in one image than group_by_tag can hold")
                 outputs.append(dict(pred=ans_h[i, :p], score=scores_h[i, :p].tolist(),
                                     image_path=path))
         return outputs

@@ -254,6 +254,47 @@ def test_decode_shift_coordinate_matches_oracle(cuda_device, h0, w0, mask_hw, st
     assert not np.array_equal(plain[2], want[2])      # the shift did something
 
 
+@pytest.mark.parametrize("max_num", [33, 50, 64])
+@pytest.mark.parametrize("h0,w0,stages", [(32, 32, 2), (24, 20, 2), (64, 64, 1)])
+def test_decode_and_grouping_max_num_above_32(cuda_device, max_num, h0, w0, stages):
+    """max_num up to 64 (the reference's top-k takes any k, bottom_up_decoder.py:131-171):
+    decode (with the coordinate shift), then grouping over 64 detections per joint."""
+    n = 2
+    rng = np.random.RandomState(max_num + h0)
+    if stages == 2:
+        d = synth.bottomup_outputs(n, 17, h0, w0, mask_hw=(4 * h0, 4 * w0), seed=max_num + h0,
+                                   max_people=12)
+        outs, mask = [d["out0"], d["out1"]], d["mask"]
+        kw, okw = {}, {}
+    else:
+        outs = [rng.uniform(-0.2, 1, (n, 34, h0, w0)).astype(np.float32)]
+        mask = (rng.random_sample((n, 2 * h0, 2 * w0)) > 0.1).astype(np.uint8)
+        kw, okw = dict(num_stages=1, with_ae_loss=[True]), dict(num_stages=1, with_ae_loss=(True,))
+    for shift in (False, True):
+        want = bd.decode(outs, mask, use_nms=True, nms_kernel=3, max_num=max_num,
+                         shift_coordinate=shift, **okw)
+        dec = mp.create_decoder("bottomup_heatmap_ae", use_nms=True, nms_kernel=3, max_num=max_num,
+                                shift_coordinate=shift, **kw)
+        got = dec([_t(o, cuda_device) for o in outs], _t(mask, cuda_device))
+        for name, g, w in zip(["val_k", "tag_k", "ind_k", "raw", "tagging"], got, want):
+            assert np.array_equal(g.cpu().numpy(), w), (name, shift)
+    val_k, tag_k, ind_k = want[:3]
+    room = bottomup.max_group_capacity(17, max_num)
+    ans, num, _ = bottomup.group_by_tag(_t(val_k, cuda_device), _t(tag_k, cuda_device),
+                                        _t(ind_k, cuda_device), synth.COCO_JOINT_ORDER,
+                                        max_groups=room)
+    ans, num = ans.cpu().numpy(), num.cpu().numpy()
+    for i in range(n):
+        w = grouping.match_by_tag(val_k[i], tag_k[i], ind_k[i], synth.COCO_JOINT_ORDER)
+        p = 0 if w.ndim == 1 else w.shape[0]
+        assert num[i] == p, i
+        if p:
+            assert np.array_equal(ans[i, :p], w), i
+    with pytest.raises(ValueError, match="max_num"):
+        mp.create_decoder("bottomup_heatmap_ae", max_num=65, **kw)(
+            [_t(o, cuda_device) for o in outs], _t(mask, cuda_device))
+
+
 # ------------------------------------------------------------------- grouping
 @pytest.mark.parametrize("mode", ["people", "ties", "crowded"])
 @pytest.mark.parametrize("rounded", [True, False])
