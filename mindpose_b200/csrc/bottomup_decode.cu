@@ -1217,7 +1217,6 @@ __device__ __forceinline__ void scan_pairs(const BuArgs& a, const float* __restr
     cb.cnt = base;
   };
 
-#pragma unroll 1
   int tog = 0;  // byte offset of pair p's slot in the ring
   for (int p = pb; p < pe; ++p) {
     cp_async_wait_pending<kPairDepth - 1>();

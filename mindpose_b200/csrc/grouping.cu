@@ -177,6 +177,156 @@ __device__ void lsap_warp(const float* cost, int ldc, int nr, int nc, LsapState 
   }
 }
 
+// The same solver for nc <= 32 * S (S = 1: every image with at most 32 people; S = 2: up to
+// 64), entirely in registers: lane l owns columns l + 32 s (v, shortest, path, row4col and the
+// column's position in the solver's `remaining` list) and rows l + 32 s (u, col4row); the
+// SR / SC sets are warp-uniform bit masks.  No shared-memory round trips and no __syncwarp in
+// the search loop: its chain of dependent steps is the run time of the kernel.  Same
+// arithmetic, same scan order and tie-breaks (the `remaining` list is permuted exactly as the
+// array version permutes it), so the assignment is the same.
+template <int S>
+__device__ void lsap_warp_regs(const float* cost, int ldc, int nr, int nc, int* col4row_out,
+                               int lane) {
+  const unsigned full = 0xffffffffu;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  double u[S], v[S];
+  int col4row[S], row4col[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) u[s] = v[s] = 0.0, col4row[s] = row4col[s] = -1;
+  // value of a per-slot register of row / column x (x warp-uniform)
+  auto at = [&](auto (&reg)[S], int x) {
+    auto val = reg[0];
+#pragma unroll
+    for (int s = 1; s < S; ++s) val = (x >> 5) == s ? reg[s] : val;
+    return __shfl_sync(full, val, x & 31);
+  };
+  for (int cur = 0; cur < nr; ++cur) {
+    int pos[S], path[S];
+    bool rem[S];
+    double shortest[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      pos[s] = nc - 1 - (lane + 32 * s);  // remaining[it] = nc - it - 1
+      rem[s] = lane + 32 * s < nc;
+      shortest[s] = kInf;
+      path[s] = -1;
+    }
+    unsigned long long SR = 0ull, SC = 0ull;
+    int num_rem = nc, sink = -1, i = cur;
+    double min_val = 0.0;
+    while (sink == -1) {
+      SR |= 1ull << i;
+      const double ui = at(u, i);
+      double sj = kInf;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (rem[s]) {
+          const double r = __dsub_rn(
+              __dsub_rn(__dadd_rn(min_val, (double)cost[i * ldc + lane + 32 * s]), ui), v[s]);
+          if (r < shortest[s]) {
+            path[s] = i;
+            shortest[s] = r;
+          }
+          sj = fmin(sj, shortest[s]);
+        }
+      }
+      const double lowest = warp_min_f64(sj);
+      // sequential scan semantics: the first position that reaches the minimum, unless some
+      // position at the minimum is an unassigned column -- then the last of those.  As ONE
+      // maximum: (unassigned, position or its reverse, column) packed into a key.
+      int key = -1;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (rem[s] && shortest[s] == lowest) {
+          const int open = row4col[s] == -1;
+          const int k = (open << 16) | ((open ? pos[s] : 127 - pos[s]) << 8) | (lane + 32 * s);
+          key = max(key, k);
+        }
+      }
+      key = warp_max_i32(key);
+      const int jsel = key & 0xff;
+      const int pe = (key >> 8) & 0xff;
+      const int index = (key >> 16) ? pe : 127 - pe;
+      min_val = lowest;
+      if (key >> 16) {
+        sink = jsel;
+      } else {
+        i = at(row4col, jsel);
+      }
+      --num_rem;
+      SC |= 1ull << jsel;
+      // remaining[index] = remaining[num_rem]
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (lane + 32 * s == jsel)
+          rem[s] = false;
+        else if (rem[s] && pos[s] == num_rem)
+          pos[s] = index;
+      }
+    }
+    // dual variables (before the augmentation: col4row is still the old assignment)
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int c = col4row[s] >= 0 ? col4row[s] : 0;
+      double sh_c = __shfl_sync(full, shortest[0], c & 31);
+#pragma unroll
+      for (int t = 1; t < S; ++t) {
+        const double o = __shfl_sync(full, shortest[t], c & 31);
+        sh_c = (c >> 5) == t ? o : sh_c;
+      }
+      const int r = lane + 32 * s;
+      if (r == cur)
+        u[s] = __dadd_rn(u[s], min_val);
+      else if ((SR >> r) & 1ull)
+        u[s] = __dadd_rn(u[s], __dsub_rn(min_val, sh_c));
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      if ((SC >> (lane + 32 * s)) & 1ull) v[s] = __dsub_rn(v[s], __dsub_rn(min_val, shortest[s]));
+    // augment along the path
+    int j = sink;
+    while (true) {
+      const int r = at(path, j);
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        if (lane + 32 * s == j) row4col[s] = r;
+      const int prev = at(col4row, r);
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        if (lane + 32 * s == r) col4row[s] = j;
+      j = prev;
+      if (r == cur) break;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+    if (lane + 32 * s < nr) col4row_out[lane + 32 * s] = col4row[s];
+  __syncwarp();
+}
+
+// np.linalg.norm over one tag channel: sqrt(d * d) in float32.  With a correctly rounded
+// square root that is |d| exactly whenever d * d stays in the normal range (radix 2), so the
+// software square root only runs outside it.
+__device__ __forceinline__ float tag_norm(float d) {
+  const float ad = fabsf(d);
+  return (ad > 1e-18f && ad < 1e18f) ? ad : __fsqrt_rn(__fmul_rn(d, d));
+}
+
+#ifdef PC_GROUP_PROFILE
+// cycles per phase, summed over the images (experiment builds only)
+__device__ unsigned long long g_group_prof[8];
+#define PC_PROF_MARK(slot)                                             \
+  do {                                                                 \
+    const long long _t = clock64();                                    \
+    if (lane == 0) atomicAdd(&g_group_prof[slot], (unsigned long long)(_t - prof_t)); \
+    prof_t = _t;                                                       \
+  } while (0)
+#else
+#define PC_PROF_MARK(slot) \
+  do {                     \
+  } while (0)
+#endif
+
 __global__ void __launch_bounds__(32)
     group_by_tag_kernel(const GroupArgs a, const __grid_constant__ GroupTables tab) {
   extern __shared__ __align__(16) unsigned char g_smem[];
@@ -208,6 +358,9 @@ __global__ void __launch_bounds__(32)
   float* ans = a.ans + img * kG * K * 4;
   int ngroups = 0;
   bool overflow = false;
+#ifdef PC_GROUP_PROFILE
+  long long prof_t = clock64();
+#endif
 
   // Group bookkeeping.  `open_or_overwrite` is the reference's
   //   key = tags[row, 0]; joint_dict[key][idx] = joints[row]; tag_dict[key] = [tags[row]]
@@ -245,37 +398,51 @@ __global__ void __launch_bounds__(32)
     __syncwarp();
   };
 
+  // The detections of a joint (lane l: ranks l and l + 32) are loaded one step ahead, so that
+  // the round trip to L2 overlaps the previous joint's assignment problem.
+  float pv[2], pt[2], px[2], py[2];
+  auto fetch = [&](int step) {
+    const int j = tab.joint_order[step];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = lane + 32 * h;
+      pv[h] = pt[h] = px[h] = py[h] = 0.f;
+      if (m < M) {
+        pv[h] = __ldg(val + j * M + m);
+        pt[h] = __ldg(tag + j * M + m);
+        px[h] = __ldg(ind + (j * M + m) * 2);
+        py[h] = __ldg(ind + (j * M + m) * 2 + 1);
+      }
+    }
+  };
+  fetch(0);
+
   for (int step = 0; step < K && !overflow; ++step) {
     const int idx = tab.joint_order[step];
     // ---- detections of this joint with val > vis_thr, compacted in rank order
     int na = 0;
     __syncwarp();
-    for (int m0 = 0; m0 < M; m0 += 32) {
-      const int m = m0 + lane;
-      float dv = 0.f, dt = 0.f, dx = 0.f, dy = 0.f;
-      bool keep = false;
-      if (m < M) {
-        dv = __ldg(val + idx * M + m);
-        dt = __ldg(tag + idx * M + m);
-        dx = __ldg(ind + (idx * M + m) * 2);
-        dy = __ldg(ind + (idx * M + m) * 2 + 1);
-        keep = dv > a.vis_thr;
-      }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const bool keep = lane + 32 * h < M && pv[h] > a.vis_thr;
       const unsigned km = __ballot_sync(0xffffffffu, keep);
       if (keep) {
         const int d = na + __popc(km & ((1u << lane) - 1));
-        s_det[d] = dx;
-        s_det[kMaxDet + d] = dy;
-        s_det[2 * kMaxDet + d] = dv;
-        s_det[3 * kMaxDet + d] = dt;
+        s_det[d] = px[h];
+        s_det[kMaxDet + d] = py[h];
+        s_det[2 * kMaxDet + d] = pv[h];
+        s_det[3 * kMaxDet + d] = pt[h];
       }
       na += __popc(km);
     }
+    if (step + 1 < K) fetch(step + 1);
     if (na == 0) continue;
     __syncwarp();
+    PC_PROF_MARK(0);
 
     if (step == 0 || ngroups == 0) {
       for (int d = 0; d < na && !overflow; ++d) open_or_overwrite(d, idx);
+      PC_PROF_MARK(3);
       continue;
     }
     const int ng = ngroups;
@@ -289,42 +456,107 @@ __global__ void __launch_bounds__(32)
     __syncwarp();
     // ---- cost matrix: |tag - ref| (sqrt of the float32 square), rounded; 1e10 padding
     const int nc = max(ng, na);
-    for (int e = lane; e < na * nc; e += 32) {
-      const int r = e / nc, c = e - r * nc;
-      float cost = 1e10f;
-      if (c < ng) {
-        const float diff = __fsub_rn(s_det[3 * kMaxDet + r], s_ref[c]);
-        cost = __fsqrt_rn(__fmul_rn(diff, diff));
-        if (a.use_rounded_norm) cost = rintf(cost);
+    if (nc <= 64) {  // lane = column: no index division, conflict-free stores
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int c = lane + 32 * s;
+        if (c < nc) {
+          const float ref = c < ng ? s_ref[c] : 0.f;
+          for (int r = 0; r < na; ++r) {
+            float cost = 1e10f;
+            if (c < ng) {
+              cost = tag_norm(__fsub_rn(s_det[3 * kMaxDet + r], ref));
+              if (a.use_rounded_norm) cost = rintf(cost);
+            }
+            s_cost[r * kG + c] = cost;
+          }
+        }
       }
-      s_cost[r * kG + c] = cost;
+    } else {
+      for (int e = lane; e < na * nc; e += 32) {
+        const int r = e / nc, c = e - r * nc;
+        float cost = 1e10f;
+        if (c < ng) {
+          cost = tag_norm(__fsub_rn(s_det[3 * kMaxDet + r], s_ref[c]));
+          if (a.use_rounded_norm) cost = rintf(cost);
+        }
+        s_cost[r * kG + c] = cost;
+      }
     }
     __syncwarp();
-    lsap_warp(s_cost, kG, na, nc, st, lane);
+    PC_PROF_MARK(1);
+    if (nc <= 32)
+      lsap_warp_regs<1>(s_cost, kG, na, nc, s_col4row, lane);
+    else if (nc <= 64)
+      lsap_warp_regs<2>(s_cost, kG, na, nc, s_col4row, lane);
+    else
+      lsap_warp(s_cost, kG, na, nc, st, lane);
+    PC_PROF_MARK(2);
 
-    // ---- apply the pairs in row order
-    for (int r = 0; r < na && !overflow; ++r) {
-      const int c = s_col4row[r];
+    // ---- apply the pairs.  The reference walks them in row order; an accepted pair writes
+    // the joint into its (old) group and appends the tag, a rejected one opens a group or
+    // overwrites the group whose key equals its tag.  Accepted pairs touch distinct old
+    // groups, rejected ones new groups -- unless a rejected tag EQUALS the key of an old
+    // group, the one case in which the order between the two kinds matters.  So: accepted
+    // pairs all at once (lane = row), then the rejected ones in row order; the rare key
+    // collision takes the plain sequential walk.
+    bool fast_apply = false;
+    if (na <= 32) {
+      const int r = lane;
+      int c = -1;
       bool accept = false;
-      if (c < ng) {
-        const float diff = __fsub_rn(s_det[3 * kMaxDet + r], s_ref[c]);
-        accept = __fsqrt_rn(__fmul_rn(diff, diff)) < a.tag_thr;
+      float rt = 0.f;
+      if (r < na) {
+        c = s_col4row[r];
+        rt = s_det[3 * kMaxDet + r];
+        if (c < ng) {
+          accept = tag_norm(__fsub_rn(rt, s_ref[c])) < a.tag_thr;
+        }
       }
-      if (accept) {
-        if (lane == 0) {
+      const unsigned acc = __ballot_sync(0xffffffffu, accept);
+      const unsigned rej = ~acc & (na == 32 ? 0xffffffffu : (1u << na) - 1u);
+      bool collide = false;
+      if (rej && r < na && !accept)
+        for (int g = 0; g < ng; ++g) collide |= s_key[g] == rt;
+      if (!__any_sync(0xffffffffu, collide)) {
+        fast_apply = true;
+        if (accept) {
           float* row = ans + (c * K + idx) * 4;
           row[0] = s_det[r];
           row[1] = s_det[kMaxDet + r];
           row[2] = s_det[2 * kMaxDet + r];
-          row[3] = s_det[3 * kMaxDet + r];
-          s_tags[c * K + s_ntag[c]] = s_det[3 * kMaxDet + r];
+          row[3] = rt;
+          s_tags[c * K + s_ntag[c]] = rt;
           s_ntag[c] += 1;
         }
         __syncwarp();
-      } else {
-        open_or_overwrite(r, idx);
+        for (unsigned m = rej; m && !overflow; m &= m - 1) open_or_overwrite(__ffs(m) - 1, idx);
       }
     }
+    if (!fast_apply) {
+      for (int r = 0; r < na && !overflow; ++r) {
+        const int c = s_col4row[r];
+        bool accept = false;
+        if (c < ng) {
+          accept = tag_norm(__fsub_rn(s_det[3 * kMaxDet + r], s_ref[c])) < a.tag_thr;
+        }
+        if (accept) {
+          if (lane == 0) {
+            float* row = ans + (c * K + idx) * 4;
+            row[0] = s_det[r];
+            row[1] = s_det[kMaxDet + r];
+            row[2] = s_det[2 * kMaxDet + r];
+            row[3] = s_det[3 * kMaxDet + r];
+            s_tags[c * K + s_ntag[c]] = s_det[3 * kMaxDet + r];
+            s_ntag[c] += 1;
+          }
+          __syncwarp();
+        } else {
+          open_or_overwrite(r, idx);
+        }
+      }
+    }
+    PC_PROF_MARK(3);
   }
 
   __syncwarp();
@@ -436,3 +668,17 @@ extern "C" int pc_transform_keypoints(float* d_ans, const int32_t* d_num_groups,
   PC_CUDA(cudaGetLastError());
   return PC_OK;
 }
+
+#ifdef PC_GROUP_PROFILE
+// experiment builds only (python -m mindpose_b200.csrc.build --variant ... with
+// PC_NVCC_DEFINES=-DPC_GROUP_PROFILE=1): cycles per phase of group_by_tag_kernel
+extern "C" int pc_group_profile(unsigned long long* out8, int reset) {
+  PC_CUDA(cudaDeviceSynchronize());
+  PC_CUDA(cudaMemcpyFromSymbol(out8, g_group_prof, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    PC_CUDA(cudaMemcpyToSymbol(g_group_prof, z, sizeof(z)));
+  }
+  return PC_OK;
+}
+#endif
