@@ -378,6 +378,21 @@ def test_grouping_more_than_128_people(cuda_device):
         bottomup.group_by_tag(*args, synth.COCO_JOINT_ORDER, max_groups=2000)
 
 
+def test_grouping_randomised_against_oracle(cuda_device):
+    """60 random configurations (joints 3..32, max_num 1..64, up to 60 people, tag ties and
+    equal keys, crowded and wide tag ranges, both norms, ignore_too_much, both capacities)
+    against the oracle with scipy's own solver: the register solver (<= 32 and <= 64 groups)
+    and the shared-memory one (more) all see traffic.  tests/stress/stress_grouping.py."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stress", "stress_grouping.py")
+    spec = importlib.util.spec_from_file_location("stress_grouping", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(60, seed=5, verbose=False) == 0
+
+
 def test_transform_keypoints_matches_oracle(cuda_device):
     val, tag, ind = grouping_inputs(7, 6, mode="people")
     ans, num, _ = bottomup.group_by_tag(_t(val, cuda_device), _t(tag, cuda_device),
