@@ -466,34 +466,6 @@ def run_config4(torch, dev, timeit, peak, iters, cpu_baseline):
     ms_d, ms_g, ms = timeit(decd, iters), timeit(grp, iters), timeit(both, iters)
     _, num, _ = bottomup.group_by_tag(val_k, tag_k, ind_k, order)
 
-    # The same work as a two-stage pipeline over consecutive batches: the grouping of batch i
-    # (64 warps, latency bound) on a second stream under the decode of batch i + 1 (HBM bound).
-    # Every batch is still decoded and grouped once; the outputs of all batches stay alive
-    # until the end so that no buffer is reused across the two streams.
-    main = torch.cuda.current_stream()
-    s_dec, s_grp = torch.cuda.Stream(), torch.cuda.Stream()
-
-    def pipelined(batches):
-        keep, t0, t1 = [], torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record(main)
-        s_dec.wait_stream(main)
-        s_grp.wait_stream(main)
-        for _ in range(batches):
-            with torch.cuda.stream(s_dec):
-                v, t, i, _, _ = dec([out0, out1], mask)
-                done = torch.cuda.Event()
-                done.record(s_dec)
-            with torch.cuda.stream(s_grp):
-                s_grp.wait_event(done)
-                keep.append((v, t, i, bottomup.group_by_tag(v, t, i, order)))
-        main.wait_stream(s_dec)
-        main.wait_stream(s_grp)
-        t1.record(main)
-        t1.synchronize()
-        return t0.elapsed_time(t1) / batches
-
-    pipelined(3)
-    ms_p = pipelined(max(iters, 10))
     # bytes the decode needs: both heat-map stacks once + the mask; the tag planes are only
     # gathered at the <= 30 kept positions per joint (not counted as read)
     need = K * 128 * 128 * 4 + K * 256 * 256 * 4 + 512 * 512 + 8160
@@ -510,10 +482,6 @@ def run_config4(torch, dev, timeit, peak, iters, cpu_baseline):
                      "note": "latency bound: one warp per image, 17 sequential assignment "
                              "problems; 8 KB per image"}],
         "people_per_image_mean": float(num.float().mean().item()),
-        "pipelined": {"ms_per_step": ms_p, "value": n / (ms_p * 1e-3),
-                      "note": "throughput over consecutive batches with the grouping of batch i "
-                              "on a second stream under the decode of batch i + 1; "
-                              "`ms_per_step` / `value` above are one batch start to end"},
     }
     if cpu_baseline:
         import multiprocessing as mpr
