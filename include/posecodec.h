@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PC_VERSION 101 /* 0.1.1 */
+#define PC_VERSION 102 /* 0.1.1 */
 
 typedef enum pc_status {
   PC_OK = 0,
@@ -135,6 +135,24 @@ typedef struct pc_warp_norm_params {
 int pc_warp_affine_u8_norm_chw(const uint8_t* d_src, const int64_t* d_src_offset,
                                const int32_t* d_src_hw, const double* d_inv, float* d_dst,
                                const pc_warp_norm_params* params, int64_t n, void* stream);
+
+/* ---- bottom-up evaluation preprocessing: rescale + pad + mask -------------
+ * BottomUpRescale.transform (mindpose/data/transform/bottomup_transform.py:170-209:
+ * cv2.resize(image, target, interpolation=cv2.INTER_LINEAR)) followed by
+ * BottomUpPad.transform (:610-648: zeros right of / below the image up to max_image_size,
+ * mask 1 on the image and 0 on the padding) -- the validation transforms of the shipped
+ * HigherHRNet recipe -- for a batch of images in one pass.  Sources as in pc_warp_affine_u8
+ * (one base pointer, a byte offset and (height, width) per image, HWC uint8, 3 channels);
+ * d_dst_wh i32 [N,2] = the (width, height) BottomUpRescale._get_new_size gives each image
+ * (host arithmetic: the Python mirror computes it); d_dst u8 [N, canvas_h, canvas_w, 3];
+ * d_mask u8 [N, canvas_h, canvas_w] or NULL.  A target larger than the canvas is cut at the
+ * canvas (the reference asserts; the Python mirror raises before the call).  Arithmetic:
+ * OpenCV's 8-bit bilinear resize, bit for bit (oracle/resize.py), including the 2 x 2 area
+ * path it takes when the source is exactly twice the target. */
+int pc_rescale_pad_u8(const uint8_t* d_src, const int64_t* d_src_offset,
+                      const int32_t* d_src_hw, const int32_t* d_dst_wh, uint8_t* d_dst,
+                      uint8_t* d_mask, int32_t canvas_w, int32_t canvas_h, int32_t channels,
+                      int64_t n, void* stream);
 
 /* Keypoint half of TopDownAffine (topdown_transform.py:224-231 / :255-259):
  * in place on d_keypoints f32 [N,K,3]; standard path moves joints with

@@ -154,6 +154,33 @@ def warp_affine_uniform(images: torch.Tensor, inv: torch.Tensor, dst_size) -> to
     return warp_affine(images, off, hw, inv, dst_size, channels=c)
 
 
+def rescale_pad(images: torch.Tensor, src_offset: torch.Tensor, src_hw: torch.Tensor,
+                dst_wh: torch.Tensor, canvas_wh, with_mask: bool = True):
+    """Bilinear rescale (cv2.resize INTER_LINEAR arithmetic) of every image to its own target
+    size into the top-left corner of a zero canvas, plus the validity mask.
+
+    images u8 (any shape: one allocation holding N HWC images), src_offset i64 [N] (bytes),
+    src_hw i32 [N,2] (height, width), dst_wh i32 [N,2] (width, height)
+    -> (canvas u8 [N, canvas_h, canvas_w, 3], mask u8 [N, canvas_h, canvas_w] or None)."""
+    if not (images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous()):
+        raise ValueError("`images` must be a contiguous uint8 CUDA tensor")
+    cw, ch = _wh(canvas_wh)
+    n = src_offset.shape[0]
+    dev = images.device
+    src_offset = src_offset.to(device=dev, dtype=torch.int64).contiguous()
+    src_hw = src_hw.to(device=dev, dtype=torch.int32).contiguous()
+    dst_wh = dst_wh.to(device=dev, dtype=torch.int32).contiguous()
+    if src_hw.shape != (n, 2) or dst_wh.shape != (n, 2):
+        raise ValueError("`src_hw` and `dst_wh` must be [N, 2]")
+    out = torch.empty((n, ch, cw, 3), dtype=torch.uint8, device=dev)
+    mask = torch.empty((n, ch, cw), dtype=torch.uint8, device=dev) if with_mask else None
+    with torch.cuda.device(dev):
+        _lib.call("pc_rescale_pad_u8", _lib.device_ptr(images), _lib.device_ptr(src_offset),
+                  _lib.device_ptr(src_hw), _lib.device_ptr(dst_wh), _lib.device_ptr(out),
+                  _lib.device_ptr(mask), cw, ch, 3, n, _lib.current_stream())
+    return out, mask
+
+
 def affine_joints(keypoints: torch.Tensor, fwd: torch.Tensor, use_udp: bool = False):
     """In place on keypoints f32 [N,K,3]; returns it."""
     if not (keypoints.is_cuda and keypoints.dtype == torch.float32 and keypoints.is_contiguous()):

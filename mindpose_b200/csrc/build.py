@@ -19,6 +19,7 @@ SOURCES = [
     "topdown_decode.cu",
     "topdown_encode.cu",
     "warp_affine.cu",
+    "rescale.cu",
     "bottomup_decode.cu",
     "bottomup_encode.cu",
     "grouping.cu",

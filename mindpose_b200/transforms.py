@@ -26,6 +26,28 @@ def _dev() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _three_point_geometry(center, scale, rot, out_wh, pixel_std):
+    """The two point triples ``get_affine_transform`` hands to cv2.getAffineTransform
+    (utils.py:73-96), float32 [3,2] each, evaluated with numpy in the dtypes the caller passed
+    (what the reference does: the scalars are float64 or float32 as they arrive, the points are
+    stored as float32)."""
+    w, h = out_wh
+    half_w = (scale * pixel_std)[0] * -0.5
+    angle = np.pi * rot / 180
+    sn, cs = np.sin(angle), np.cos(angle)
+    direction = [0.0 * cs - half_w * sn, 0.0 * sn + half_w * cs]
+    src = np.zeros((3, 2), dtype=np.float32)
+    src[0] = center
+    src[1] = center + direction
+    dst = np.zeros((3, 2), dtype=np.float32)
+    dst[0] = [w * 0.5, h * 0.5]
+    dst[1] = np.array([w * 0.5, h * 0.5]) + np.array([0.0, w * -0.5])
+    for pts in (src, dst):  # third point: (a - b) turned by 90 degrees about b
+        d = pts[0] - pts[1]
+        pts[2] = pts[1] + np.array([-d[1], d[0]], dtype=np.float32)
+    return src, dst
+
+
 class Transform:
     """Column tuple <-> state dict adapter (transform.py:6-79)."""
 
@@ -143,20 +165,7 @@ class TopDownAffine(TopDownTransform):
             m[1, 0], m[1, 1] = sn * ky, cs * ky
             m[1, 2] = ky * (-0.5 * size_in[0] * sn - 0.5 * size_in[1] * cs + 0.5 * size_tgt[1])
             return "matrix", m
-        half_w = (scale * pixel_std)[0] * -0.5
-        angle = np.pi * rot / 180
-        sn, cs = np.sin(angle), np.cos(angle)
-        direction = [0.0 * cs - half_w * sn, 0.0 * sn + half_w * cs]
-        src = np.zeros((3, 2), dtype=np.float32)
-        src[0] = center
-        src[1] = center + direction
-        dst = np.zeros((3, 2), dtype=np.float32)
-        dst[0] = [w * 0.5, h * 0.5]
-        dst[1] = np.array([w * 0.5, h * 0.5]) + np.array([0.0, w * -0.5])
-        for pts in (src, dst):  # third point: (a - b) turned by 90 degrees about b
-            d = pts[0] - pts[1]
-            pts[2] = pts[1] + np.array([-d[1], d[0]], dtype=np.float32)
-        return "points", src, dst
+        return ("points",) + _three_point_geometry(center, scale, rot, (w, h), pixel_std)
 
     def _host_matrix(self, center, scale, rot) -> Optional[torch.Tensor]:
         """Forward matrix f64 [1,2,3] on the device for a ROTATED sample (None at rot == 0,
@@ -316,3 +325,154 @@ class BottomUpGenerateTarget(BottomUpTransform):
         cfg = self._transform_cfg
         return bottomup.encode_targets(keypoints, cfg["heatmap_sizes"], sigma=self.sigma,
                                        max_num=self.max_num, tag_per_joint=cfg["tag_per_joint"])
+
+
+def _rescale_size(image_wh, max_wh) -> Tuple[int, int]:
+    """Target (w, h) of ``BottomUpRescale`` (bottomup_transform.py:152-168): the image fills the
+    ``max_image_size`` box (turned by 90 degrees for a portrait image) along one side; float64
+    ratios and Python's round (half to even), as the reference evaluates them."""
+    w, h = int(image_wh[0]), int(image_wh[1])
+    box_w, box_h = int(max_wh[0]), int(max_wh[1])
+    if w < h:
+        box_w, box_h = box_h, box_w
+    if w / h > box_w / box_h:
+        return box_w, int(round(h * box_w / w))
+    return int(round(w * box_h / h)), box_h
+
+
+@register("transform", extra_name="bottomup_rescale")
+class BottomUpRescale(BottomUpTransform):
+    """Rescale the image into the ``max_image_size`` box, aspect ratio kept
+    (bottomup_transform.py:144-209; the first validation transform of the shipped recipe).
+
+    Required keys: image.  Returned keys: image, center, scale, image_shape.
+    ``rescale_pad_batch`` runs this transform and ``BottomUpPad`` for a batch in one kernel.
+    """
+
+    def transform(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        image = np.ascontiguousarray(state["image"])
+        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+            raise ValueError("`image` must be a uint8 HWC array of 3 channels")
+        height, width = image.shape[:2]
+        tw, th = _rescale_size((width, height), self._transform_cfg["max_image_size"])
+        canvas, _, meta = self.rescale_pad_batch([image], canvas_wh=(tw, th), with_mask=False)
+        return dict(image=canvas[0].cpu().numpy(), center=meta["center"][0],
+                    scale=meta["scale"][0], image_shape=(tw, th))
+
+    def rescale_pad_batch(self, images, canvas_wh=None, with_mask: bool = True):
+        """images: a list of uint8 HWC arrays / tensors (any sizes), or one u8 tensor
+        [N, H, W, 3] -> (canvas u8 [N, CH, CW, 3] CUDA, mask u8 [N, CH, CW] or None, meta) with
+        meta = dict(center int64 [N,2], scale f64 [N,2], image_shape int64 [N,2]) as numpy,
+        exactly what BottomUpRescale followed by BottomUpPad return per image.
+
+        ``canvas_wh`` defaults to ``max_image_size`` (landscape box); portrait images need the
+        turned box, so a mixed batch needs a canvas that holds both (the reference pads each
+        image to its own orientation; a batch tensor has one shape)."""
+        cfg = self._transform_cfg
+        dev = _dev()
+        if isinstance(images, torch.Tensor) and images.dim() == 4:
+            images = list(images)
+        sizes = [(int(im.shape[1]), int(im.shape[0])) for im in images]   # (w, h)
+        for im in images:
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError("every image must be HWC with 3 channels")
+        targets = [_rescale_size(wh, cfg["max_image_size"]) for wh in sizes]
+        if canvas_wh is None:
+            canvas_wh = tuple(int(v) for v in cfg["max_image_size"])
+        cw, ch = int(canvas_wh[0]), int(canvas_wh[1])
+        for (tw, th) in targets:
+            if tw > cw or th > ch:   # the reference: assert target_width >= width ...
+                raise ValueError(f"a {tw}x{th} rescaled image does not fit the {cw}x{ch} canvas")
+        # one allocation, every image at a 16-byte aligned offset
+        offs, total = [], 0
+        for (w, h) in sizes:
+            offs.append(total)
+            total += (w * h * 3 + 15) // 16 * 16
+        blob = torch.empty(max(total, 16), dtype=torch.uint8, device=dev)
+        for im, off, (w, h) in zip(images, offs, sizes):
+            t = im if isinstance(im, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(im))
+            if t.dtype != torch.uint8:
+                raise ValueError("images must be uint8")
+            blob[off:off + w * h * 3].copy_(t.reshape(-1), non_blocking=True)
+        src_hw = torch.tensor([[h, w] for (w, h) in sizes], dtype=torch.int32).reshape(-1, 2)
+        dst_wh = torch.tensor(targets, dtype=torch.int32).reshape(-1, 2)
+        canvas, mask = codec.rescale_pad(blob, torch.tensor(offs, dtype=torch.int64), src_hw,
+                                         dst_wh, (cw, ch), with_mask=with_mask)
+        pixel_std = cfg["pixel_std"]
+        meta = dict(center=np.array([[round(w / 2), round(h / 2)] for (w, h) in sizes]),
+                    scale=np.array([[w / pixel_std, h / pixel_std] for (w, h) in sizes]),
+                    image_shape=np.array(targets))
+        return canvas, mask, meta
+
+
+@register("transform", extra_name="bottomup_pad")
+class BottomUpPad(BottomUpTransform):
+    """Pad the image with zeros to ``max_image_size`` (turned for a portrait image) and make the
+    validity mask (bottomup_transform.py:602-648).  Required keys: image.  Returned keys:
+    image, mask.  A copy, not arithmetic: it stays on the host for a single sample;
+    ``BottomUpRescale.rescale_pad_batch`` writes the padded canvas and the mask on the device
+    in the same pass as the rescale."""
+
+    def transform(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        image = state["image"]
+        height, width = image.shape[:2]
+        target_w, target_h = (int(v) for v in self._transform_cfg["max_image_size"])
+        if width < height:
+            target_w, target_h = target_h, target_w
+        if target_w < width or target_h < height:
+            raise AssertionError("the image is larger than max_image_size")
+        out = np.zeros((target_h, target_w) + tuple(image.shape[2:]), dtype=image.dtype)
+        out[:height, :width] = image
+        mask = np.zeros((target_h, target_w), dtype=np.uint8)
+        mask[:height, :width] = 1
+        return dict(image=out, mask=mask)
+
+
+@register("transform", extra_name="bottomup_resize")
+class BottomUpResize(BottomUpTransform):
+    """Short side to ``size`` (rounded up to ``base_length``), long side rounded up to
+    ``base_length``, through the affine warp (bottomup_transform.py:212-302: get_affine_transform
+    with rotation 0 and cv2.warpAffine) -- the crop-warp kernel of the top-down path.
+
+    Required keys: image.  Returned keys: image, mask, center, scale, image_shape.
+    """
+
+    def __init__(self, is_train: bool = True, config: Optional[Dict[str, Any]] = None,
+                 size: int = 512, base_length: int = 64) -> None:
+        super().__init__(is_train=is_train, config=config)
+        self.size = size
+        self.base_length = base_length
+
+    def _get_new_size(self, image_wh, pixel_std: float = 200.0):
+        w, h = image_wh
+        unit = self.base_length
+
+        def up(x):
+            return int(np.ceil(x / unit)) * unit
+
+        short = up(self.size)
+        if w < h:
+            tw, th = short, up(short / w * h)
+            scale = np.array([w / pixel_std, th / tw * w / pixel_std])
+        else:
+            th, tw = short, up(short / h * w)
+            scale = np.array([tw / th * h / pixel_std, h / pixel_std])
+        return (tw, th), np.array([round(w / 2), round(h / 2)]), scale
+
+    def transform(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        dev = _dev()
+        image = np.ascontiguousarray(state["image"])
+        if image.dtype != np.uint8 or image.ndim != 3:
+            raise ValueError("`image` must be a uint8 HWC array")
+        height, width = image.shape[:2]
+        target, center, scale = self._get_new_size((width, height),
+                                                   self._transform_cfg["pixel_std"])
+        # the reference calls get_affine_transform with its default pixel_std (200), whatever
+        # the config says (bottomup_transform.py:291)
+        src, dst = _three_point_geometry(center, scale, 0.0, target, 200.0)
+        _, inv = codec.affine_from_points(torch.from_numpy(src[None]).to(dev),
+                                          torch.from_numpy(dst[None]).to(dev))
+        out = codec.warp_affine_uniform(torch.from_numpy(image[None]).to(dev), inv, target)
+        return dict(image=out[0].cpu().numpy(),
+                    mask=np.ones((target[1], target[0]), dtype=np.uint8),
+                    center=center, scale=scale, image_shape=target)

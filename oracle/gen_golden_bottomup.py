@@ -129,9 +129,57 @@ def refine_missing_golden(golden_dir):
     np.savez_compressed(os.path.join(golden_dir, "refine_missing_ref.npz"), **out)
 
 
+# (source h, w) of the eval-side preprocessing cases; max_image_size is [104, 64] so that the
+# fixture stays small (the arithmetic does not depend on the size)
+RESCALE_CASES = [(60, 80), (80, 60), (48, 101), (33, 37), (64, 128), (128, 208), (52, 52)]
+RESCALE_MAX = [104, 64]
+
+
+def rescale_image(seed, h, w):
+    return np.random.RandomState(seed).randint(0, 256, (h, w, 3)).astype(np.uint8)
+
+
+def rescale_pad_golden(ns, golden_dir):
+    """BottomUpRescale -> BottomUpPad and BottomUpResize of the unmodified reference
+    (bottomup_transform.py:144-209, :602-648, :212-302)."""
+    import hashlib
+
+    cfg = dict(image_size=[64, 64], max_image_size=RESCALE_MAX, heatmap_sizes=[[16, 16], [32, 32]],
+               flip_pairs=[[1, 2]], pixel_std=200.0, tag_per_joint=True)
+    rescale = ns.bottomup.BottomUpRescale(is_train=False, config=cfg)
+    padder = ns.bottomup.BottomUpPad(is_train=False, config=cfg)
+    resize = ns.bottomup.BottomUpResize(is_train=False, config=cfg, size=64, base_length=32)
+    out = {}
+    for ci, (h, w) in enumerate(RESCALE_CASES):
+        img = rescale_image(100 + ci, h, w)
+        r = rescale.transform(dict(image=img.copy()))
+        p = padder.transform(dict(image=r["image"].copy()))
+        out[f"rescaled_{ci}"] = r["image"]
+        out[f"center_{ci}"], out[f"scale_{ci}"] = np.asarray(r["center"]), np.asarray(r["scale"])
+        out[f"shape_{ci}"] = np.asarray(r["image_shape"])
+        out[f"padded_{ci}"], out[f"mask_{ci}"] = p["image"], p["mask"]
+        z = resize.transform(dict(image=img.copy()))
+        out[f"resized_{ci}"], out[f"resized_mask_{ci}"] = z["image"], z["mask"]
+        out[f"resized_center_{ci}"] = np.asarray(z["center"])
+        out[f"resized_scale_{ci}"] = np.asarray(z["scale"])
+        out[f"resized_shape_{ci}"] = np.asarray(z["image_shape"])
+    # the shipped recipe's own sizes (max_image_size [832, 512]), kept as digests
+    big = dict(cfg, max_image_size=[832, 512])
+    rescale = ns.bottomup.BottomUpRescale(is_train=False, config=big)
+    padder = ns.bottomup.BottomUpPad(is_train=False, config=big)
+    digests = []
+    for ci, (h, w) in enumerate([(480, 640), (640, 427), (375, 500)]):
+        r = rescale.transform(dict(image=rescale_image(200 + ci, h, w)))
+        p = padder.transform(dict(image=r["image"]))
+        digests.append(hashlib.sha256(p["image"].tobytes() + p["mask"].tobytes()).hexdigest())
+    out["big_digests"] = np.array(digests)
+    np.savez_compressed(os.path.join(golden_dir, "bottomup_rescale_ref.npz"), **out)
+
+
 def main(ns, golden_dir):
     bottomup_encode_golden(ns, golden_dir)
     refine_missing_golden(golden_dir)
+    rescale_pad_golden(ns, golden_dir)
 
     import scipy.optimize
 

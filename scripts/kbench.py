@@ -42,7 +42,7 @@ def timeit(fn, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--only", default="decode,encode,warp,bottomup,group,bu_encode,refine,nms,sweep")
+    ap.add_argument("--only", default="decode,encode,warp,bottomup,group,bu_encode,refine,nms,sweep,rescale")
     ap.add_argument("--json", default="")
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -239,6 +239,19 @@ def main():
         med, mn = timeit(fn, args.iters)
         report("bottomup_encode 64 x 2 x 17 x 256^2 (8 people)", n, "images",
                2 * 17 * 256 * 256 * 4 + 2 * 30 * 17 * 8, med, mn)
+    if "rescale" in only:
+        # bottom-up evaluation preprocessing: 256 images 480 x 640 -> 683 x 512 in an 832 x 512
+        # canvas + mask (source read once, canvas and mask written once)
+        n, sh, sw, cw, ch = 256, 480, 640, 832, 512
+        g = torch.Generator(device=dev).manual_seed(0)
+        imgs = torch.randint(0, 256, (n, sh, sw, 3), device=dev, dtype=torch.uint8, generator=g)
+        off = torch.arange(n, device=dev, dtype=torch.int64) * (sh * sw * 3)
+        hw = torch.tensor([[sh, sw]] * n, dtype=torch.int32, device=dev)
+        wh = torch.tensor([[683, 512]] * n, dtype=torch.int32, device=dev)
+        fn = lambda: codec.rescale_pad(imgs, off, hw, wh, (cw, ch))  # noqa: E731
+        med, mn = timeit(fn, args.iters)
+        report("rescale + pad + mask 480x640 -> 683x512 in 832x512 (256 images)", n, "images",
+               sh * sw * 3 + cw * ch * 4, med, mn)
     if args.json:
         with open(args.json, "w") as f:
             json.dump(rows, f, indent=1)
