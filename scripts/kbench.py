@@ -252,6 +252,23 @@ def main():
         med, mn = timeit(fn, args.iters)
         report("rescale + pad + mask 480x640 -> 683x512 in 832x512 (256 images)", n, "images",
                sh * sw * 3 + cw * ch * 4, med, mn)
+        try:   # the reference's own two calls on one host core, beside it
+            import time
+
+            import cv2
+            cv2.setNumThreads(1)
+            host = imgs[:16].cpu().numpy()
+            t0 = time.perf_counter()
+            for im in host:
+                r = cv2.resize(im, (683, 512), interpolation=cv2.INTER_LINEAR)
+                np.pad(r, ((0, ch - 512), (0, cw - 683), (0, 0)))
+                m = np.zeros((ch, cw), np.uint8)
+                m[:512, :683] = 1
+            dt = (time.perf_counter() - t0) / len(host)
+            print(f"  cv2.resize + np.pad + mask on one host core: {dt * 1e3:.3f} ms per image "
+                  f"({1 / dt:.0f} images/s)")
+        except ImportError:
+            pass
     if args.json:
         with open(args.json, "w") as f:
             json.dump(rows, f, indent=1)
