@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PC_VERSION 102 /* 0.1.1 */
+#define PC_VERSION 103 /* 0.1.1 */
 
 typedef enum pc_status {
   PC_OK = 0,
@@ -153,6 +153,17 @@ int pc_rescale_pad_u8(const uint8_t* d_src, const int64_t* d_src_offset,
                       const int32_t* d_src_hw, const int32_t* d_dst_wh, uint8_t* d_dst,
                       uint8_t* d_mask, int32_t canvas_w, int32_t canvas_h, int32_t channels,
                       int64_t n, void* stream);
+
+/* The same with the pipeline's next step fused, as pc_warp_affine_u8_norm_chw does for the crop
+ * warp: vision.Normalize(mean * 255, std * 255) + HWC2CHW (mindpose/data/data_factory.py:127-138).
+ * d_dst f32 [N, 3, canvas_h, canvas_w] = (pixel - mean[c]) / std[c]; the uint8 canvas is not
+ * materialised and the zero padding becomes (0 - mean[c]) / std[c], which is what Normalize makes
+ * of it in the reference's pipeline.  params: dst_w / dst_h = the canvas, mean / std as handed to
+ * vision.Normalize.  Any canvas width. */
+int pc_rescale_pad_u8_norm_chw(const uint8_t* d_src, const int64_t* d_src_offset,
+                               const int32_t* d_src_hw, const int32_t* d_dst_wh, float* d_dst,
+                               uint8_t* d_mask, const pc_warp_norm_params* params, int64_t n,
+                               void* stream);
 
 /* Keypoint half of TopDownAffine (topdown_transform.py:224-231 / :255-259):
  * in place on d_keypoints f32 [N,K,3]; standard path moves joints with

@@ -218,6 +218,8 @@ SIGNATURES = {
         c_int, [_P, _P, _P, _P, _P, POINTER(WarpNormParams), c_int64, _P]),
     "pc_rescale_pad_u8": (
         c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_int64, _P]),
+    "pc_rescale_pad_u8_norm_chw": (
+        c_int, [_P, _P, _P, _P, _P, _P, POINTER(WarpNormParams), c_int64, _P]),
     "pc_affine_joints": (c_int, [_P, _P, c_int32, c_int32, c_int64, _P]),
     "pc_topdown_encode": (c_int, [_P, _P, _P, POINTER(EncodeParams), c_int64, _P]),
     "pc_topdown_decode": (

@@ -155,13 +155,18 @@ def warp_affine_uniform(images: torch.Tensor, inv: torch.Tensor, dst_size) -> to
 
 
 def rescale_pad(images: torch.Tensor, src_offset: torch.Tensor, src_hw: torch.Tensor,
-                dst_wh: torch.Tensor, canvas_wh, with_mask: bool = True):
+                dst_wh: torch.Tensor, canvas_wh, with_mask: bool = True,
+                mean: Optional[Sequence[float]] = None, std: Optional[Sequence[float]] = None):
     """Bilinear rescale (cv2.resize INTER_LINEAR arithmetic) of every image to its own target
     size into the top-left corner of a zero canvas, plus the validity mask.
 
     images u8 (any shape: one allocation holding N HWC images), src_offset i64 [N] (bytes),
     src_hw i32 [N,2] (height, width), dst_wh i32 [N,2] (width, height)
-    -> (canvas u8 [N, canvas_h, canvas_w, 3], mask u8 [N, canvas_h, canvas_w] or None)."""
+    -> (canvas u8 [N, canvas_h, canvas_w, 3], mask u8 [N, canvas_h, canvas_w] or None).
+
+    With ``mean`` / ``std`` (the values given to ``vision.Normalize``, i.e. already multiplied
+    by 255) the pipeline's Normalize + HWC2CHW step (data_factory.py:127-138) is fused in and
+    the canvas comes back as float32 [N, 3, canvas_h, canvas_w]."""
     if not (images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous()):
         raise ValueError("`images` must be a contiguous uint8 CUDA tensor")
     cw, ch = _wh(canvas_wh)
@@ -172,8 +177,26 @@ def rescale_pad(images: torch.Tensor, src_offset: torch.Tensor, src_hw: torch.Te
     dst_wh = dst_wh.to(device=dev, dtype=torch.int32).contiguous()
     if src_hw.shape != (n, 2) or dst_wh.shape != (n, 2):
         raise ValueError("`src_hw` and `dst_wh` must be [N, 2]")
-    out = torch.empty((n, ch, cw, 3), dtype=torch.uint8, device=dev)
     mask = torch.empty((n, ch, cw), dtype=torch.uint8, device=dev) if with_mask else None
+    if (mean is None) != (std is None):
+        raise ValueError("give both `mean` and `std`, or neither")
+    if mean is not None:
+        mean = np.asarray(mean, dtype=np.float32).reshape(-1)
+        std = np.asarray(std, dtype=np.float32).reshape(-1)
+        if mean.shape[0] != 3 or std.shape[0] != 3:
+            raise ValueError("`mean` and `std` must have three entries")
+        out = torch.empty((n, 3, ch, cw), dtype=torch.float32, device=dev)
+        p = _lib.WarpNormParams()
+        p.dst_w, p.dst_h, p.channels = cw, ch, 3
+        for c in range(3):
+            p.mean[c], p.std[c] = float(mean[c]), float(std[c])
+        with torch.cuda.device(dev):
+            _lib.call("pc_rescale_pad_u8_norm_chw", _lib.device_ptr(images),
+                      _lib.device_ptr(src_offset), _lib.device_ptr(src_hw), _lib.device_ptr(dst_wh),
+                      _lib.device_ptr(out), _lib.device_ptr(mask), ctypes.byref(p), n,
+                      _lib.current_stream())
+        return out, mask
+    out = torch.empty((n, ch, cw, 3), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.call("pc_rescale_pad_u8", _lib.device_ptr(images), _lib.device_ptr(src_offset),
                   _lib.device_ptr(src_hw), _lib.device_ptr(dst_wh), _lib.device_ptr(out),

@@ -214,15 +214,62 @@ __device__ __forceinline__ uint32_t pinned(uint32_t v) {
   return v;
 }
 
+// vision.Normalize(mean * 255, std * 255) of the step after the transforms
+// (mindpose/data/data_factory.py:127-138), as in the fused crop warp (warp_affine.cu, row N2):
+// the IEEE quotient, or x * (1 / std) plus one exact residual step when the host has verified
+// that form for all 256 pixel values of every channel.
+struct RescaleNorm {
+  float mean[3], std[3], rcp[3];
+  int32_t fast;
+};
+__device__ __forceinline__ float rescale_norm_value(uint32_t px, float mean, float std, float rcp,
+                                                    bool fast) {
+  const float x = __fsub_rn((float)px, mean);
+  if (!fast) return __fdiv_rn(x, std);
+  const float q0 = __fmul_rn(x, rcp);
+  return __fmaf_rn(__fmaf_rn(-q0, std, x), rcp, q0);
+}
+
+// Where a thread's pixel of each row goes.  NORM = false: uint8 HWC, a warp's 32 pixels as 24
+// words (lanes 4g .. 4g+3 hold the pixels of columns 4c .. 4c+3; three of them store a word
+// each).  NORM = true: float32 CHW planes, Normalize fused (the uint8 canvas is never written;
+// the zero padding becomes (0 - mean) / std, as Normalize makes it in the reference's pipeline).
+template <bool NORM>
+struct RescaleOut {
+  uint8_t* o;        // !NORM: this lane's word of its group of four pixels
+  float* f;          // NORM: this column of channel 0's plane
+  uint8_t* m;        // mask byte of this column (dereferenced only if store_m)
+  uint32_t opitch, fplane, CW, selO;
+  bool store_px, store_m;
+  RescaleNorm norm;
+
+  __device__ __forceinline__ void row(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t mask_value) {
+    if (NORM) {
+      if (store_px) {
+        const bool fast = norm.fast != 0;
+        f[0] = rescale_norm_value(v0, norm.mean[0], norm.std[0], norm.rcp[0], fast);
+        f[fplane] = rescale_norm_value(v1, norm.mean[1], norm.std[1], norm.rcp[1], fast);
+        f[2 * (size_t)fplane] = rescale_norm_value(v2, norm.mean[2], norm.std[2], norm.rcp[2], fast);
+      }
+      f += CW;
+    } else {
+      const uint32_t px = __byte_perm(__byte_perm(v0, v1, 0x0040), v2, 0x5410);
+      const uint32_t nxt = __shfl_down_sync(0xffffffffu, px, 1);
+      if (store_px) *reinterpret_cast<uint32_t*>(o) = __byte_perm(px, nxt, selO);
+      o += opitch;
+    }
+    if (store_m) *m = (uint8_t)mask_value;
+    m += CW;
+  }
+};
+
 // This thread's column of one tile.  AREA: the exact 2 x 2 reduction.  PITCH4: the source row
 // pitch is a multiple of 4 bytes, so the alignment of the thread's window -- and with it the
 // byte-permute selectors -- is the same in every row.
-template <bool AREA, bool PITCH4>
+template <bool AREA, bool PITCH4, bool NORM>
 __device__ __forceinline__ void rescale_column(const uint8_t* __restrict__ image, uint32_t win,
                                                uint32_t wpair, const RescaleRow* s_row, int rows,
-                                               uint8_t* o, uint32_t opitch, bool store_px,
-                                               uint32_t selO, uint8_t* m, uint32_t mpitch,
-                                               bool store_m, uint32_t mval) {
+                                               RescaleOut<NORM>& out, uint32_t mval) {
   uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(image) + win) & 3u;
   uint32_t selA = pinned(0x4130u + 0x1111u * a);              // (A, B) -> r0 r1 g0 g1
   uint32_t selB = pinned(((6u + a) & 7u) | ((1u + a) << 4));  // (B, Z) -> b0 b1 . .
@@ -283,12 +330,7 @@ __device__ __forceinline__ void rescale_column(const uint8_t* __restrict__ image
     for (int c = 0; c < 3; ++c)
       v[c] = AREA ? ((rr.z ? hx[c] + hy[c] : 0u) + 2u) >> 2
                   : (mulhi_u32(rr.z, hx[c]) + mulhi_u32(rr.w, hy[c]) + 2u) >> 2;
-    const uint32_t px = __byte_perm(__byte_perm(v[0], v[1], 0x0040), v[2], 0x5410);
-    const uint32_t nxt = __shfl_down_sync(0xffffffffu, px, 1);
-    if (store_px) *reinterpret_cast<uint32_t*>(o) = __byte_perm(px, nxt, selO);
-    o += opitch;
-    if (store_m) *m = (rr.z | rr.w) ? (uint8_t)mval : (uint8_t)0;
-    m += mpitch;
+    out.row(v[0], v[1], v[2], (rr.z | rr.w) ? mval : 0u);
   };
   uint32_t ha[3] = {0u, 0u, 0u}, hb[3] = {0u, 0u, 0u};
 #pragma unroll 1
@@ -305,11 +347,12 @@ __device__ __forceinline__ void rescale_column(const uint8_t* __restrict__ image
 // or two 128-byte lines; a warp's 32 pixels (96 bytes) leave as 24 words (one shuffle, one
 // byte permute).  Needs canvas rows that start on word boundaries (canvas_w % 4 == 0) and
 // sources at least two pixels wide; row offsets are 32-bit (images below 4 GB).
+template <bool NORM>
 __global__ void __launch_bounds__(kRescaleMaxThreads, PC_RESCALE_MINB)
     rescale_pad_u8x3_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
                             const int32_t* __restrict__ src_hw, const int32_t* __restrict__ dst_wh,
-                            uint8_t* __restrict__ dst, uint8_t* __restrict__ mask, int CW, int CH,
-                            int col_blocks, int row_tiles) {
+                            void* __restrict__ dst_any, uint8_t* __restrict__ mask, int CW, int CH,
+                            int col_blocks, int row_tiles, const RescaleNorm norm) {
   __shared__ __align__(16) RescaleRow s_row[kRescaleRows];
   const int tid = threadIdx.x, lane = tid & 31;
   int b = blockIdx.x;
@@ -331,14 +374,18 @@ __global__ void __launch_bounds__(kRescaleMaxThreads, PC_RESCALE_MINB)
   const bool area = tw > 0 && sw == 2 * tw && sh == 2 * th;
 
   const uint32_t k4 = (uint32_t)lane & 3u;
-  const uint32_t opitch = (uint32_t)CW * 3u;
-  // lanes 4g .. 4g+3 hold the pixels of columns 4c .. 4c+3; three of them store a word each
-  uint8_t* o = dst + ((size_t)img * CH + row_begin) * opitch + (size_t)(x >> 2) * 12 +
-               (size_t)k4 * 4;
-  const bool store_px = x < CW && k4 < 3;
-  const bool store_m = mask != nullptr && x < CW;
-  uint8_t* m = mask + ((size_t)img * CH + row_begin) * CW + x;  // (only dereferenced if store_m)
-  const uint32_t selO = pinned(k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u));
+  RescaleOut<NORM> out;
+  out.opitch = (uint32_t)CW * 3u;
+  out.fplane = (uint32_t)CH * (uint32_t)CW;
+  out.CW = (uint32_t)CW;
+  out.o = static_cast<uint8_t*>(dst_any) + ((size_t)img * CH + row_begin) * out.opitch +
+          (size_t)(x >> 2) * 12 + (size_t)k4 * 4;
+  out.f = static_cast<float*>(dst_any) + ((size_t)img * 3 * CH + row_begin) * CW + x;
+  out.store_px = x < CW && (NORM || k4 < 3);
+  out.store_m = mask != nullptr && x < CW;
+  out.m = mask + ((size_t)img * CH + row_begin) * CW + x;
+  out.selO = pinned(k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u));
+  out.norm = norm;
 
   if (tw == 0 || row_begin >= th || sw == 1) {
     // (uniform) A tile of padding, or a source one pixel wide (no second pixel to make a load
@@ -361,11 +408,7 @@ __global__ void __launch_bounds__(kRescaleMaxThreads, PC_RESCALE_MINB)
           px |= ((((b0 * r0) >> 16) + ((b1 * r1) >> 16) + 2u) >> 2) << (8 * c);
         }
       }
-      const uint32_t nxt = __shfl_down_sync(0xffffffffu, px, 1);
-      if (store_px) *reinterpret_cast<uint32_t*>(o) = __byte_perm(px, nxt, selO);
-      o += opitch;
-      if (store_m) *m = inside ? 1 : 0;
-      m += CW;
+      out.row(px & 0xffu, (px >> 8) & 0xffu, px >> 16, inside ? 1u : 0u);
     }
     return;
   }
@@ -422,18 +465,12 @@ __global__ void __launch_bounds__(kRescaleMaxThreads, PC_RESCALE_MINB)
   const uint32_t mval = x < tw ? 1u : 0u;
   __syncthreads();
   if (x - lane >= tw) {  // (warp-uniform) every column of this warp is padding
-    for (int i = 0; i < rows; ++i) {
-      if (store_px) *reinterpret_cast<uint32_t*>(o) = 0u;
-      o += opitch;
-      if (store_m) *m = 0;
-      m += CW;
-    }
+    for (int i = 0; i < rows; ++i) out.row(0u, 0u, 0u, 0u);
     return;
   }
   const bool pitch4 = (spitch & 3u) == 0u;
-#define PC_RESCALE_GO(A_, P_)                                                                \
-  rescale_column<A_, P_>(image, win, wpair, s_row, rows, o, opitch, store_px, selO, m,       \
-                         (uint32_t)CW, store_m, mval)
+#define PC_RESCALE_GO(A_, P_) \
+  rescale_column<A_, P_, NORM>(image, win, wpair, s_row, rows, out, mval)
   if (area) {
     if (pitch4) PC_RESCALE_GO(true, true);
     else PC_RESCALE_GO(true, false);
@@ -448,28 +485,47 @@ __global__ void __launch_bounds__(kRescaleMaxThreads, PC_RESCALE_MINB)
 
 using namespace pc;
 
-extern "C" int pc_rescale_pad_u8(const uint8_t* d_src, const int64_t* d_src_offset,
-                                 const int32_t* d_src_hw, const int32_t* d_dst_wh,
-                                 uint8_t* d_dst, uint8_t* d_mask, int32_t canvas_w,
-                                 int32_t canvas_h, int32_t channels, int64_t n, void* stream) {
-  PC_REQUIRE(n >= 0, PC_ERR_INVALID_ARGUMENT, "pc_rescale_pad_u8: n < 0");
+// Does q0 = x * (1 / std) corrected by one residual step give the IEEE quotient x / std for all
+// 256 pixel values of every channel?  (As in warp_affine.cu.)
+static bool rescale_norm_fast_ok(RescaleNorm* na) {
+  bool ok = true;
+  for (int c = 0; c < 3; ++c) {
+    const float std = na->std[c], mean = na->mean[c];
+    const float rcp = 1.0f / std;
+    na->rcp[c] = rcp;
+    for (int v = 0; v < 256 && ok; ++v) {
+      const float x = (float)v - mean;
+      const float q0 = x * rcp;
+      const float q = fmaf(fmaf(-q0, std, x), rcp, q0);
+      const float want = x / std;
+      ok = memcmp(&q, &want, sizeof(float)) == 0;
+    }
+  }
+  return ok;
+}
+
+static int rescale_launch(const char* who, const uint8_t* d_src, const int64_t* d_src_offset,
+                          const int32_t* d_src_hw, const int32_t* d_dst_wh, void* d_dst,
+                          uint8_t* d_mask, int32_t canvas_w, int32_t canvas_h, int32_t channels,
+                          const RescaleNorm* norm, int64_t n, void* stream) {
+  PC_REQUIRE(n >= 0, PC_ERR_INVALID_ARGUMENT, "%s: n < 0", who);
   PC_REQUIRE(channels == 3, PC_ERR_UNSUPPORTED,
-             "pc_rescale_pad_u8: %d channels (the pipeline's images are 3-channel uint8)",
-             channels);
+             "%s: %d channels (the pipeline's images are 3-channel uint8)", who, channels);
   PC_REQUIRE(canvas_w >= 1 && canvas_h >= 1 && canvas_w <= 16384 && canvas_h <= 16384,
-             PC_ERR_INVALID_ARGUMENT, "pc_rescale_pad_u8: canvas %d x %d outside [1, 16384]",
-             canvas_w, canvas_h);
+             PC_ERR_INVALID_ARGUMENT, "%s: canvas %d x %d outside [1, 16384]", who, canvas_w,
+             canvas_h);
   if (n == 0) return PC_OK;
   PC_REQUIRE(d_src && d_src_offset && d_src_hw && d_dst_wh && d_dst, PC_ERR_INVALID_ARGUMENT,
-             "pc_rescale_pad_u8: NULL tensor pointer");
+             "%s: NULL tensor pointer", who);
   cudaStream_t st = (cudaStream_t)stream;
-  // The column kernel writes a warp's 32 pixels as 24 aligned words: it needs every row of
-  // the canvas to start on a word boundary.  Any other canvas takes the plain kernel.
-  if (canvas_w % 4 != 0 || (reinterpret_cast<uintptr_t>(d_dst) & 3u) != 0) {
+  // The uint8 column kernel writes a warp's 32 pixels as 24 aligned words: it needs every row
+  // of the canvas to start on a word boundary.  Any other uint8 canvas takes the plain kernel.
+  if (!norm && (canvas_w % 4 != 0 || (reinterpret_cast<uintptr_t>(d_dst) & 3u) != 0)) {
     const int tiles = (canvas_h + kGenericRows - 1) / kGenericRows;
-    PC_REQUIRE(n * tiles < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "pc_rescale_pad_u8: batch too large");
+    PC_REQUIRE(n * tiles < 0x7fffffffLL, PC_ERR_UNSUPPORTED, "%s: batch too large", who);
     rescale_pad_generic_kernel<<<(unsigned)(n * tiles), kGenericThreads, 0, st>>>(
-        d_src, d_src_offset, d_src_hw, d_dst_wh, d_dst, d_mask, canvas_w, canvas_h, tiles);
+        d_src, d_src_offset, d_src_hw, d_dst_wh, static_cast<uint8_t*>(d_dst), d_mask, canvas_w,
+        canvas_h, tiles);
     PC_CUDA(cudaGetLastError());
     return PC_OK;
   }
@@ -478,10 +534,47 @@ extern "C" int pc_rescale_pad_u8(const uint8_t* d_src, const int64_t* d_src_offs
   // columns per CTA: the canvas width split evenly, rounded up to whole warps
   const int threads = (((canvas_w + col_blocks - 1) / col_blocks) + 31) & ~31;
   PC_REQUIRE(n * row_tiles * col_blocks < 0x7fffffffLL, PC_ERR_UNSUPPORTED,
-             "pc_rescale_pad_u8: batch too large");
-  rescale_pad_u8x3_kernel<<<(unsigned)(n * row_tiles * col_blocks), threads, 0, st>>>(
-      d_src, d_src_offset, d_src_hw, d_dst_wh, d_dst, d_mask, canvas_w, canvas_h, col_blocks,
-      row_tiles);
+             "%s: batch too large", who);
+  const unsigned grid = (unsigned)(n * row_tiles * col_blocks);
+  if (norm) {
+    rescale_pad_u8x3_kernel<true><<<grid, threads, 0, st>>>(
+        d_src, d_src_offset, d_src_hw, d_dst_wh, d_dst, d_mask, canvas_w, canvas_h, col_blocks,
+        row_tiles, *norm);
+  } else {
+    RescaleNorm none;
+    memset(&none, 0, sizeof(none));
+    rescale_pad_u8x3_kernel<false><<<grid, threads, 0, st>>>(
+        d_src, d_src_offset, d_src_hw, d_dst_wh, d_dst, d_mask, canvas_w, canvas_h, col_blocks,
+        row_tiles, none);
+  }
   PC_CUDA(cudaGetLastError());
   return PC_OK;
+}
+
+extern "C" int pc_rescale_pad_u8(const uint8_t* d_src, const int64_t* d_src_offset,
+                                 const int32_t* d_src_hw, const int32_t* d_dst_wh,
+                                 uint8_t* d_dst, uint8_t* d_mask, int32_t canvas_w,
+                                 int32_t canvas_h, int32_t channels, int64_t n, void* stream) {
+  return rescale_launch("pc_rescale_pad_u8", d_src, d_src_offset, d_src_hw, d_dst_wh, d_dst,
+                        d_mask, canvas_w, canvas_h, channels, nullptr, n, stream);
+}
+
+extern "C" int pc_rescale_pad_u8_norm_chw(const uint8_t* d_src, const int64_t* d_src_offset,
+                                          const int32_t* d_src_hw, const int32_t* d_dst_wh,
+                                          float* d_dst, uint8_t* d_mask,
+                                          const pc_warp_norm_params* params, int64_t n,
+                                          void* stream) {
+  PC_REQUIRE(params != nullptr, PC_ERR_INVALID_ARGUMENT,
+             "pc_rescale_pad_u8_norm_chw: params is NULL");
+  RescaleNorm na;
+  for (int c = 0; c < 3; ++c) {
+    na.mean[c] = params->mean[c];
+    na.std[c] = params->std[c];
+    PC_REQUIRE(params->std[c] != 0.f, PC_ERR_INVALID_ARGUMENT,
+               "pc_rescale_pad_u8_norm_chw: std[%d] is 0", c);
+  }
+  na.fast = rescale_norm_fast_ok(&na) ? 1 : 0;
+  return rescale_launch("pc_rescale_pad_u8_norm_chw", d_src, d_src_offset, d_src_hw, d_dst_wh,
+                        d_dst, d_mask, params->dst_w, params->dst_h, params->channels, &na, n,
+                        stream);
 }

@@ -359,7 +359,8 @@ class BottomUpRescale(BottomUpTransform):
         return dict(image=canvas[0].cpu().numpy(), center=meta["center"][0],
                     scale=meta["scale"][0], image_shape=(tw, th))
 
-    def rescale_pad_batch(self, images, canvas_wh=None, with_mask: bool = True):
+    def rescale_pad_batch(self, images, canvas_wh=None, with_mask: bool = True,
+                          normalize_mean=None, normalize_std=None):
         """images: a list of uint8 HWC arrays / tensors (any sizes), or one u8 tensor
         [N, H, W, 3] -> (canvas u8 [N, CH, CW, 3] CUDA, mask u8 [N, CH, CW] or None, meta) with
         meta = dict(center int64 [N,2], scale f64 [N,2], image_shape int64 [N,2]) as numpy,
@@ -367,7 +368,11 @@ class BottomUpRescale(BottomUpTransform):
 
         ``canvas_wh`` defaults to ``max_image_size`` (landscape box); portrait images need the
         turned box, so a mixed batch needs a canvas that holds both (the reference pads each
-        image to its own orientation; a batch tensor has one shape)."""
+        image to its own orientation; a batch tensor has one shape).
+
+        With ``normalize_mean`` / ``normalize_std`` (the ``create_pipeline`` arguments, in [0, 1]
+        units: data_factory.py:78-79) the pipeline's Normalize + HWC2CHW step is fused in and
+        the canvas comes back as float32 [N, 3, CH, CW] (padding = (0 - mean) / std)."""
         cfg = self._transform_cfg
         dev = _dev()
         if isinstance(images, torch.Tensor) and images.dim() == 4:
@@ -396,8 +401,13 @@ class BottomUpRescale(BottomUpTransform):
             blob[off:off + w * h * 3].copy_(t.reshape(-1), non_blocking=True)
         src_hw = torch.tensor([[h, w] for (w, h) in sizes], dtype=torch.int32).reshape(-1, 2)
         dst_wh = torch.tensor(targets, dtype=torch.int32).reshape(-1, 2)
+        mean = std = None
+        if normalize_mean is not None:
+            # np.array(mean) * 255.0 in float64, handed to Normalize as float32
+            mean = (np.array(normalize_mean) * 255.0).tolist()
+            std = (np.array(normalize_std) * 255.0).tolist()
         canvas, mask = codec.rescale_pad(blob, torch.tensor(offs, dtype=torch.int64), src_hw,
-                                         dst_wh, (cw, ch), with_mask=with_mask)
+                                         dst_wh, (cw, ch), with_mask=with_mask, mean=mean, std=std)
         pixel_std = cfg["pixel_std"]
         meta = dict(center=np.array([[round(w / 2), round(h / 2)] for (w, h) in sizes]),
                     scale=np.array([[w / pixel_std, h / pixel_std] for (w, h) in sizes]),

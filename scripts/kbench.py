@@ -252,6 +252,11 @@ def main():
         med, mn = timeit(fn, args.iters)
         report("rescale + pad + mask 480x640 -> 683x512 in 832x512 (256 images)", n, "images",
                sh * sw * 3 + cw * ch * 4, med, mn)
+        fn = lambda: codec.rescale_pad(imgs, off, hw, wh, (cw, ch), mean=[123.675, 116.28, 103.53],  # noqa: E731
+                                       std=[58.395, 57.12, 57.375])
+        med, mn = timeit(fn, args.iters)
+        report("... + normalize + CHW f32 (256 images)", n, "images",
+               sh * sw * 3 + cw * ch * 13, med, mn)
         try:   # the reference's own two calls on one host core, beside it
             import time
 

@@ -42,7 +42,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.pc_version() == 102
+    assert lib.pc_version() == 103
     assert isinstance(lib.pc_last_error(), bytes)
 
 

@@ -120,3 +120,32 @@ def test_rescale_pad_argument_errors(cuda_device):
         t.rescale_pad_batch([np.zeros((8, 8, 1), np.uint8)])
     out, mask, meta = t.rescale_pad_batch([], canvas_wh=(8, 8))
     assert out.shape == (0, 8, 8, 3) and mask.shape == (0, 8, 8)
+
+
+@pytest.mark.parametrize("stats", ["imagenet", "other"])
+def test_rescale_pad_normalized_chw(cuda_device, golden, stats):
+    """Normalize + HWC2CHW fused in: equal to (float32(canvas) - mean) / std on the bit-exact
+    uint8 canvas of the reference, padding included (Normalize sees the padded zeros too)."""
+    g = golden("bottomup_rescale_ref.npz")
+    t = mp.create_transform("bottomup_rescale", is_train=False, config=CFG)
+    if stats == "imagenet":
+        mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    else:
+        mean, std = [0.31, 0.5, 0.123], [0.3, 0.11, 0.27]     # (the division path)
+    ids = [ci for ci, (h, w) in enumerate(ggb.RESCALE_CASES) if w >= h]
+    imgs = [ggb.rescale_image(100 + ci, *ggb.RESCALE_CASES[ci]) for ci in ids]
+    for canvas in (tuple(ggb.RESCALE_MAX), (105, 67)):
+        out, mask, _ = t.rescale_pad_batch(imgs, canvas_wh=canvas, normalize_mean=mean,
+                                           normalize_std=std)
+        out, mask = out.cpu().numpy(), mask.cpu().numpy()
+        m32 = (np.array(mean) * 255.0).astype(np.float32)
+        s32 = (np.array(std) * 255.0).astype(np.float32)
+        for j, ci in enumerate(ids):
+            ref = g[f"padded_{ci}"]
+            u8 = np.zeros((canvas[1], canvas[0], 3), np.uint8)
+            u8[:ref.shape[0], :ref.shape[1]] = ref
+            want = ((u8.astype(np.float32) - m32) / s32).transpose(2, 0, 1)
+            assert out[j].dtype == np.float32 and np.array_equal(out[j], want), (stats, canvas, ci)
+            wm = np.zeros((canvas[1], canvas[0]), np.uint8)
+            wm[:ref.shape[0], :ref.shape[1]] = g[f"mask_{ci}"]
+            assert np.array_equal(mask[j], wm)
