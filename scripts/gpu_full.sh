@@ -15,7 +15,7 @@ for k,v in (d.get('configs') or {}).items(): print(k, v['ms_per_step'], v['value
 "; tail -3 $out/${tag}_bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 3 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
 echo "bench ref exit $?"; cut -c1-300 $out/${tag}_bench_reference.json
-for sec in decode encode warp bottomup bu_encode refine nms; do
+for sec in decode encode warp bottomup bu_encode refine nms rescale; do
   timeout 240 python scripts/kbench.py --iters 10 --only $sec,group >> $out/${tag}_kbench.log 2>&1 || echo "kbench $sec failed rc=$?" >> $out/${tag}_kbench.log
 done
 grep -v "exact-pass" $out/${tag}_kbench.log
