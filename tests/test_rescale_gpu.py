@@ -149,3 +149,22 @@ def test_rescale_pad_normalized_chw(cuda_device, golden, stats):
             wm = np.zeros((canvas[1], canvas[0]), np.uint8)
             wm[:ref.shape[0], :ref.shape[1]] = g[f"mask_{ci}"]
             assert np.array_equal(mask[j], wm)
+
+
+def test_rescale_pad_camera_sizes_match_oracle(cuda_device):
+    """Camera-sized sources into the recipe's canvas: 2.3 x and 3.6 x reductions (no source row
+    is shared between output rows), the exact 2 x 2 reduction, a row pitch that is not a
+    multiple of 4 bytes, a portrait image in the turned canvas."""
+    big = dict(CFG, max_image_size=[832, 512])
+    t = mp.create_transform("bottomup_rescale", is_train=False, config=big)
+    rng = np.random.RandomState(9)
+    for (h, w), canvas in (((1080, 1920), (832, 512)), ((1024, 1664), (832, 512)),
+                           ((1333, 2001), (832, 512)), ((3000, 2000), (512, 832))):
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        out, mask, meta = t.rescale_pad_batch([img], canvas_wh=canvas)
+        tw, th = R.rescale_size((w, h), (832, 512))
+        assert tuple(meta["image_shape"][0]) == (tw, th)
+        want = np.zeros((canvas[1], canvas[0], 3), np.uint8)
+        want[:th, :tw] = R.resize_linear_u8(img, (tw, th))
+        assert np.array_equal(out[0].cpu().numpy(), want), (h, w)
+        assert int(mask[0].sum()) == tw * th
