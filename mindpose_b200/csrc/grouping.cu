@@ -454,43 +454,78 @@ __global__ void __launch_bounds__(32)
       s_ref[g] = __fdiv_rn(np_sum_f32(s_tags + g * K, nt, 1), (float)nt);
     }
     __syncwarp();
-    // ---- cost matrix: |tag - ref| (sqrt of the float32 square), rounded; 1e10 padding
     const int nc = max(ng, na);
-    if (nc <= 64) {  // lane = column: no index division, conflict-free stores
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int c = lane + 32 * s;
-        if (c < nc) {
-          const float ref = c < ng ? s_ref[c] : 0.f;
-          for (int r = 0; r < na; ++r) {
-            float cost = 1e10f;
-            if (c < ng) {
-              cost = tag_norm(__fsub_rn(s_det[3 * kMaxDet + r], ref));
-              if (a.use_rounded_norm) cost = rintf(cost);
-            }
-            s_cost[r * kG + c] = cost;
-          }
+    // ---- Quick solve.  If every detection's cheapest group is cheapest STRICTLY and no two
+    // detections share it, that assignment is the unique optimum (any other one pays strictly
+    // more in some row and never less in the others), so it is what scipy returns -- no
+    // solver run, no cost matrix.  Well separated tags, the normal case, end here; ties (tags
+    // that round to the same distance) fall through to the solver.  Only without padded
+    // columns (na <= ng): next to 1e10 entries the solver's float64 sums no longer resolve
+    // small gaps, and its answer is then the one to reproduce, optimal or not.
+    bool solved = false;
+    if (nc <= 32 && na <= ng) {
+      const float ref = lane < ng ? s_ref[lane] : 0.f;
+      unsigned taken = 0u;
+      int mine = -1;
+      bool ok = true;
+      for (int r = 0; r < na; ++r) {
+        float cost = tag_norm(__fsub_rn(s_det[3 * kMaxDet + r], ref));
+        if (a.use_rounded_norm) cost = rintf(cost);
+        // cost >= +0: integer order of the bits == float order
+        const int key = lane < ng ? __float_as_int(cost) : 0x7fffffff;
+        const int mn = warp_min_i32(key);
+        const unsigned at = __ballot_sync(0xffffffffu, key == mn);
+        if ((at & (at - 1u)) != 0u || (at & taken) != 0u) {  // (uniform) a tie, or a shared group
+          ok = false;
+          break;
         }
+        taken |= at;
+        if (lane == r) mine = __ffs(at) - 1;
       }
-    } else {
-      for (int e = lane; e < na * nc; e += 32) {
-        const int r = e / nc, c = e - r * nc;
-        float cost = 1e10f;
-        if (c < ng) {
-          cost = tag_norm(__fsub_rn(s_det[3 * kMaxDet + r], s_ref[c]));
-          if (a.use_rounded_norm) cost = rintf(cost);
-        }
-        s_cost[r * kG + c] = cost;
+      if (ok) {
+        if (lane < na) s_col4row[lane] = mine;
+        __syncwarp();
+        solved = true;
       }
     }
-    __syncwarp();
-    PC_PROF_MARK(1);
-    if (nc <= 32)
-      lsap_warp_regs<1>(s_cost, kG, na, nc, s_col4row, lane);
-    else if (nc <= 64)
-      lsap_warp_regs<2>(s_cost, kG, na, nc, s_col4row, lane);
-    else
-      lsap_warp(s_cost, kG, na, nc, st, lane);
+    if (!solved) {
+      // ---- cost matrix: |tag - ref| (sqrt of the float32 square), rounded; 1e10 padding
+      if (nc <= 64) {  // lane = column: no index division, conflict-free stores
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int c = lane + 32 * s;
+          if (c < nc) {
+            const float ref = c < ng ? s_ref[c] : 0.f;
+            for (int r = 0; r < na; ++r) {
+              float cost = 1e10f;
+              if (c < ng) {
+                cost = tag_norm(__fsub_rn(s_det[3 * kMaxDet + r], ref));
+                if (a.use_rounded_norm) cost = rintf(cost);
+              }
+              s_cost[r * kG + c] = cost;
+            }
+          }
+        }
+      } else {
+        for (int e = lane; e < na * nc; e += 32) {
+          const int r = e / nc, c = e - r * nc;
+          float cost = 1e10f;
+          if (c < ng) {
+            cost = tag_norm(__fsub_rn(s_det[3 * kMaxDet + r], s_ref[c]));
+            if (a.use_rounded_norm) cost = rintf(cost);
+          }
+          s_cost[r * kG + c] = cost;
+        }
+      }
+      __syncwarp();
+      PC_PROF_MARK(1);
+      if (nc <= 32)
+        lsap_warp_regs<1>(s_cost, kG, na, nc, s_col4row, lane);
+      else if (nc <= 64)
+        lsap_warp_regs<2>(s_cost, kG, na, nc, s_col4row, lane);
+      else
+        lsap_warp(s_cost, kG, na, nc, st, lane);
+    }
     PC_PROF_MARK(2);
 
     // ---- apply the pairs.  The reference walks them in row order; an accepted pair writes

@@ -40,8 +40,20 @@ def main():
     lib = _lib.load()
     prof = getattr(lib, "pc_group_profile", None)
     print("library:", _lib.LIB_PATH, "(profile build)" if prof else "")
-    for people in (8, 20):
-        val_k, tag_k, ind_k = inputs(dev, people)
+    for people in (8, 20, -12):
+        if people < 0:
+            # clean tags: 12 people, every joint detected, tags 3 apart with little noise (no
+            # fragments) -- every joint's assignment has a strict, distinct minimum per row
+            g = torch.Generator(device=dev).manual_seed(5)
+            n, m, p = 64, 30, -people
+            val_k = torch.zeros(n, K, m, device=dev)
+            tag_k = torch.zeros(n, K, m, 1, device=dev)
+            ind_k = torch.randint(0, 256, (n, K, m, 2), device=dev, generator=g).float()
+            val_k[:, :, :p] = 0.9 - 0.05 * torch.arange(p, device=dev)[None, None]
+            tag_k[:, :, :p, 0] = 3.0 * torch.arange(p, device=dev)[None, None] + \
+                0.1 * torch.randn(n, K, p, device=dev, generator=g)
+        else:
+            val_k, tag_k, ind_k = inputs(dev, people)
         order = synth.COCO_JOINT_ORDER
         for _ in range(5):
             _, num, _ = bottomup.group_by_tag(val_k, tag_k, ind_k, order)
