@@ -63,3 +63,36 @@ def test_python_round_is_half_to_even_like_the_reference():
     assert transforms._rescale_size((101, 50), (104, 64)) == R.rescale_size((101, 50), (104, 64))
     for w, h in [(3, 2), (5, 2), (37, 33), (640, 427), (427, 640), (500, 375)]:
         assert transforms._rescale_size((w, h), (832, 512)) == R.rescale_size((w, h), (832, 512))
+
+
+@pytest.mark.needs_reference
+def test_sizes_and_images_against_live_reference():
+    """In the build container: the unmodified BottomUpRescale / BottomUpResize / BottomUpPad for
+    many image sizes (target sizes, centres, scales of the product's host arithmetic) and a few
+    images through the oracle's arithmetic."""
+    from oracle import ref_loader
+
+    ns = ref_loader.load()
+    cfg = dict(CFG, max_image_size=[832, 512])
+    rescale = ns.bottomup.BottomUpRescale(is_train=False, config=cfg)
+    resize = ns.bottomup.BottomUpResize(is_train=False, config=cfg, size=512, base_length=64)
+    mine = transforms.BottomUpResize(is_train=False, config=cfg, size=512, base_length=64)
+    rng = np.random.RandomState(1)
+    sizes = [(640, 480), (480, 640), (500, 375), (333, 500), (1, 1), (832, 512), (1664, 1024)]
+    sizes += [(int(rng.randint(1, 2000)), int(rng.randint(1, 2000))) for _ in range(300)]
+    for w, h in sizes:
+        assert transforms._rescale_size((w, h), cfg["max_image_size"]) == \
+            rescale._get_new_size([w, h], cfg["max_image_size"]), (w, h)
+        want = resize._get_new_size([w, h], 512, base_length=64, pixel_std=200.0)
+        got = mine._get_new_size((w, h), 200.0)
+        assert tuple(got[0]) == tuple(want[0]), (w, h)
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), (w, h)
+    pad = ns.bottomup.BottomUpPad(is_train=False, config=cfg)
+    for h, w in [(97, 131), (240, 427), (600, 400)]:
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        ref = rescale.transform(dict(image=img.copy()))
+        got = R.rescale(img, cfg["max_image_size"])
+        assert np.array_equal(got["image"], ref["image"]), (h, w)
+        assert np.array_equal(got["center"], ref["center"]) and np.array_equal(got["scale"], ref["scale"])
+        p_ref, p_got = pad.transform(dict(image=ref["image"])), R.pad(got["image"], cfg["max_image_size"])
+        assert np.array_equal(p_got["image"], p_ref["image"]) and np.array_equal(p_got["mask"], p_ref["mask"])
