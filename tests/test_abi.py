@@ -137,3 +137,45 @@ def test_graft_entry_build_runs():
     import __graft_entry__ as entry
 
     entry.build()
+
+
+def _prototypes():
+    """name -> list of parameter declarations, parsed from the header's prototypes."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|const char\s*\*)\s+(pc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        out[m.group(1)] = [] if params == ["void"] else params
+    return out
+
+
+def test_ctypes_signatures_match_the_prototypes():
+    """Same number of arguments, and the same kind (pointer / 32-bit / 64-bit / float) in every
+    position, as the header declares -- an argument added on one side only would otherwise
+    shift everything after it silently."""
+    from mindpose_b200 import _lib
+
+    protos = _prototypes()
+    assert len(protos) >= 20
+    kinds = {ctypes.c_int32: "i32", ctypes.c_int: "i32", ctypes.c_uint32: "i32",
+             ctypes.c_int64: "i64", ctypes.c_float: "f32", ctypes.c_double: "f64"}
+    for name, params in protos.items():
+        assert name in _lib.SIGNATURES, name
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(argtypes) == len(params), (name, len(argtypes), params)
+        for decl, at in zip(params, argtypes):
+            if "*" in decl:
+                want = "ptr"
+            elif re.search(r"\b(int64_t|long long)\b", decl):
+                want = "i64"
+            elif re.search(r"\bfloat\b", decl):
+                want = "f32"
+            elif re.search(r"\bdouble\b", decl):
+                want = "f64"
+            elif re.search(r"\b(int32_t|uint32_t|int)\b", decl):
+                want = "i32"
+            else:
+                raise AssertionError(f"{name}: cannot classify `{decl}`")
+            got = kinds.get(at, "ptr")
+            assert got == want, (name, decl, at)
