@@ -76,6 +76,40 @@ def test_struct_sizes_match_header(tmp_path):
         assert ctypes.sizeof(structs[name]) == int(size), name
 
 
+def test_struct_field_offsets_match_header(tmp_path):
+    """Every field of every ctypes mirror sits at the offset the header gives the field of the
+    same name (two swapped fields of one type would keep the size)."""
+    from mindpose_b200 import _lib
+
+    structs = {
+        "pc_box_params": _lib.BoxParams,
+        "pc_affine_params": _lib.AffineParams,
+        "pc_warp_params": _lib.WarpParams,
+        "pc_encode_params": _lib.EncodeParams,
+        "pc_warp_norm_params": _lib.WarpNormParams,
+        "pc_topdown_decode_params": _lib.TopDownDecodeParams,
+        "pc_bottomup_decode_params": _lib.BottomUpDecodeParams,
+        "pc_bottomup_encode_params": _lib.BottomUpEncodeParams,
+        "pc_group_params": _lib.GroupParams,
+        "pc_refine_params": _lib.RefineParams,
+        "pc_oks_nms_params": _lib.OksNmsParams,
+        "pc_affine_host_params": _lib.AffineHostParams,
+    }
+    lines = []
+    for cname, cls in structs.items():
+        for field in cls._fields_:
+            lines.append(f'  printf("{cname} {field[0]} %zu\\n", offsetof({cname}, {field[0]}));')
+    src = tmp_path / "offsets.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "posecodec.h"\n'
+                   'int main(void) {\n' + "\n".join(lines) + "\n  return 0;\n}\n")
+    exe = tmp_path / "offsets"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    for line in out.strip().splitlines():
+        cname, field, off = line.split()
+        assert getattr(structs[cname], field).offset == int(off), (cname, field)
+
+
 def test_argument_errors_raise_value_error_without_gpu(lib):
     """Validation happens before any CUDA call, so it is checkable on CPU."""
     from mindpose_b200 import _lib
