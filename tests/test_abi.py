@@ -93,6 +93,7 @@ def test_struct_field_offsets_match_header(tmp_path):
         "pc_group_params": _lib.GroupParams,
         "pc_refine_params": _lib.RefineParams,
         "pc_oks_nms_params": _lib.OksNmsParams,
+        "pc_gather_target": _lib.GatherTarget,
         "pc_affine_host_params": _lib.AffineHostParams,
     }
     lines = []
